@@ -1,0 +1,101 @@
+"""Seeded synthetic weights and inputs for the TTS tail.
+
+There is no network on the build or GPU boxes, so the HuggingFace checkpoints the
+reference loads (``microsoft/speecht5_hifigan``, ``sobomax/speecht5-rt.post_vocoder.v2``,
+/root/reference/HelloSippyTTSRT/HelloSippyRTPipe.py:171-176) are replaced by random
+weights with the same state_dict keys and shapes.  transformers' default init
+(std 0.01) gives |audio| ~ 2e-5 and makes every tolerance vacuous, so the weights are
+drawn at ~1/sqrt(fan_in) instead, which yields O(1) audio.
+
+State-dict layouts follow the reference modules exactly:
+  * HiFiGAN : transformers SpeechT5HifiGan (modeling_speecht5.py:2974-3010)
+  * chunker : AmendmentNetwork1 (/root/reference/HelloSippyTTSRT/HelloSippyRT.py:202-217)
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+HIFIGAN_SEED = 1234
+CHUNKER_SEED = 4321
+MEL_SEED = 7
+
+UPSAMPLE_INITIAL_CHANNEL = 512
+UPSAMPLE_RATES = (4, 4, 4, 4)
+UPSAMPLE_KERNELS = (8, 8, 8, 8)
+RESBLOCK_KERNELS = (3, 7, 11)
+RESBLOCK_DILATIONS = (1, 3, 5)
+NUM_MELS = 80
+
+
+def _conv_w(g, cout, cin, k, fan_in=None):
+    fan_in = cin * k if fan_in is None else fan_in
+    return torch.randn(cout, cin, k, generator=g) / math.sqrt(fan_in)
+
+
+def _bias(g, n):
+    return torch.randn(n, generator=g) * 0.01
+
+
+def hifigan_state_dict(seed: int = HIFIGAN_SEED) -> Dict[str, torch.Tensor]:
+    """Random SpeechT5HifiGan weights (default SpeechT5HifiGanConfig), fp32, CPU."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    sd["mean"] = torch.randn(NUM_MELS, generator=g) * 0.5 - 4.0
+    sd["scale"] = torch.rand(NUM_MELS, generator=g) * 1.5 + 1.0
+    sd["conv_pre.weight"] = _conv_w(g, UPSAMPLE_INITIAL_CHANNEL, NUM_MELS, 7)
+    sd["conv_pre.bias"] = _bias(g, UPSAMPLE_INITIAL_CHANNEL)
+    ch = UPSAMPLE_INITIAL_CHANNEL
+    for i, (r, k) in enumerate(zip(UPSAMPLE_RATES, UPSAMPLE_KERNELS)):
+        cin, cout = ch, ch // 2
+        # ConvTranspose1d weight is (in, out, k); each output sees k/stride taps per input channel
+        w = torch.randn(cin, cout, k, generator=g) / math.sqrt(cin * k / r)
+        sd[f"upsampler.{i}.weight"] = w
+        sd[f"upsampler.{i}.bias"] = _bias(g, cout)
+        for j, rk in enumerate(RESBLOCK_KERNELS):
+            n = i * len(RESBLOCK_KERNELS) + j
+            for d in range(len(RESBLOCK_DILATIONS)):
+                # He gain on conv1 so the residual branches carry about as much energy as the trunk
+                sd[f"resblocks.{n}.convs1.{d}.weight"] = _conv_w(g, cout, cout, rk) * math.sqrt(2.0)
+                sd[f"resblocks.{n}.convs1.{d}.bias"] = _bias(g, cout)
+                sd[f"resblocks.{n}.convs2.{d}.weight"] = _conv_w(g, cout, cout, rk)
+                sd[f"resblocks.{n}.convs2.{d}.bias"] = _bias(g, cout)
+        ch = cout
+    sd["conv_post.weight"] = _conv_w(g, 1, ch, 7) * 0.5
+    sd["conv_post.bias"] = _bias(g, 1)
+    return sd
+
+
+def chunker_state_dict(seed: int = CHUNKER_SEED) -> Dict[str, torch.Tensor]:
+    """Random AmendmentNetwork1 weights, fp32, CPU."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    sd["conv_pre_m.weight"] = _conv_w(g, 32, 80, 3)
+    sd["conv_pre_m.bias"] = _bias(g, 32)
+    sd["conv_pre_a.weight"] = _conv_w(g, 160, 256, 3, fan_in=256 * 3 * 0.05)  # audio is ~0.2 rms
+    sd["conv_pre_a.bias"] = _bias(g, 160)
+    sd["upsampler.0.weight"] = torch.randn(192, 128, 8, generator=g) / math.sqrt(192 * 2)
+    sd["upsampler.0.bias"] = _bias(g, 128)
+    sd["upsampler.1.weight"] = torch.randn(128, 64, 8, generator=g) / math.sqrt(128 * 2)
+    sd["upsampler.1.bias"] = _bias(g, 64)
+    sd["resblock.conv1.weight"] = _conv_w(g, 64, 64, 3)
+    sd["resblock.conv1.bias"] = _bias(g, 64)
+    sd["resblock.conv2.weight"] = _conv_w(g, 64, 64, 3)
+    sd["resblock.conv2.bias"] = _bias(g, 64)
+    sd["post_conv.weight"] = _conv_w(g, 256, 64, 8)
+    sd["post_conv.bias"] = _bias(g, 256) + 1.0  # gains centred near 1 like a trained seam-smoother
+    return sd
+
+
+def synth_mel(batch: int, nframes: int, seed: int = MEL_SEED) -> torch.Tensor:
+    """Log-mel-like input: randn*2-4, shape (batch, nframes, 80), fp32, CPU."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, nframes, NUM_MELS, generator=g) * 2.0 - 4.0
+
+
+def synth_audio(batch: int, nsamples: int, seed: int = 20240101) -> torch.Tensor:
+    """U(-0.9, 0.9) audio used by the codec sweeps (vector G2)."""
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(batch, nsamples, generator=g) * 2 - 1) * 0.9
