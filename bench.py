@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 TTS tail (mel chunks -> HiFiGAN -> chunker -> 16k->8k -> G.711).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Metric (BASELINE.json): concurrent real-time 8 kHz G.711 TTS streams per job at RTF <= 1
+= seconds of audio produced per second of device time.  A step is one reference `infer()` tail
+(HelloSippyRTPipe.py:231-240) over every session of the batch: 32 new mel frames -> 4 windows of 12 frames
+-> 8,192 samples @16 kHz -> 4,096 G.711 bytes (0.512 s of audio) per session.
+
+Prints ONE JSON line on rank 0.  `value` is timed with inputs resident in HBM; `e2e` goes through the
+host-buffer C-ABI entry (pinned H2D of the mel, D2H of the G.711 bytes, inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+AUDIO_S_PER_FRAME = 256 / 16000.0
+# algorithmic work per 12-frame window
+FLOP_PER_WINDOW_TC = 12 * 2 * (4 * 33.030144e6 + 4 * 1.048576e6)     # upsamplers + ResBlocks, the tcgen05 kernels
+FLOP_PER_WINDOW_ALL = 12 * 273.318e6 + 25.68e6 + 0.057e6 * 4
+CODEC_BYTES_PER_OUT = 9.0                                            # 2 fp32 in + 1 byte out per 8 kHz sample
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], tf_sustained=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], source="measured")
+    return dict(hbm_gbs=6650.0, tf_sustained=1400.0, tf_burst=1590.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower() == "active" for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_tail_fn():
+    """The reference's own CPU arithmetic for the path: transformers SpeechT5HifiGan (the third-party module the
+    reference calls) when importable, the oracle's restatements for AmendmentNetwork1 / Resample / G711Codec.encode
+    (their sources live in /root/reference, which does not exist on the GPU box)."""
+    import torch
+    from infernos_b200 import synth
+    from oracle import codec as ocodec
+    from oracle import tail as otail
+    vsd, csd = synth.hifigan_state_dict(), synth.chunker_state_dict()
+    kind = "port"
+    try:
+        from transformers import SpeechT5HifiGan, SpeechT5HifiGanConfig
+        voc = SpeechT5HifiGan(SpeechT5HifiGanConfig())
+        voc.load_state_dict(vsd, strict=True)
+        voc.eval()
+        vocoder = lambda win: voc(win)
+        desc = "transformers.SpeechT5HifiGan + oracle AmendmentNetwork1/Resample/G.711 restatements"
+    except Exception:
+        vocoder = lambda win: otail.hifigan_forward(vsd, win)
+        desc = "oracle torch restatement of HiFiGAN/AmendmentNetwork1/Resample/G.711"
+
+    def step(pre, mel):
+        with torch.no_grad():
+            B = mel.size(0)
+            win, new_pre = otail.build_windows(pre, mel)
+            audio = vocoder(win)
+            audio = otail.chunker_forward(csd, win, audio)
+            audio = torch.cat(audio.split(B, dim=0), dim=1)
+            audio = otail.resample(audio, 16000, 8000)
+            by = ocodec.encode_f32(audio.numpy(), 0)
+        return new_pre, by
+
+    return step, kind, desc
+
+
+def run_cpu(sessions: int, steps: int, warmup: int, frames: int = 32):
+    import torch
+    from infernos_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, kind, desc = cpu_tail_fn()
+    mel = synth.synth_mel(sessions, frames, seed=7)
+    pre = torch.zeros(sessions, 4, 80)
+    for _ in range(warmup):
+        pre, _ = step(pre, mel)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pre, _ = step(pre, mel)
+    dt = time.perf_counter() - t0
+    streams = sessions * frames * AUDIO_S_PER_FRAME * steps / dt
+    return dict(value=streams, ms_per_step=dt / steps * 1e3, kind=kind, cores=torch.get_num_threads(),
+                sample=f"{sessions} sessions x {frames} mel frames per step, {steps} steps, fp32, {desc}")
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    sessions = args.ref_sessions
+    r = run_cpu(sessions, args.steps, min(args.warmup, 1) if args.warmup else 0)
+    out = {
+        "impl": "reference", "metric": "real-time G.711 TTS streams (RTF<=1)", "value": round(r["value"], 3), "unit": "streams",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(r["ms_per_step"], 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"TTS tail (HiFiGAN+chunker+16k->8k+G.711), {sessions} sessions x 32-frame calls on host CPU cores",
+                   "sessions_per_step": sessions, "frames_per_call": 32},
+        "cpu_baseline": {"value": round(r["value"], 3), "unit": "streams", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": round(r["value"], 3), "unit": "streams", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def main_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from infernos_b200 import synth
+    from infernos_b200.engine import TTSTail, kernel_launch_count
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S, F = args.sessions, args.frames
+    nwin = F // 8
+    max_windows = min(S * nwin, args.max_windows)
+    tail = TTSTail(dev, synth.hifigan_state_dict(), synth.chunker_state_dict(), mode=args.mode, max_sessions=S, max_windows=max_windows)
+    mel_h = synth.synth_mel(S, F, seed=7 + rank).pin_memory()
+    slots_h = torch.arange(S, dtype=torch.int32).pin_memory()
+    g_h = torch.empty(S, F * 128, dtype=torch.uint8).pin_memory()
+    mel_d, slots_d = mel_h.to(dev), slots_h.to(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        tail.tail(slots_d, mel_d, want_audio=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        tail.tail(slots_d, mel_d, want_audio=False)
+    e1.record()
+    barrier()
+    launches = kernel_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    audio_s = S * world * F * AUDIO_S_PER_FRAME * args.steps
+    value = audio_s / (ms_total / 1e3)
+
+    # ---- end-to-end timing through the host-buffer entry ------------------------------------------
+    for _ in range(min(args.warmup, 3)):
+        tail.tail_host(slots_h, mel_h, g_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tail.tail_host(slots_h, mel_h, g_h)
+    torch.cuda.synchronize(dev)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    barrier()
+    e2e_value = audio_s / (e2e_ms / 1e3)
+
+    # ---- per-kernel-class timing for the roofline (separate pass, events around every launch) --------
+    tail.profile_begin()
+    psteps = max(1, min(args.steps, 3))
+    for _ in range(psteps):
+        tail.tail(slots_d, mel_d, want_audio=False)
+    ms_cls, n_cls = tail.profile_end()
+    peaks = load_peaks()
+    W_step = S * nwin
+    tc_ms = ms_cls["conv_tc"] if args.mode == "bf16" else ms_cls["conv_f32"]
+    tc_n = n_cls["conv_tc"] if args.mode == "bf16" else n_cls["conv_f32"]
+    roofline = codec_roof = None
+    if tc_ms > 0:
+        tf = FLOP_PER_WINDOW_TC * W_step * psteps / (tc_ms / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "k_conv_umma (76 launches per sub-batch: 4 upsamplers + 72 ResBlock convs)" if args.mode == "bf16" else "k_conv_simt",
+                    "achieved": round(tf, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(tf / peaks["tf_sustained"], 4),
+                    "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)", "traffic": None,
+                    "launches": tc_n, "avg_launch_ms": round(tc_ms / max(tc_n, 1), 4), "share_of_step": round(tc_ms / max(sum(ms_cls.values()), 1e-9), 4)}
+    if ms_cls["resample_g711"] > 0:
+        gbs = CODEC_BYTES_PER_OUT * S * F * 128 * psteps / (ms_cls["resample_g711"] / 1e3) / 1e9
+        codec_roof = {"bound": "hbm", "kernel": "k_resample_2to1_vec (fused 16k->8k + G.711)", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"],
+                      "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 4), "peak_source": peaks["source"], "traffic": None,
+                      "avg_launch_ms": round(ms_cls["resample_g711"] / max(n_cls["resample_g711"], 1), 4)}
+
+    # ---- control-plane stats gather (the only collective; NCCL) -----------------------------------
+    stats = torch.tensor([float(S), float(args.steps), float(S * F * 128 * args.steps), float(launches)], device=dev, dtype=torch.float64)
+    if world > 1:
+        allstats = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(allstats, stats)
+    else:
+        allstats = [stats]
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_cpu(args.ref_sessions, 3, 1)
+        cpu = {"value": round(r["value"], 3), "unit": "streams", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+
+    if rank == 0:
+        out = {
+            "metric": "real-time G.711 TTS streams (RTF<=1)", "value": round(value, 1), "unit": "streams", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"batched vocoder+chunker+resample+G.711, {S} concurrent sessions per GPU, {F}-frame calls "
+                                   f"({nwin} windows of 12 frames, 8 emitted each), {args.mode} conv path",
+                       "sessions_per_gpu": S, "frames_per_call": F, "mode": args.mode, "sharding": "sessions block-partitioned, no data-plane collective",
+                       "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush",
+                       "vocoder_msamples_per_s": round(S * world * F * 256 * args.steps / (ms_total / 1e3) / 1e6, 1)},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 1), "unit": "streams", "h2d_bytes_per_step": int(mel_h.numel() * 4 + slots_h.numel() * 4) * world,
+                    "d2h_bytes_per_step": int(g_h.numel()) * world, "ms_per_step": round(e2e_ms / args.steps, 3)},
+            "gpu_launches": int(sum(float(s[3]) for s in allstats)),
+            "roofline": roofline, "roofline_codec": codec_roof,
+            "kernel_ms_per_step": {k: round(v / psteps, 3) for k, v in ms_cls.items()},
+            "cpu_baseline": cpu,
+            "per_gpu_stats": [{"sessions": int(s[0]), "steps": int(s[1]), "g711_bytes": int(s[2])} for s in allstats],
+            "hbm_bytes_ctx": tail.device_bytes,
+        }
+        print(json.dumps(out), flush=True)
+    tail.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sessions", type=int, default=1024, help="concurrent sessions per GPU")
+    ap.add_argument("--frames", type=int, default=32, help="mel frames per session per call (reference: 32)")
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--max-windows", type=int, default=4096, help="workspace capacity in 12-frame windows (sub-batch size)")
+    ap.add_argument("--ref-sessions", type=int, default=16, help="sessions per step of the CPU arm's bounded sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it so that there is one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    main_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+/*
+ * infernos_b200 — C-ABI of the B200-native TTS tail (mel chunks -> HiFiGAN -> chunker -> 16k->8k -> G.711).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point names the
+ * reference interface it replaces (paths relative to the sippy/Infernos tree).  All `d_*` pointers are
+ * BORROWED device pointers on the context's device; `h_*` are host pointers; `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).  Functions return 0 on success, non-zero on error;
+ * b2_last_error() returns the message.  Nothing here falls back to the CPU.
+ *
+ * Threading: one thread at a time per context (the reference serialises every torch call behind
+ * InfernGlobals().torcher, HelloSippyTTSRT/HelloSippyRTPipe.py:156,192,246).  The ctx-less codec calls are
+ * stateless and thread-safe (Core/Codecs/G711.py encode is called from per-call RTPOutputWorker threads).
+ */
+#ifndef INFERNOS_B200_H
+#define INFERNOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define B2_API __attribute__((visibility("default")))
+#else
+#define B2_API
+#endif
+
+/* precision modes of the vocoder (north_star: fp32 max-abs 1e-3, bf16 >= 40 dB SNR) */
+#define B2_MODE_FP32 0 /* CUDA-core fp32 convolutions                                  */
+#define B2_MODE_BF16 1 /* tcgen05 tensor-core convolutions: bf16 operands, fp32 accumulate + fp32 residual stream */
+
+#define B2_LAW_ULAW 0 /* PCMU, RTP payload type 0 (Core/Codecs/G711.py:22-23) */
+#define B2_LAW_ALAW 1 /* PCMA, RTP payload type 8 (extension; audioop.lin2alaw semantics) */
+#define B2_LAW_NONE (-1)
+
+typedef struct b2_ctx b2_ctx;
+
+B2_API int b2_abi_version(void);
+/* message of the last failed call on this thread (ctx may be NULL for the ctx-less calls) */
+B2_API const char *b2_last_error(const b2_ctx *ctx);
+
+/* ---- context: packed weights, workspaces, per-session state pool ------------------------------------
+ * Replaces what HelloSippyRTPipe.__init__ builds (HelloSippyRTPipe.py:155-189): vocoder, chunker, resampler.
+ * max_sessions sizes the pre_frames pool (state.pre_frames, HelloSippyRTPipe.py:67,77,233), one 4x80 fp32
+ * slot per session.  max_windows bounds the number of 12-frame windows one call may process. */
+B2_API b2_ctx *b2_ctx_create(int device, int mode, int max_sessions, int max_windows);
+B2_API void b2_ctx_destroy(b2_ctx *ctx);
+B2_API int b2_ctx_mode(const b2_ctx *ctx);
+/* bytes of HBM held by the context (weights + workspaces + state) */
+B2_API size_t b2_ctx_device_bytes(const b2_ctx *ctx);
+
+/* Weights, by state_dict key, fp32 host memory, torch layout:
+ *   vocoder  keys of transformers SpeechT5HifiGan  (mean, scale, conv_pre.weight, upsampler.0.weight, resblocks.0.convs1.0.weight, ...)
+ *   chunker  keys of AmendmentNetwork1             (HelloSippyTTSRT/HelloSippyRT.py:202-217)
+ * replacing SpeechT5HifiGan.from_pretrained / AmendmentNetwork1.from_pretrained (HelloSippyRTPipe.py:171-179). */
+B2_API int b2_load_vocoder_tensor(b2_ctx *ctx, const char *key, const float *h_data, const int64_t *shape, int ndim);
+B2_API int b2_load_chunker_tensor(b2_ctx *ctx, const char *key, const float *h_data, const int64_t *shape, int ndim);
+/* packs the loaded weights for the kernels; must be called once after all tensors are loaded */
+B2_API int b2_weights_finalize(b2_ctx *ctx);
+/* 28 taps of torchaudio Resample(16000,8000).kernel and 2x15 taps of Resample(8000,16000).kernel; the library
+ * has the same values built in, this lets the host pass torchaudio's own (HelloSippyRTPipe.py:185-186). */
+B2_API int b2_set_resample_taps(const float *h_down28, const float *h_up30);
+
+/* ---- the three callables the reference engine holds (HelloSippyRTPipe.py:236,237,240) ---------------- */
+/* self.vocoder(spectrogram): d_mel (W,T,80) fp32 -> d_audio (W, 256*T) fp32.   T >= 1, W*T <= 12*max_windows */
+B2_API int b2_vocoder_forward(b2_ctx *ctx, const float *d_mel, int W, int T, float *d_audio, void *stream);
+/* self.chunker(spectrogram, audio): d_mel (W,12,80), d_audio (W,3072) -> d_out (W,2048) */
+B2_API int b2_chunker_forward(b2_ctx *ctx, const float *d_mel, const float *d_audio, int W, float *d_out, void *stream);
+/* self.resampler(audio): (rows, L) fp32 @16k -> (rows, ceil(L/2)) fp32 @8k, zero padding per row per call */
+B2_API int b2_resample_2to1(const float *d_in, size_t rows, size_t L, float *d_out, void *stream);
+
+/* ---- fused tail: HelloSippyRTPipe.infer() lines 231-240 (+ G711Codec.encode) in one call --------------
+ * d_slots (B) int32: pre_frames slot of each session; d_mel (B, nframes, 80) fp32: the post-net mel frames of
+ * this call (nframes % 8 == 0; the reference uses 32).  Outputs, either may be NULL:
+ *   d_g711  (B, nframes*128) uint8  : G.711 payload bytes of the 8 kHz audio (law = B2_LAW_ULAW/ALAW)
+ *   d_audio (B, nframes*128) fp32   : state.audio at 8 kHz (what unbatch_and_dispatch slices)
+ * The pre_frames slots are updated in place.  Sessions are independent; B*nframes/8 <= max_windows. */
+B2_API int b2_tts_tail(b2_ctx *ctx, const int32_t *d_slots, const float *d_mel, int B, int nframes, int law,
+                uint8_t *d_g711, float *d_audio, void *stream);
+/* same, with HOST buffers (pinned for full speed): H2D of slots+mel, the tail, D2H of the outputs, and a
+ * stream synchronise before returning.  This is the end-to-end entry the e2e benchmark times. */
+B2_API int b2_tts_tail_host(b2_ctx *ctx, const int32_t *h_slots, const float *h_mel, int B, int nframes, int law,
+                     uint8_t *h_g711, float *h_audio, void *stream);
+/* zero the pre_frames of the given slots (HelloSippyPipeState.__init__, HelloSippyRTPipe.py:77); h_slots host */
+B2_API int b2_session_reset(b2_ctx *ctx, const int32_t *h_slots, int n, void *stream);
+/* read / write one session's pre_frames (4x80 fp32, host) — used to migrate or checkpoint a session */
+B2_API int b2_session_get_pre_frames(b2_ctx *ctx, int slot, float *h_out, void *stream);
+B2_API int b2_session_set_pre_frames(b2_ctx *ctx, int slot, const float *h_in, void *stream);
+
+/* ---- Core/Codecs (G711.py:25-47), ctx-less, stateless ----------------------------------------------- */
+/* G711Codec.encode: clamp(x*32767,-32768,32767) -> int16 (trunc toward zero) -> G.711 code.  n samples. */
+B2_API int b2_g711_encode_f32(const float *d_in, size_t n, int law, uint8_t *d_out, void *stream);
+B2_API int b2_g711_encode_i16(const int16_t *d_in, size_t n, int law, uint8_t *d_out, void *stream);
+/* the float -> int16 step on its own (G711.py:27) */
+B2_API int b2_f32_to_pcm16(const float *d_in, size_t n, int16_t *d_out, void *stream);
+/* G711Codec.decode without resampling: code -> int16 -> float / 32767.0 */
+B2_API int b2_g711_decode_f32(const uint8_t *d_in, size_t n, int law, float *d_out, void *stream);
+B2_API int b2_g711_decode_i16(const uint8_t *d_in, size_t n, int law, int16_t *d_out, void *stream);
+/* fused resampler + encoder: (rows, L) fp32 @16k -> (rows, ceil(L/2)) G.711 bytes @8k */
+B2_API int b2_resample_g711_encode(const float *d_in, size_t rows, size_t L, int law, uint8_t *d_out, void *stream);
+/* G711Codec.decode(resample=True, sample_rate=16000): (rows, L) bytes @8k -> (rows, 2L) fp32 @16k
+ * (G711.py:44-46 -> Core/AudioChunk.py:19-24 -> config/InfernGlobals.py:23-26) */
+B2_API int b2_g711_decode_upsample(const uint8_t *d_in, size_t rows, size_t L, int law, float *d_out, void *stream);
+/* AudioChunk.resample 8k -> 16k on its own: (rows, L) -> (rows, 2L) */
+B2_API int b2_resample_1to2(const float *d_in, size_t rows, size_t L, float *d_out, void *stream);
+
+/* ---- single-layer entry points (unit tests of the two convolution kernel families) -----------------
+ * One Conv1d(Cin, Cout, k, dilation=dil, padding=(k-1)*dil/2) over channels-last activations [W][T][C]:
+ *   h_weight torch layout [Cout][Cin][k] fp32 host, h_bias [Cout] host; d_residual / d_out32 fp32 [W][T][Cout] (may be NULL);
+ *   d_outb bf16 [W][T][Cout] = bf16(leaky_relu(out, slope)) (may be NULL); out is divided by `div` first.
+ * b2_conv1d_tc : tcgen05 kernel, d_in bf16 (already activated).   b2_conv1d_f32 : CUDA-core kernel, d_in fp32,
+ * leaky_relu(pre_slope) applied to the input. */
+B2_API int b2_conv1d_tc(const void *d_in_bf16, const float *h_weight, const float *h_bias, int W, int T, int Cin, int Cout, int k, int dil,
+                        const float *d_residual, float *d_out32, void *d_outb, float slope, float div, void *stream);
+B2_API int b2_conv1d_f32(const float *d_in, const float *h_weight, const float *h_bias, int W, int T, int Cin, int Cout, int k, int dil,
+                         float pre_slope, const float *d_residual, float *d_out32, void *d_outb, float slope, float div, void *stream);
+
+/* ---- bookkeeping the benchmark reports ------------------------------------------------------------- */
+/* number of kernels this library has launched in this process since load (all contexts) */
+B2_API uint64_t b2_kernel_launch_count(void);
+/* Per-kernel-class device timing (CUDA events on the launching stream around every launch of this context)
+ * between b2_profile_begin and b2_profile_end.  Classes: 0 tcgen05 convs, 1 CUDA-core convs, 2 conv_post+tanh,
+ * 3 resample+G.711, 4 other (window builder, chunker prologue/epilogue).  Arrays of 8. */
+B2_API int b2_profile_begin(b2_ctx *ctx);
+B2_API int b2_profile_end(b2_ctx *ctx, double *ms_by_class, uint64_t *launches_by_class);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INFERNOS_B200_H */

@@ -1,0 +1,327 @@
+// fp32 CUDA-core kernels of the TTS tail (see conv_simt.cuh).  Restates, never copies:
+//   transformers SpeechT5HifiGan.forward / HifiGanResidualBlock.forward (modeling_speecht5.py:2954-2962, 3055-3085)
+//   AmendmentNetwork1.forward (HelloSippyTTSRT/HelloSippyRT.py:219-237)
+//   window builder (HelloSippyTTSRT/HelloSippyRTPipe.py:231-235)
+#include "conv_simt.cuh"
+
+namespace b2 {
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.0f ? v : v * slope; }
+
+// ---------------------------------------------------------------------------------------------------
+// generic conv1d as a tiled SGEMM: M = W*Tout flattened rows, N = Cout, K = taps*Cin.
+// CTA tile 128 x BN, 256 threads, 8 x (BN/16) outputs per thread, K chunk 16.
+// ---------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(256) k_conv_simt(ConvArgs a) {
+    constexpr int BM = 128, KC = 16, TN = BN / 16;
+    __shared__ __align__(16) float As[KC][BM];
+    __shared__ __align__(16) float Bs[KC][BN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long long M = (long long)a.W * a.Tout;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+
+    // the row this thread loads for the A tile
+    const int lrow = tid & 127;
+    const int lc4 = tid >> 7;                     // 0..1 (+2 on the second pass)
+    const long long lr = m0 + lrow;
+    const bool lvalid = lr < M;
+    const int lw = lvalid ? (int)(lr / a.Tout) : 0;
+    const int lt = lvalid ? (int)(lr - (long long)lw * a.Tout) : 0;
+    const float *in_w = a.in + (long long)lw * a.Tin * a.Cin;
+
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int e = 0; e < TN; e++) acc[i][e] = 0.0f;
+
+    for (int j = 0; j < a.taps; j++) {
+        const int tin = lt * a.stride + j * a.dil - a.pad;
+        const bool rvalid = lvalid && tin >= 0 && tin < a.Tin;
+        const float *in_row = in_w + (long long)tin * a.Cin;
+        const float *w_tap = a.wt + (long long)j * a.Cin * a.Cout;
+        for (int c0 = 0; c0 < a.Cin; c0 += KC) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int c = c0 + (lc4 + 2 * q) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rvalid && c < a.Cin) v = __ldg(reinterpret_cast<const float4 *>(in_row + c));
+                const int cc = (lc4 + 2 * q) * 4;
+                As[cc + 0][lrow] = lrelu(v.x, a.pre_slope);
+                As[cc + 1][lrow] = lrelu(v.y, a.pre_slope);
+                As[cc + 2][lrow] = lrelu(v.z, a.pre_slope);
+                As[cc + 3][lrow] = lrelu(v.w, a.pre_slope);
+            }
+            if (BN == 64 || tid < 128) {
+                constexpr int N4 = BN / 4;
+                const int kk = tid / N4, n4 = tid % N4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + kk < a.Cin && n0 + n4 * 4 < a.Cout)
+                    v = __ldg(reinterpret_cast<const float4 *>(w_tap + (long long)(c0 + kk) * a.Cout + n0 + n4 * 4));
+                *reinterpret_cast<float4 *>(&Bs[kk][n4 * 4]) = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8]);
+                const float4 a1 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8 + 4]);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                float bv[TN];
+                if constexpr (TN == 4) {
+                    const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+                    bv[0] = b.x; bv[1] = b.y; bv[2] = b.z; bv[3] = b.w;
+                } else {
+                    const float2 b = *reinterpret_cast<const float2 *>(&Bs[kk][tx * 2]);
+                    bv[0] = b.x; bv[1] = b.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int e = 0; e < TN; e++) acc[i][e] = fmaf(av[i], bv[e], acc[i][e]);
+            }
+            __syncthreads();
+        }
+    }
+
+    const int col = n0 + tx * TN;
+    if (col >= a.Cout) return;
+    float bias[TN];
+#pragma unroll
+    for (int e = 0; e < TN; e++) bias[e] = a.bias ? __ldg(a.bias + col + e) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const long long r = m0 + ty * 8 + i;
+        if (r >= M) continue;
+        const long long o = r * a.Cout + col;
+        float v[TN];
+#pragma unroll
+        for (int e = 0; e < TN; e++) v[e] = acc[i][e] + bias[e];
+        if (a.residual) {
+#pragma unroll
+            for (int e = 0; e < TN; e++) v[e] += a.residual[o + e];
+        }
+        if (a.accumulate) {
+#pragma unroll
+            for (int e = 0; e < TN; e++) v[e] = a.out[o + e] + v[e];
+        }
+        if (a.div != 1.0f) {
+#pragma unroll
+            for (int e = 0; e < TN; e++) v[e] = __fdiv_rn(v[e], a.div);
+        }
+        if (a.out) {
+            if constexpr (TN == 4) *reinterpret_cast<float4 *>(a.out + o) = make_float4(v[0], v[1], v[2], v[3]);
+            else *reinterpret_cast<float2 *>(a.out + o) = make_float2(v[0], v[1]);
+        }
+        if (a.out_bf16) {
+#pragma unroll
+            for (int e = 0; e < TN; e += 2) {
+                __nv_bfloat162 p = __floats2bfloat162_rn(lrelu(v[e], a.bf16_slope), lrelu(v[e + 1], a.bf16_slope));
+                *reinterpret_cast<__nv_bfloat162 *>(a.out_bf16 + o + e) = p;
+            }
+        }
+    }
+}
+
+int launch_conv_simt(const ConvArgs &a, cudaStream_t st) {
+    if (a.W <= 0 || a.Tout <= 0) return 0;
+    if (a.Cin % 4 || a.Cout % 4) return set_error("conv_simt: Cin (%d) and Cout (%d) must be multiples of 4", a.Cin, a.Cout);
+    const long long M = (long long)a.W * a.Tout;
+    if (a.Cout % 64 == 0) {
+        dim3 grid((unsigned)cdiv(M, 128), (unsigned)(a.Cout / 64));
+        k_conv_simt<64><<<grid, 256, 0, st>>>(a);
+    } else {
+        dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(a.Cout, 32));
+        k_conv_simt<32><<<grid, 256, 0, st>>>(a);
+    }
+    B2_LAUNCH_OK("k_conv_simt");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv_post: leaky_relu(0.01) -> Conv1d(32 -> 1, k7, pad 3) -> tanh
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_conv_post(const float *__restrict__ in, const float *__restrict__ wt, const float *__restrict__ bias,
+                                                  float *__restrict__ out, long long M, int T) {
+    __shared__ float ws[7 * 32];
+    if (threadIdx.x < 224) ws[threadIdx.x] = wt[threadIdx.x];
+    __syncthreads();
+    const float b = bias[0];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += stride) {
+        const int t = (int)(r % T);
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const int tt = t + j - 3;
+            if (tt < 0 || tt >= T) continue;
+            const float4 *p = reinterpret_cast<const float4 *>(in + (r + j - 3) * 32);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; c4++) {
+                const float4 v = __ldg(p + c4);
+                acc = fmaf(ws[j * 32 + c4 * 4 + 0], lrelu(v.x, 0.01f), acc);
+                acc = fmaf(ws[j * 32 + c4 * 4 + 1], lrelu(v.y, 0.01f), acc);
+                acc = fmaf(ws[j * 32 + c4 * 4 + 2], lrelu(v.z, 0.01f), acc);
+                acc = fmaf(ws[j * 32 + c4 * 4 + 3], lrelu(v.w, 0.01f), acc);
+            }
+        }
+        out[r] = tanhf(acc + b);
+    }
+}
+
+int launch_conv_post(const float *in, const float *wt, const float *bias, float *out, int W, int T, cudaStream_t st) {
+    const long long M = (long long)W * T;
+    if (M <= 0) return 0;
+    long long blocks = (M + 255) / 256;
+    long long cap = (long long)sm_count() * 16;
+    k_conv_post<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(in, wt, bias, out, M, T);
+    B2_LAUNCH_OK("k_conv_post");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// window builder: one CTA per session
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_windows(const int32_t *__restrict__ slots, const float *__restrict__ mel, float *__restrict__ pre_pool,
+                                                      const float *__restrict__ mean, const float *__restrict__ scale,
+                                                      float *__restrict__ win_raw, float *__restrict__ win_norm, int B, int nframes) {
+    const int nwin = nframes / 8;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const int slot = slots[b];
+        float *pre = pre_pool + (long long)slot * 320;
+        const float *m = mel + (long long)b * nframes * 80;
+        const long long wbase = (long long)b * nwin * 960;
+        // spec frame f (0 .. nframes+3): f < 4 -> pre[f], else mel[f-4]; window i covers frames 8i .. 8i+11
+        for (int e = threadIdx.x; e < nwin * 960; e += blockDim.x) {
+            const int i = e / 960, rem = e - i * 960;
+            const int fr = rem / 80, bin = rem - fr * 80;
+            const int f = 8 * i + fr;
+            const float v = (f < 4) ? pre[f * 80 + bin] : m[(f - 4) * 80 + bin];
+            win_raw[wbase + e] = v;
+            win_norm[wbase + e] = __fdiv_rn(v - mean[bin], scale[bin]);
+        }
+        __syncthreads();   // every read of pre[] is done before it is overwritten
+        for (int e = threadIdx.x; e < 320; e += blockDim.x) pre[e] = m[(nframes - 4) * 80 + e];
+        __syncthreads();
+    }
+}
+
+int launch_build_windows(const int32_t *slots, const float *mel, float *pre_pool, const float *mean, const float *scale,
+                         float *win_raw, float *win_norm, int B, int nframes, cudaStream_t st) {
+    if (B <= 0) return 0;
+    k_build_windows<<<B, 256, 0, st>>>(slots, mel, pre_pool, mean, scale, win_raw, win_norm, B, nframes);
+    B2_LAUNCH_OK("k_build_windows");
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) k_normalise(const float *__restrict__ mel, const float *__restrict__ mean, const float *__restrict__ scale,
+                                                  float *__restrict__ out, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int bin = (int)(i % 80);
+        out[i] = __fdiv_rn(mel[i] - mean[bin], scale[bin]);
+    }
+}
+
+int launch_normalise(const float *mel, const float *mean, const float *scale, float *out, size_t rows, cudaStream_t st) {
+    size_t n = rows * 80;
+    if (n == 0) return 0;
+    size_t blocks = (n + 255) / 256, cap = (size_t)sm_count() * 16;
+    k_normalise<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(mel, mean, scale, out, n);
+    B2_LAUNCH_OK("k_normalise");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// chunker prologue: one CTA (192 threads) per window; thread = output channel, 12 accumulators (time).
+// warp 0 = the 32 mel channels (Cin 80), warps 1..5 = the 160 audio channels (Cin 256).
+// mel_view[ci][t] = mel_window_flat[ci*12 + t]; audio_view[ci][t] = audio[ci*12 + t]  (raw .view, not a transpose)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) k_chunker_pre(const float *__restrict__ mel, const float *__restrict__ audio,
+                                                    const float *__restrict__ wm, const float *__restrict__ bm,
+                                                    const float *__restrict__ wa, const float *__restrict__ ba,
+                                                    float *__restrict__ z0, int W) {
+    __shared__ __align__(16) float sm[80 * 12];
+    __shared__ __align__(16) float sa[256 * 12];
+    const int tid = threadIdx.x;
+    for (int w = blockIdx.x; w < W; w += gridDim.x) {
+        for (int e = tid; e < 960; e += 192) sm[e] = mel[(long long)w * 960 + e];
+        for (int e = tid; e < 3072; e += 192) sa[e] = audio[(long long)w * 3072 + e];
+        __syncthreads();
+        float acc[12];
+        const bool is_mel = tid < 32;
+        const int co = is_mel ? tid : tid - 32;
+        const int Cin = is_mel ? 80 : 256, Cout = is_mel ? 32 : 160;
+        const float *src = is_mel ? sm : sa;
+        const float *wt = is_mel ? wm : wa;
+        const float b = is_mel ? bm[co] : ba[co];
+#pragma unroll
+        for (int t = 0; t < 12; t++) acc[t] = b;
+        for (int ci = 0; ci < Cin; ci++) {
+            const float4 x0 = *reinterpret_cast<const float4 *>(src + ci * 12);
+            const float4 x1 = *reinterpret_cast<const float4 *>(src + ci * 12 + 4);
+            const float4 x2 = *reinterpret_cast<const float4 *>(src + ci * 12 + 8);
+            const float x[14] = {0.f, x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, 0.f};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float wv = __ldg(wt + ((long long)k * Cin + ci) * Cout + co);
+#pragma unroll
+                for (int t = 0; t < 12; t++) acc[t] = fmaf(wv, x[t + k], acc[t]);
+            }
+        }
+        float *o = z0 + (long long)w * 12 * 192 + tid;
+#pragma unroll
+        for (int t = 0; t < 12; t++) o[t * 192] = acc[t];
+        __syncthreads();
+    }
+}
+
+int launch_chunker_pre(const float *mel, const float *audio, const float *wm, const float *bm, const float *wa, const float *ba,
+                       float *z0, int W, cudaStream_t st) {
+    if (W <= 0) return 0;
+    int cap = sm_count() * 8;
+    k_chunker_pre<<<W < cap ? W : cap, 192, 0, st>>>(mel, audio, wm, bm, wa, ba, z0, W);
+    B2_LAUNCH_OK("k_chunker_pre");
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) k_chunker_final(const float *__restrict__ audio, const float *__restrict__ post, float *__restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const long long w = e >> 11;
+        const int i = (int)(e & 2047);
+        const float g = lrelu(post[w * 2048 + (i & 7) * 256 + (i >> 3)], 0.01f);
+        out[e] = tanhf(audio[w * 3072 + 512 + i] * g);
+    }
+}
+
+int launch_chunker_final(const float *audio, const float *post, float *out, int W, cudaStream_t st) {
+    const long long n = (long long)W * 2048;
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256, cap = (long long)sm_count() * 16;
+    k_chunker_final<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(audio, post, out, n);
+    B2_LAUNCH_OK("k_chunker_final");
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) k_trim(const float *__restrict__ audio, float *__restrict__ out, long long n, int Lin, int lo, int Lout) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const long long w = e / Lout;
+        const int i = (int)(e - w * Lout);
+        out[e] = audio[w * Lin + lo + i];
+    }
+}
+
+int launch_trim(const float *audio, float *out, int W, int Lin, int lo, int Lout, cudaStream_t st) {
+    const long long n = (long long)W * Lout;
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256, cap = (long long)sm_count() * 16;
+    k_trim<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(audio, out, n, Lin, lo, Lout);
+    B2_LAUNCH_OK("k_trim");
+    return 0;
+}
+
+}  // namespace b2

@@ -1,0 +1,383 @@
+// tcgen05 (UMMA) implicit-GEMM conv1d, hand-written for sm_100a.
+//
+// One CTA computes a 128-row x N_TILE tile of   out[w][t][n] = bias[n] + sum_j sum_ci Wb[j][n][ci] * in[w][t + j*dil - pad][ci]
+// for the HiFiGAN upsamplers (ConvTranspose1d restated as a 3-tap conv, see tail.cu:pack_convT) and ResBlock convs
+// (modeling_speecht5.py:2954-2962, 3066-3067), with bias / residual / MRF-accumulate / leaky-ReLU fused in the epilogue.
+//
+//   A operand (activations, M = time)  : the tile's rows PLUS the conv halo are brought into shared memory ONCE with
+//       cp.async (zero-filled outside the window: every window is padded on its own, HelloSippyRTPipe.py:234-236),
+//       in the un-swizzled K-major "interleaved" UMMA layout [channel/8][row][8 channels].  In that layout consecutive
+//       rows are exactly 16 bytes apart, so filter tap j is the SAME buffer read through a descriptor whose start
+//       address is advanced by j*dil rows: the k taps cost no extra global or L2 traffic.
+//   B operand (weights, N = out chans) : streamed per (K-block, tap) by TMA into a 128B/64B-swizzled ring, mbarrier pipelined.
+//   D accumulator                      : fp32 in TMEM (N_TILE columns), read back with tcgen05.ld by four epilogue warps.
+//
+// Warp roles (192 threads): warps 0-3 = A producers, then epilogue (TMEM lanes 32*warp..); warp 4 = TMA producer for B;
+// warp 5 = TMEM allocator + single-thread tcgen05.mma issuer.
+#include "conv_umma.cuh"
+
+#include <cuda.h>
+#include <mutex>
+
+namespace b2 {
+
+static constexpr int kThreads = 192;
+static constexpr int kMaxKB = 8;      // Cin <= 512 in blocks of 64
+
+struct UmmaParams {
+    const __nv_bfloat16 *in;
+    const float *bias;
+    const float *residual;
+    const float *acc_src;
+    float *out32;
+    __nv_bfloat16 *outb;
+    float outb_slope, div;
+    int W, T, Cin, N, taps, dil, pad;
+    int R;            // rows of the A buffer (128 + (taps-1)*dil, made odd)
+    int KB;           // K block: 64 (128B swizzle) or 32 (64B swizzle)
+    int nkb;          // Cin / KB
+    int nseg;         // windows per tile (short windows), else 1
+    int period;       // row period between the windows of a tile (T + pad), or 1<<30
+    int tiles_per_win;// ceil(T / 128) when nseg == 1
+    int stages;       // B ring depth
+};
+
+// ---------------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1 = sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(layout_type & 7) << 61;
+    return d;
+}
+
+__device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.0f ? v : v * slope; }
+
+// ---------------------------------------------------------------------------------------------------- kernel
+template <int N_TILE>
+__global__ void __launch_bounds__(kThreads) k_conv_umma(const __grid_constant__ CUtensorMap tmap_w, const UmmaParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = p.KB;
+    const uint32_t b_stage_bytes = (uint32_t)N_TILE * KB * 2;
+    const uint32_t a_bytes = (uint32_t)p.R * p.Cin * 2;
+    uint8_t *sB = smem;
+    uint8_t *sA = smem + (size_t)p.stages * b_stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + ((a_bytes + 15) & ~15u));
+    // bars: [0..stages) b_full, [stages..2*stages) b_empty, [2*stages .. +kMaxKB) a_full, then acc_full
+    const uint32_t bar_b_full = smem_u32(bars);
+    const uint32_t bar_b_empty = smem_u32(bars + p.stages);
+    const uint32_t bar_a_full = smem_u32(bars + 2 * p.stages);
+    const uint32_t bar_acc = smem_u32(bars + 2 * p.stages + kMaxKB);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + kMaxKB + 1);
+
+    // ---- tile coordinates
+    int w0, t0;
+    if (p.nseg > 1) { w0 = blockIdx.x * p.nseg; t0 = 0; }
+    else { w0 = blockIdx.x / p.tiles_per_win; t0 = (blockIdx.x - w0 * p.tiles_per_win) * 128; }
+    const int n0 = blockIdx.y * N_TILE;
+
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
+        for (int s = 0; s < p.stages; s++) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+        for (int k = 0; k < kMaxKB; k++) mbar_init(bar_a_full + 8 * k, 128);
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)N_TILE) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // =========================== A producer: tile rows + halo, once ===========================
+        const int tid = threadIdx.x;
+        const uint32_t sA_u32 = smem_u32(sA);
+        const int cpr = KB / 8;                       // 16-byte pieces per row per K block
+        const int pieces = p.R * cpr;
+        for (int kb = 0; kb < p.nkb; kb++) {
+            for (int q = tid; q < pieces; q += 128) {
+                const int r = q / cpr, c = q - r * cpr;
+                const int u = r - p.pad;
+                const int s = (u >= 0) ? u / p.period : 0;
+                const int t = t0 + (u - s * p.period);
+                const int w = w0 + s;
+                const bool ok = (t >= 0) && (t < p.T) && (s < p.nseg) && (w < p.W);
+                const __nv_bfloat16 *src = ok ? p.in + ((size_t)w * p.T + t) * p.Cin + kb * KB + c * 8 : p.in;
+                cp_async16(sA_u32 + (uint32_t)(((kb * cpr + c) * p.R + r) * 16), src, ok ? 16u : 0u);
+            }
+            cp_async_arrive_noinc(bar_a_full + 8 * kb);
+        }
+        // =========================== epilogue ===========================
+        mbar_wait(bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int m = warp * 32 + lane;
+        const int s = m / p.period;
+        const int t = t0 + (m - s * p.period);
+        const int w = w0 + s;
+        const bool ok = (t < p.T) && (s < p.nseg) && (w < p.W);
+        const size_t row_off = ((size_t)w * p.T + t) * p.N + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);   // warp-collective: no divergence before it
+            if (!ok) continue;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c0 + i));
+                v[i] = __uint_as_float(acc[i]) + b.x; v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
+                v[i + 2] = __uint_as_float(acc[i + 2]) + b.z; v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
+            }
+            if (p.residual) {
+                const float4 *rp = reinterpret_cast<const float4 *>(p.residual + row_off + c0);
+#pragma unroll
+                for (int i = 0; i < 8; i++) { const float4 r4 = rp[i]; v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w; }
+            }
+            if (p.acc_src) {
+                const float4 *ap = reinterpret_cast<const float4 *>(p.acc_src + row_off + c0);
+#pragma unroll
+                for (int i = 0; i < 8; i++) { const float4 r4 = ap[i]; v[4 * i] = r4.x + v[4 * i]; v[4 * i + 1] = r4.y + v[4 * i + 1]; v[4 * i + 2] = r4.z + v[4 * i + 2]; v[4 * i + 3] = r4.w + v[4 * i + 3]; }
+            }
+            if (p.div != 1.0f) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) v[i] = __fdiv_rn(v[i], p.div);
+            }
+            if (p.out32) {
+                float4 *op = reinterpret_cast<float4 *>(p.out32 + row_off + c0);
+#pragma unroll
+                for (int i = 0; i < 8; i++) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            if (p.outb) {
+                uint4 *op = reinterpret_cast<uint4 *>(p.outb + row_off + c0);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(lrelu_f(v[8 * i + 2 * e], p.outb_slope), lrelu_f(v[8 * i + 2 * e + 1], p.outb_slope));
+                        pk[e] = *reinterpret_cast<uint32_t *>(&h2);
+                    }
+                    op[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // =========================== B producer (TMA) ===========================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < p.nkb; kb++) {
+                for (int j = 0; j < p.taps; j++) {
+                    mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(bar_b_full + 8 * stage, b_stage_bytes);
+                    tma_load_3d(smem_u32(sB + (size_t)stage * b_stage_bytes), &tmap_w, bar_b_full + 8 * stage, kb * KB, n0, j);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N = N_TILE, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t sA_u32 = smem_u32(sA);
+            const uint32_t a_lbo = (uint32_t)p.R * 16;                  // between the two 8-channel chunks of one K=16 step
+            const uint32_t b_layout = (KB == 64) ? 2u : 4u;             // SWIZZLE_128B : SWIZZLE_64B
+            const uint32_t b_sbo = 8u * (uint32_t)KB * 2;               // 8 rows of KB bf16
+            const int ksteps = KB / 16;
+            int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
+            for (int kb = 0; kb < p.nkb; kb++) {
+                mbar_wait(bar_a_full + 8 * kb, 0);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA (async proxy) reads
+                for (int j = 0; j < p.taps; j++) {
+                    mbar_wait(bar_b_full + 8 * stage, phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t b_base = smem_u32(sB + (size_t)stage * b_stage_bytes);
+                    for (int ks = 0; ks < ksteps; ks++) {
+                        const uint32_t a_addr = sA_u32 + (uint32_t)((((kb * (KB / 8) + ks * 2) * p.R) + j * p.dil) * 16);
+                        const uint64_t adesc = smem_desc(a_addr, a_lbo, 128u, 0u);
+                        const uint64_t bdesc = smem_desc(b_base + ks * 32, 0u, b_sbo, b_layout);
+                        umma_f16(tmem_base, adesc, bdesc, idesc, accum);
+                        accum = 1;
+                    }
+                    umma_commit(bar_b_empty + 8 * stage);   // frees the B slot when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+            umma_commit(bar_acc);
+        }
+        __syncwarp();
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)N_TILE) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::mutex g_init_mu;
+static bool g_attr_set[64][4] = {};
+
+static int n_tile_for(const Layer &l) {
+    if (l.Cout >= 256) return (l.Cin >= 512) ? 128 : 256;
+    return l.Cout;     // 32, 64, 128
+}
+
+int umma_init() {
+    std::lock_guard<std::mutex> g(g_init_mu);
+    if (g_encode) return 0;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return set_error("cuTensorMapEncodeTiled is not available from the driver: %s", cudaGetErrorString(e));
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return 0;
+}
+
+int umma_prepare_layer(Layer &l) {
+    if (umma_init()) return 1;
+    if (l.Cin % 32 || (l.Cin > 32 && l.Cin % 64) || l.Cin > 64 * kMaxKB) return set_error("conv_umma: unsupported Cin %d", l.Cin);
+    const int nt = n_tile_for(l);
+    if (l.Cout % nt || (nt != 32 && nt != 64 && nt != 128 && nt != 256)) return set_error("conv_umma: unsupported Cout %d", l.Cout);
+    if (l.stride != 1) return set_error("conv_umma: stride must be 1");
+    const int KB = l.Cin >= 64 ? 64 : 32;
+    CUtensorMap *tm = new CUtensorMap();
+    cuuint64_t gdim[3] = {(cuuint64_t)l.Cin, (cuuint64_t)l.Cout, (cuuint64_t)l.taps};
+    cuuint64_t gstr[2] = {(cuuint64_t)l.Cin * 2, (cuuint64_t)l.Cin * l.Cout * 2};
+    cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)nt, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)l.wbf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { delete tm; return set_error("cuTensorMapEncodeTiled failed with CUresult %d (Cin %d Cout %d taps %d)", (int)r, l.Cin, l.Cout, l.taps); }
+    l.tmap = tm;
+    return 0;
+}
+
+void umma_free_layer(Layer &l) {
+    if (l.tmap) { delete reinterpret_cast<CUtensorMap *>(l.tmap); l.tmap = nullptr; }
+}
+
+template <int NT>
+static int launch_nt(const CUtensorMap &tm, const UmmaParams &p, dim3 grid, size_t smem, cudaStream_t st, int slot) {
+    int dev = 0;
+    B2_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 64 && !g_attr_set[dev][slot]) {
+        B2_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        g_attr_set[dev][slot] = true;
+    }
+    k_conv_umma<NT><<<grid, kThreads, smem, st>>>(tm, p);
+    B2_LAUNCH_OK("k_conv_umma");
+    return 0;
+}
+
+int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
+    const Layer &l = *a.layer;
+    if (!l.tmap || !l.wbf) return set_error("conv_umma: layer has no tensor-core weights (context not in B2_MODE_BF16?)");
+    if (a.W <= 0 || a.T <= 0) return 0;
+    if ((l.taps - 1) * l.dil != 2 * l.pad) return set_error("conv_umma: only 'same' convolutions are supported");
+    UmmaParams p;
+    p.in = a.in; p.bias = l.bias; p.residual = a.residual; p.acc_src = a.acc_src; p.out32 = a.out32; p.outb = a.outb;
+    p.outb_slope = a.outb_slope; p.div = a.div;
+    p.W = a.W; p.T = a.T; p.Cin = l.Cin; p.N = l.Cout; p.taps = l.taps; p.dil = l.dil; p.pad = l.pad;
+    p.R = (128 + (l.taps - 1) * l.dil) | 1;
+    p.KB = l.Cin >= 64 ? 64 : 32;
+    p.nkb = l.Cin / p.KB;
+    const int nt = n_tile_for(l);
+    unsigned mtiles;
+    if (a.T < 128) {
+        const int G = l.pad;
+        p.nseg = std::max(1, (128 + G) / (a.T + G));
+        p.period = a.T + G;
+        p.tiles_per_win = 1;
+        mtiles = (unsigned)cdiv(a.W, p.nseg);
+    } else {
+        p.nseg = 1; p.period = 1 << 30; p.tiles_per_win = cdiv(a.T, 128);
+        mtiles = (unsigned)((long long)a.W * p.tiles_per_win);
+    }
+    const size_t a_bytes = ((size_t)p.R * l.Cin * 2 + 15) & ~(size_t)15;
+    const size_t b_stage = (size_t)nt * p.KB * 2;
+    const size_t tail_bytes = (2 * 8 + kMaxKB + 1) * 8 + 16;
+    int stages = 4;
+    while (stages > 2 && stages * b_stage + a_bytes + tail_bytes > 200 * 1024) stages--;
+    const int total_b = p.nkb * l.taps;
+    if (stages > total_b) stages = std::max(1, total_b);
+    p.stages = stages;
+    const size_t smem = stages * b_stage + a_bytes + tail_bytes;
+    if (smem > 227 * 1024) return set_error("conv_umma: tile needs %zu bytes of shared memory", smem);
+    dim3 grid(mtiles, (unsigned)(l.Cout / nt));
+    const CUtensorMap &tm = *reinterpret_cast<const CUtensorMap *>(l.tmap);
+    switch (nt) {
+        case 32: return launch_nt<32>(tm, p, grid, smem, st, 0);
+        case 64: return launch_nt<64>(tm, p, grid, smem, st, 1);
+        case 128: return launch_nt<128>(tm, p, grid, smem, st, 2);
+        default: return launch_nt<256>(tm, p, grid, smem, st, 3);
+    }
+}
+
+}  // namespace b2

@@ -1,0 +1,32 @@
+// tcgen05 (UMMA) implicit-GEMM conv1d for the HiFiGAN upsamplers and ResBlocks (B2_MODE_BF16).
+#pragma once
+#include "common.cuh"
+#include "ctx.cuh"
+
+namespace b2 {
+
+// out[w][t][n] = epi( bias[n] + sum_{j<taps} sum_{ci} Wb[j][n][ci] * in[w][t + j*dil - pad][ci] )      (stride 1)
+//   in    bf16 channels-last [W][T][Cin], activation already applied by its producer
+//   epi(v): v += residual (fp32); v += acc_src (fp32); v /= div; out32 = v; outb = bf16(lrelu(v, outb_slope))
+// N = layer.Cout (for a ConvTranspose1d packed as a 3-tap conv, Cout is 4x the module's out channels and the
+// output row [t][4*C] is the channels-last image of output times 4t..4t+3).
+struct UmmaConvArgs {
+    const __nv_bfloat16 *in = nullptr;
+    const Layer *layer = nullptr;
+    const float *residual = nullptr;
+    float *out32 = nullptr;
+    __nv_bfloat16 *outb = nullptr;
+    float outb_slope = 1.0f;
+    const float *acc_src = nullptr;   // may alias out32 (same element read then written by one thread)
+    float div = 1.0f;
+    int W = 0, T = 0;
+};
+
+int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st);
+// builds the TMA descriptor of a layer's bf16 weights; called once from b2_weights_finalize
+int umma_prepare_layer(Layer &l);
+void umma_free_layer(Layer &l);
+// one-time, per process: resolves cuTensorMapEncodeTiled and sets kernel attributes
+int umma_init();
+
+}  // namespace b2

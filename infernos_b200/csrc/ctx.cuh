@@ -1,0 +1,78 @@
+// Context of the TTS tail: packed weights, workspaces, per-session state pool.
+#pragma once
+#include "common.cuh"
+#include <map>
+#include <string>
+#include <vector>
+
+namespace b2 {
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+};
+
+// one convolution layer, packed for both kernel families
+struct Layer {
+    int Cin = 0, Cout = 0, taps = 0, dil = 1, pad = 0, stride = 1;
+    float *w32 = nullptr;            // [taps][Cin][Cout] fp32 (CUDA-core path)
+    float *bias = nullptr;           // [Cout] fp32
+    __nv_bfloat16 *wbf = nullptr;    // [taps][Cout][Cin] bf16, K-major (tensor-core path); nullptr if unused
+    void *tmap = nullptr;            // host copy of the CUtensorMap for wbf (tensor-core path)
+};
+
+struct Workspace {
+    // sized for `cap_frames` mel frames in flight (12 per window)
+    float *win_raw = nullptr, *win_norm = nullptr;     // [F][80]
+    float *c0 = nullptr;                               // [F][512] fp32 (FP32 mode)
+    float *h = nullptr, *y = nullptr, *r = nullptr, *s0 = nullptr, *s1 = nullptr;   // [F*8192] fp32
+    __nv_bfloat16 *c0b = nullptr;                      // [F][512] bf16 (BF16 mode)
+    __nv_bfloat16 *hb = nullptr, *yb = nullptr, *rb = nullptr, *sb = nullptr;       // [F*8192] bf16
+    float *audio = nullptr;                            // [F*256]
+    // chunker, per window
+    float *z0 = nullptr, *z1 = nullptr, *z2 = nullptr, *zy = nullptr, *z3 = nullptr, *post = nullptr;
+    float *audio16k = nullptr;                         // [W][2048]
+    int32_t *slots = nullptr;                          // device copy for the host entry point
+    float *mel_in = nullptr;                           // device staging for the host entry point
+    uint8_t *g711_out = nullptr;
+    float *audio8k_out = nullptr;
+};
+
+// optional per-kernel-class timing with CUDA events on the launching stream (used by bench.py's roofline leg)
+enum ProfClass { PC_CONV_TC = 0, PC_CONV_F32 = 1, PC_CONV_POST = 2, PC_RESAMPLE_G711 = 3, PC_OTHER = 4, PC_COUNT = 8 };
+struct ProfSpan { int cls; cudaEvent_t a, b; };
+struct Prof {
+    bool on = false;
+    std::vector<ProfSpan> spans;
+    void begin(int cls, cudaStream_t st) {
+        if (!on) return;
+        ProfSpan s; s.cls = cls;
+        cudaEventCreate(&s.a); cudaEventCreate(&s.b);
+        cudaEventRecord(s.a, st);
+        spans.push_back(s);
+    }
+    void end(cudaStream_t st) { if (on) cudaEventRecord(spans.back().b, st); }
+};
+
+}  // namespace b2
+
+struct b2_ctx {
+    int device = 0, mode = 0, max_sessions = 0, max_windows = 0;
+    bool finalized = false;
+    std::map<std::string, b2::HostTensor> voc_raw, chk_raw;
+    std::vector<void *> allocs;
+    size_t device_bytes = 0;
+    std::string err;
+    b2::Prof prof;
+
+    float *mean = nullptr, *scale = nullptr;
+    b2::Layer conv_pre, up[4], res1[4][3][3], res2[4][3][3];
+    float *post_w = nullptr, *post_b = nullptr;        // conv_post [7][32], [1]
+    // chunker
+    float *cwm = nullptr, *cbm = nullptr, *cwa = nullptr, *cba = nullptr;
+    b2::Layer c_up[2], c_res1, c_res2, c_post;
+
+    float *pre_pool = nullptr;                         // [max_sessions][4][80]
+    b2::Workspace ws;
+    size_t host_stage_cap_sessions = 0, host_stage_cap_frames = 0;
+};

@@ -1,0 +1,283 @@
+"""Python face of the B200 TTS tail: owns one C-ABI context per GPU and exposes the three callables the
+reference engine holds (vocoder / chunker / resampler: /root/reference/HelloSippyTTSRT/HelloSippyRTPipe.py:236,237,240)
+plus the fused tail.  torch is used only for device memory and streams."""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, resample_taps
+from ._lib import LAW_ALAW, LAW_NONE, LAW_ULAW, MODE_BF16, MODE_FP32
+
+_MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, MODE_FP32: MODE_FP32, MODE_BF16: MODE_BF16}
+_taps_set = set()
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device (infernos_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def ensure_taps(device: torch.device) -> None:
+    """Hands torchaudio-identical taps to the library once per device (it also has them built in)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _taps_set:
+        return
+    lib = _lib.load()
+    d = resample_taps.down_taps().numpy()
+    u = resample_taps.up_taps().reshape(30).numpy()
+    with torch.cuda.device(idx):
+        _lib.check(lib.b2_set_resample_taps(d.ctypes.data_as(ctypes.c_void_p), u.ctypes.data_as(ctypes.c_void_p)), "set_resample_taps")
+    _taps_set.add(idx)
+
+
+class TTSTail:
+    """One context = packed weights + workspaces + the pre_frames pool of the sessions on one GPU."""
+
+    def __init__(self, device, vocoder_sd: Dict[str, torch.Tensor], chunker_sd: Optional[Dict[str, torch.Tensor]] = None,
+                 mode="bf16", max_sessions: int = 1024, max_windows: int = 1024):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("infernos_b200 runs on CUDA devices only (no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device is visible (infernos_b200 has no CPU fallback)")
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.index)
+        self.mode = _MODES[mode]
+        self.max_sessions, self.max_windows = int(max_sessions), int(max_windows)
+        self.ctx = self.lib.b2_ctx_create(self.index, self.mode, self.max_sessions, self.max_windows)
+        if not self.ctx:
+            raise RuntimeError("b2_ctx_create: " + self.lib.b2_last_error(None).decode())
+        try:
+            self._load(vocoder_sd, self.lib.b2_load_vocoder_tensor)
+            if chunker_sd is not None:
+                self._load(chunker_sd, self.lib.b2_load_chunker_tensor)
+            _lib.check(self.lib.b2_weights_finalize(self.ctx), "weights_finalize")
+            ensure_taps(self.device)
+        except Exception:
+            self.close()
+            raise
+        self.has_chunker = chunker_sd is not None
+
+    def _load(self, sd, fn):
+        for k, v in sd.items():
+            t = v.detach().to("cpu", torch.float32).contiguous()
+            shape = (ctypes.c_int64 * t.dim())(*t.shape)
+            _lib.check(fn(self.ctx, k.encode(), ctypes.c_void_p(t.data_ptr()), shape, t.dim()), f"load {k}")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.b2_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.b2_ctx_device_bytes(self.ctx))
+
+    # ---- the reference's three callables ------------------------------------------------------------
+    def vocoder(self, spectrogram: torch.Tensor) -> torch.Tensor:
+        """SpeechT5HifiGan.forward: (W,T,80) -> (W,256*T); un-batched (T,80) -> (256*T,)."""
+        squeeze = spectrogram.dim() == 2
+        x = spectrogram.unsqueeze(0) if squeeze else spectrogram
+        in_dtype = x.dtype
+        x = _require_cuda(x.to(torch.float32), torch.float32, "spectrogram")
+        W, T, nm = x.shape
+        if nm != 80:
+            raise RuntimeError(f"spectrogram must have 80 mel bins, got {nm}")
+        out = torch.empty(W, T * 256, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_vocoder_forward(self.ctx, x.data_ptr(), W, T, out.data_ptr(), _stream_ptr(x.device)), "vocoder_forward")
+        out = out.to(in_dtype) if in_dtype != torch.float32 else out
+        return out.squeeze(0) if squeeze else out
+
+    def chunker(self, mel: torch.Tensor, audio: torch.Tensor) -> torch.Tensor:
+        """AmendmentNetwork1.forward: mel (W,12,80), audio (W,3072) -> (W,2048)."""
+        in_dtype = audio.dtype
+        m = _require_cuda(mel.to(torch.float32), torch.float32, "mel")
+        a = _require_cuda(audio.to(torch.float32), torch.float32, "audio")
+        W = a.size(0)
+        if tuple(m.shape) != (W, 12, 80) or a.size(1) != 3072:
+            raise RuntimeError(f"chunker expects mel (W,12,80) and audio (W,3072), got {tuple(m.shape)} and {tuple(a.shape)}")
+        out = torch.empty(W, 2048, device=a.device, dtype=torch.float32)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_chunker_forward(self.ctx, m.data_ptr(), a.data_ptr(), W, out.data_ptr(), _stream_ptr(a.device)), "chunker_forward")
+        return out.to(in_dtype) if in_dtype != torch.float32 else out
+
+    def resampler(self, audio: torch.Tensor) -> torch.Tensor:
+        """torchaudio Resample(16000, 8000): (..., L) -> (..., ceil(L/2))."""
+        return resample_2to1(audio)
+
+    # ---- fused tail ----------------------------------------------------------------------------------
+    def tail(self, slots: torch.Tensor, mel: torch.Tensor, law: int = LAW_ULAW, want_g711: bool = True,
+             want_audio: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """slots (B,) int32 cuda, mel (B,n,80) fp32 cuda -> (g711 (B,n*128) uint8 | None, audio8k (B,n*128) fp32 | None)."""
+        s = _require_cuda(slots, torch.int32, "slots")
+        m = _require_cuda(mel, torch.float32, "mel")
+        B, n, nm = m.shape
+        if nm != 80 or s.numel() != B:
+            raise RuntimeError("tail expects mel (B,n,80) and slots (B,)")
+        g = torch.empty(B, n * 128, device=m.device, dtype=torch.uint8) if want_g711 else None
+        a = torch.empty(B, n * 128, device=m.device, dtype=torch.float32) if want_audio else None
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_tts_tail(self.ctx, s.data_ptr(), m.data_ptr(), B, n, law if want_g711 else LAW_NONE,
+                                            g.data_ptr() if g is not None else None, a.data_ptr() if a is not None else None,
+                                            _stream_ptr(m.device)), "tts_tail")
+        return g, a
+
+    def tail_host(self, slots: torch.Tensor, mel: torch.Tensor, out_g711: Optional[torch.Tensor], out_audio: Optional[torch.Tensor] = None,
+                  law: int = LAW_ULAW) -> None:
+        """End-to-end entry with HOST (ideally pinned) tensors; returns after the outputs are in host memory."""
+        if slots.is_cuda or mel.is_cuda:
+            raise RuntimeError("tail_host takes host tensors")
+        B, n, _ = mel.shape
+        assert slots.dtype == torch.int32 and mel.dtype == torch.float32 and slots.is_contiguous() and mel.is_contiguous()
+        if out_g711 is not None:
+            assert out_g711.dtype == torch.uint8 and out_g711.numel() == B * n * 128 and out_g711.is_contiguous()
+        if out_audio is not None:
+            assert out_audio.dtype == torch.float32 and out_audio.numel() == B * n * 128 and out_audio.is_contiguous()
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_tts_tail_host(self.ctx, slots.data_ptr(), mel.data_ptr(), B, n, law,
+                                                 out_g711.data_ptr() if out_g711 is not None else None,
+                                                 out_audio.data_ptr() if out_audio is not None else None,
+                                                 _stream_ptr(self.device)), "tts_tail_host")
+
+    def profile_begin(self) -> None:
+        _lib.check(self.lib.b2_profile_begin(self.ctx), "profile_begin")
+
+    def profile_end(self):
+        """-> ({class: ms}, {class: launches}) for classes conv_tc, conv_f32, conv_post, resample_g711, other."""
+        ms = (ctypes.c_double * 8)()
+        n = (ctypes.c_uint64 * 8)()
+        _lib.check(self.lib.b2_profile_end(self.ctx, ms, n), "profile_end")
+        names = ["conv_tc", "conv_f32", "conv_post", "resample_g711", "other"]
+        return {k: ms[i] for i, k in enumerate(names)}, {k: int(n[i]) for i, k in enumerate(names)}
+
+    def reset_sessions(self, slots: Sequence[int]) -> None:
+        arr = (ctypes.c_int32 * len(slots))(*[int(s) for s in slots])
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_session_reset(self.ctx, arr, len(slots), _stream_ptr(self.device)), "session_reset")
+
+    def get_pre_frames(self, slot: int) -> torch.Tensor:
+        out = torch.empty(4, 80, dtype=torch.float32)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_session_get_pre_frames(self.ctx, int(slot), out.data_ptr(), _stream_ptr(self.device)), "get_pre_frames")
+        return out
+
+    def set_pre_frames(self, slot: int, frames: torch.Tensor) -> None:
+        f = frames.detach().to("cpu", torch.float32).contiguous()
+        assert tuple(f.shape) == (4, 80)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_session_set_pre_frames(self.ctx, int(slot), f.data_ptr(), _stream_ptr(self.device)), "set_pre_frames")
+
+
+# ---- ctx-less codec / resampler calls --------------------------------------------------------------------
+def _flat_rows(x: torch.Tensor):
+    shape = x.shape
+    return x.reshape(-1, shape[-1]) if x.dim() > 1 else x.reshape(1, -1), shape
+
+
+def resample_2to1(audio: torch.Tensor) -> torch.Tensor:
+    in_dtype = audio.dtype
+    x = _require_cuda(audio.to(torch.float32), torch.float32, "audio")
+    ensure_taps(x.device)
+    rows, shape = _flat_rows(x)
+    L = rows.size(1)
+    out = torch.empty(rows.size(0), (L + 1) // 2, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b2_resample_2to1(rows.data_ptr(), rows.size(0), L, out.data_ptr(), _stream_ptr(x.device)), "resample_2to1")
+    out = out.reshape(tuple(shape[:-1]) + (out.size(1),))
+    return out.to(in_dtype) if in_dtype != torch.float32 else out
+
+
+def resample_1to2(audio: torch.Tensor) -> torch.Tensor:
+    in_dtype = audio.dtype
+    x = _require_cuda(audio.to(torch.float32), torch.float32, "audio")
+    ensure_taps(x.device)
+    rows, shape = _flat_rows(x)
+    L = rows.size(1)
+    out = torch.empty(rows.size(0), 2 * L, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b2_resample_1to2(rows.data_ptr(), rows.size(0), L, out.data_ptr(), _stream_ptr(x.device)), "resample_1to2")
+    out = out.reshape(tuple(shape[:-1]) + (2 * L,))
+    return out.to(in_dtype) if in_dtype != torch.float32 else out
+
+
+def g711_encode(audio: torch.Tensor, law: int = LAW_ULAW) -> torch.Tensor:
+    """float (any shape, cuda) or int16 PCM -> uint8 codes, same shape."""
+    lib = _lib.load()
+    if not audio.is_cuda:
+        raise RuntimeError("g711_encode needs a CUDA tensor (no CPU fallback)")
+    out = torch.empty(audio.shape, device=audio.device, dtype=torch.uint8)
+    with torch.cuda.device(audio.device):
+        if audio.dtype == torch.int16:
+            x = audio.contiguous()
+            _lib.check(lib.b2_g711_encode_i16(x.data_ptr(), x.numel(), law, out.data_ptr(), _stream_ptr(x.device)), "g711_encode_i16")
+        else:
+            x = audio.to(torch.float32).contiguous()
+            _lib.check(lib.b2_g711_encode_f32(x.data_ptr(), x.numel(), law, out.data_ptr(), _stream_ptr(x.device)), "g711_encode_f32")
+    return out
+
+
+def f32_to_pcm16(audio: torch.Tensor) -> torch.Tensor:
+    x = _require_cuda(audio, torch.float32, "audio")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.int16)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b2_f32_to_pcm16(x.data_ptr(), x.numel(), out.data_ptr(), _stream_ptr(x.device)), "f32_to_pcm16")
+    return out
+
+
+def g711_decode(codes: torch.Tensor, law: int = LAW_ULAW, dtype=torch.float32) -> torch.Tensor:
+    x = _require_cuda(codes, torch.uint8, "codes")
+    out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    with torch.cuda.device(x.device):
+        if dtype == torch.int16:
+            _lib.check(_lib.load().b2_g711_decode_i16(x.data_ptr(), x.numel(), law, out.data_ptr(), _stream_ptr(x.device)), "g711_decode_i16")
+        elif dtype == torch.float32:
+            _lib.check(_lib.load().b2_g711_decode_f32(x.data_ptr(), x.numel(), law, out.data_ptr(), _stream_ptr(x.device)), "g711_decode_f32")
+        else:
+            raise RuntimeError("g711_decode: dtype must be float32 or int16")
+    return out
+
+
+def resample_g711_encode(audio16k: torch.Tensor, law: int = LAW_ULAW) -> torch.Tensor:
+    """(rows, L) fp32 @16 kHz -> (rows, ceil(L/2)) G.711 bytes @8 kHz, one fused kernel."""
+    x = _require_cuda(audio16k, torch.float32, "audio16k")
+    ensure_taps(x.device)
+    rows, shape = _flat_rows(x)
+    L = rows.size(1)
+    out = torch.empty(rows.size(0), (L + 1) // 2, device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b2_resample_g711_encode(rows.data_ptr(), rows.size(0), L, law, out.data_ptr(), _stream_ptr(x.device)), "resample_g711_encode")
+    return out.reshape(tuple(shape[:-1]) + (out.size(1),))
+
+
+def g711_decode_upsample(codes: torch.Tensor, law: int = LAW_ULAW) -> torch.Tensor:
+    """(rows, L) G.711 bytes @8 kHz -> (rows, 2L) fp32 @16 kHz."""
+    x = _require_cuda(codes, torch.uint8, "codes")
+    ensure_taps(x.device)
+    rows, shape = _flat_rows(x)
+    L = rows.size(1)
+    out = torch.empty(rows.size(0), 2 * L, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b2_g711_decode_upsample(rows.data_ptr(), rows.size(0), L, law, out.data_ptr(), _stream_ptr(x.device)), "g711_decode_upsample")
+    return out.reshape(tuple(shape[:-1]) + (2 * L,))
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.load().b2_kernel_launch_count())

@@ -1,0 +1,86 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares; the host-side
+helpers (taps, synthetic weights) are deterministic; no compute call is made (there is no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from infernos_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_all_exported(lib):
+    from infernos_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "infernos_b200.h")).read()
+    syms = set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", hdr))
+    assert len(syms) >= 25
+    assert syms == set(_lib.SIGNATURES), (syms ^ set(_lib.SIGNATURES))
+    for s in syms:
+        assert getattr(lib, s) is not None
+    assert lib.b2_abi_version() == 1
+
+
+def test_no_cuda_device_fails_loudly(lib):
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ctx = lib.b2_ctx_create(0, 1, 4, 4)
+    assert not ctx
+    assert b"no CPU fallback" in lib.b2_last_error(None)
+    from infernos_b200 import synth
+    from infernos_b200.engine import TTSTail
+    with pytest.raises(RuntimeError):
+        TTSTail("cuda:0", synth.hifigan_state_dict())
+    with pytest.raises(RuntimeError):
+        TTSTail("cpu", synth.hifigan_state_dict())
+
+
+def test_bad_ctx_arguments(lib):
+    assert not lib.b2_ctx_create(0, 7, 4, 4)
+    assert b"mode" in lib.b2_last_error(None)
+    assert not lib.b2_ctx_create(0, 0, 0, 4)
+
+
+def test_taps_match_torchaudio_golden():
+    from infernos_b200 import resample_taps as rt
+    t = np.load(os.path.join(ROOT, "tests", "golden", "resample_taps.npz"))
+    assert np.array_equal(rt.down_taps().numpy(), t["down"])
+    assert np.array_equal(rt.up_taps().numpy(), t["up"])
+    inc = open(os.path.join(ROOT, "infernos_b200", "csrc", "resample_taps.inc")).read()
+    vals = [float.fromhex(v) for v in re.findall(r"(-?0x[0-9a-f.]+p[+-]\d+)f", inc)]
+    assert len(vals) == 58
+    assert np.array_equal(np.array(vals[:28], dtype=np.float32), t["down"])
+    assert np.array_equal(np.array(vals[28:], dtype=np.float32).reshape(2, 15), t["up"])
+
+
+def test_synthetic_weights_are_deterministic_and_complete():
+    from infernos_b200 import synth
+    a, b = synth.hifigan_state_dict(), synth.hifigan_state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert sum(v.numel() for k, v in a.items() if k not in ("mean", "scale")) == 12_656_257 - 0
+    c = synth.chunker_state_dict()
+    assert sum(v.numel() for v in c.values()) == 549_120
+    try:
+        from transformers import SpeechT5HifiGan, SpeechT5HifiGanConfig
+    except Exception:
+        return
+    m = SpeechT5HifiGan(SpeechT5HifiGanConfig())
+    assert set(m.state_dict().keys()) == set(a.keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(a[k].shape), k
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "infernos_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
