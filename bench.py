@@ -152,14 +152,15 @@ def main_reference(args, rank, world):
 def main_b200(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
-    from infernos_b200 import synth
+    from infernos_b200 import sharding, synth
     from infernos_b200.engine import TTSTail, kernel_launch_count
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    S, F = args.sessions, args.frames
+    F = args.frames
+    first, S = sharding.shard_range(args.sessions * world, world, rank)      # weak scaling: a fixed block of sessions per GPU
     nwin = F // 8
     max_windows = min(S * nwin, args.max_windows)
     tail = TTSTail(dev, synth.hifigan_state_dict(), synth.chunker_state_dict(), mode=args.mode, max_sessions=S, max_windows=max_windows)
@@ -175,11 +176,7 @@ def main_b200(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
 
     def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(ms, device=dev)
 
     # ---- device-resident timing -------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -237,12 +234,8 @@ def main_b200(args, rank, local_rank, world):
                       "avg_launch_ms": round(ms_cls["resample_g711"] / max(n_cls["resample_g711"], 1), 4)}
 
     # ---- control-plane stats gather (the only collective; NCCL) -----------------------------------
-    stats = torch.tensor([float(S), float(args.steps), float(S * F * 128 * args.steps), float(launches)], device=dev, dtype=torch.float64)
-    if world > 1:
-        allstats = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(allstats, stats)
-    else:
-        allstats = [stats]
+    allstats = sharding.gather_stats({"sessions": S, "steps": args.steps, "g711_bytes": S * F * 128 * args.steps,
+                                      "kernel_launches": launches, "device_ms": e0.elapsed_time(e1)}, device=dev)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -262,11 +255,12 @@ def main_b200(args, rank, local_rank, world):
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "streams", "h2d_bytes_per_step": int(mel_h.numel() * 4 + slots_h.numel() * 4) * world,
                     "d2h_bytes_per_step": int(g_h.numel()) * world, "ms_per_step": round(e2e_ms / args.steps, 3)},
-            "gpu_launches": int(sum(float(s[3]) for s in allstats)),
+            "gpu_launches": int(sum(s["kernel_launches"] for s in allstats)),
             "roofline": roofline, "roofline_codec": codec_roof,
             "kernel_ms_per_step": {k: round(v / psteps, 3) for k, v in ms_cls.items()},
             "cpu_baseline": cpu,
-            "per_gpu_stats": [{"sessions": int(s[0]), "steps": int(s[1]), "g711_bytes": int(s[2])} for s in allstats],
+            "per_gpu_stats": [{"sessions": int(s["sessions"]), "steps": int(s["steps"]), "g711_bytes": int(s["g711_bytes"]),
+                               "device_ms": round(s["device_ms"], 3)} for s in allstats],
             "hbm_bytes_ctx": tail.device_bytes,
         }
         print(json.dumps(out), flush=True)

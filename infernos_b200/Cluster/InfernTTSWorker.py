@@ -1,0 +1,80 @@
+"""TTS worker thread with the reference's API (/root/reference/Cluster/InfernTTSWorker.py:56-105):
+InfernTTSWorker(lang, output_sr, device=None), .infer(wi) / .start() / .stop() / .process_batch(wis),
+.get_voice / .get_rand_voice / .get_rand_voice_id, attributes max_batch_size, tts_engine, output_sr.
+
+The reference caps a batch at 8 because its eager tail is launch-bound; the B200 tail wants thousands of
+windows in flight, so max_batch_size defaults to the engine's slot pool.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from infernos_b200.Cluster.InfernBatchedWorker import InfernBatchedWorker
+from infernos_b200.HelloSippyTTSRT.HelloSippyRTPipe import HelloSippyPipeState, HelloSippyPipeStateBatched, HelloSippyPlayRequest, HelloSippyRTPipe
+
+# language -> HF model table of the reference (InfernTTSWorker.py:37-45); resolving these needs the hub
+lang2model = {
+    "en": {},
+    "it": {"model": "Sandiago21/speecht5_finetuned_voxpopuli_it"},
+    "es": {"model": "Sandiago21/speecht5_finetuned_facebook_voxpopuli_spanish"},
+    "fr": {"model": "Sandiago21/speecht5_finetuned_facebook_voxpopuli_french"},
+    "de": {"model": "JFuellem/speecht5_finetuned_voxpopuli_de"},
+    "pt": {"model": "evertonaleixo/speecht5_finetuned_fleurs_ptbr"},
+    "ru": {"model": "zaebee/speecht5_tts_common_ru"},
+    "ja": {"model": "esnya/japanese_speecht5_tts"},
+}
+
+
+def get_torch_hw() -> str:
+    if torch.cuda.is_available():
+        return "cuda"
+    raise AttributeError("Could not find CUDA devices (infernos_b200 is CUDA-only)")
+
+
+class InfernTTSWorker(InfernBatchedWorker):
+    max_batch_size: int = 8
+    debug = False
+    tts_engine: HelloSippyRTPipe
+    output_sr: int
+
+    def __init__(self, lang, output_sr, device=None, **engine_kwa):
+        super().__init__()
+        if device is None:
+            device = get_torch_hw()
+        kwa = dict(lang2model[lang])
+        kwa.update(engine_kwa)
+        self.tts_engine = HelloSippyRTPipe(device, output_sr=output_sr, **kwa)
+        self.output_sr = output_sr
+        self.max_batch_size = engine_kwa.get("max_batch_size", self.tts_engine.tail.max_sessions)
+
+    def process_batch(self, wis: List[HelloSippyPlayRequest]):
+        new_states = [HelloSippyPipeState(self.tts_engine, r) for r in wis]
+        state = HelloSippyPipeStateBatched(new_states, self.tts_engine)
+        while True:
+            try:
+                self.tts_engine.infer(state)
+            except RuntimeError as e:
+                self.handle_runtime_error(e, state, wis)
+                raise
+            if not self.tts_engine.unbatch_and_dispatch(state):
+                break
+
+    def handle_runtime_error(self, e, state, wis: List[HelloSippyPlayRequest]):
+        print(f"InfernTTSWorker.handle_runtime_error: {e}")
+        for d in state.dispatch:                      # end every still-open sentence so callers do not hang
+            if d is not None:
+                try:
+                    d(None)
+                except Exception:
+                    pass
+
+    def get_voice(self, *args):
+        return self.tts_engine.get_voice(*args)
+
+    def get_rand_voice(self):
+        return self.tts_engine.get_rand_voice()
+
+    def get_rand_voice_id(self):
+        return self.tts_engine.get_rand_voice_id()

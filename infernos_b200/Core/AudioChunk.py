@@ -1,0 +1,40 @@
+"""Audio container (mirror of /root/reference/Core/AudioChunk.py:8-24).  resample() runs the library's
+8 kHz <-> 16 kHz polyphase kernels; other rate pairs are not on this path and raise."""
+from __future__ import annotations
+
+import torch
+
+
+class AudioChunk:
+    debug: bool = False
+    samplerate: int
+    audio: torch.Tensor
+    track_id: int = 0
+    active: bool = True
+
+    def __init__(self, audio: torch.Tensor, samplerate: int):
+        assert isinstance(audio, torch.Tensor)
+        self.audio = audio
+        self.samplerate = samplerate
+
+    def resample(self, sample_rate: int):
+        assert sample_rate != self.samplerate
+        from infernos_b200 import engine
+        pair = (self.samplerate, sample_rate)
+        audio = self.audio.to(torch.float)
+        if not audio.is_cuda:
+            if not torch.cuda.is_available():
+                raise RuntimeError("AudioChunk.resample needs a CUDA device (infernos_b200 has no CPU fallback)")
+            audio = audio.cuda()
+        if pair == (8000, 16000):
+            out = engine.resample_1to2(audio)
+        elif pair == (16000, 8000):
+            out = engine.resample_2to1(audio)
+        else:
+            raise RuntimeError(f"AudioChunk.resample: {pair[0]} -> {pair[1]} Hz is not on the accelerated path")
+        self.audio = out.to(device=self.audio.device, dtype=self.audio.dtype)
+        self.samplerate = sample_rate
+        return self
+
+    def duration(self) -> float:
+        return self.audio.size(0) / self.samplerate

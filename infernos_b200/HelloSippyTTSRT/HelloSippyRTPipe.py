@@ -1,0 +1,336 @@
+"""Drop-in for the reference's batched streaming TTS engine, with the tail computed by the B200 library.
+
+Same public names and call signatures as /root/reference/HelloSippyTTSRT/HelloSippyRTPipe.py:
+  HelloSippyPlayRequest (:47-53), HelloSippyPipeState (:59-79), HelloSippyPipeStateBatched (:81-118),
+  HelloSippyRTPipe(device, model, get_processor, output_sr, **kwa) (:139-189), .infer(state) (:191-240),
+  .unbatch_and_dispatch(state) -> bool (:242-259), .get_voice / get_rand_voice / get_rand_voice_id (:261-272),
+  class attributes chunk_size=8, pre_nframes=2, post_nframes=2, model_sr=16000 (:144-153).
+
+What differs, by design:
+  * lines 231-240 (window builder -> vocoder -> chunker -> re-assembly -> resampler) are ONE C-ABI call
+    (b2_tts_tail) when output_sr == 8000; state.pre_frames lives in a per-session slot in HBM.  The three
+    callables the reference holds (self.vocoder, self.chunker, self.resampler) are still there and are used,
+    in the reference's own order, when output_sr == 16000 or fused=False.
+  * the G.711 payload of every call is produced on the GPU in the same pass (state.g711); the reference encodes
+    later, per call, on the CPU of another process (RTP/RTPOutputWorker.py:118).
+  * unbatch_and_dispatch does one device->host copy per call instead of two .item() syncs and one .cpu() per session.
+  * the autoregressive front half (SpeechT5 encoder/decoder/postnet, :111-118, :195-230) is out of this project's
+    scope: it is reached through a small `frontend` object.  SpeechT5Frontend wraps a transformers model and
+    issues the same calls the reference does; tests and benchmarks script it.
+"""
+from __future__ import annotations
+
+import threading
+import uuid
+import weakref
+from typing import Callable, List, Optional
+
+import torch
+
+from infernos_b200._lib import LAW_ALAW, LAW_ULAW
+from infernos_b200.engine import TTSTail
+
+
+class SessCmd:
+    pass
+
+
+class SessSyncCmd(SessCmd):
+    live: tuple
+
+    def __init__(self, sessions):
+        self.live = tuple(sorted(sessions.keys()))
+
+
+class SessDispatchCmd(SessCmd):
+    session: uuid.UUID
+
+    def __init__(self, session_id: uuid.UUID):
+        self.session = session_id
+
+
+class HelloSippyPlayRequest(SessDispatchCmd):
+    text: str
+    speaker: torch.Tensor
+    dispatch: Callable
+
+    def __init__(self, session_id: uuid.UUID, text: str, speaker: torch.Tensor, dispatch: Callable):
+        self.text, self.speaker, self.dispatch = text, speaker, dispatch
+        super().__init__(session_id)
+
+
+def make_tensor(x):
+    return torch.tensor([x], dtype=torch.long)
+
+
+class HelloSippyPipeState:
+    """Per-request state before batching (reference :59-79)."""
+
+    def __init__(self, pp: "HelloSippyRTPipe", req: HelloSippyPlayRequest):
+        self.session, self.dispatch = req.session, req.dispatch
+        text = req.text if pp.cleanup_text is None else pp.cleanup_text(req.text)
+        self.text = text
+        self.inputs = pp.frontend.tokenize(text)
+        self.speaker_embeddings = req.speaker
+        self.encoder_attention_mask = torch.ones_like(self.inputs, dtype=torch.int)
+        self.starts_at = make_tensor(pp.post_nframes // pp.reduction_factor)
+        self.ends_at = make_tensor(-1)
+
+
+class HelloSippyPipeStateBatched:
+    """Batch state (reference :81-118).  pre_frames is a set of slots in the engine's HBM pool."""
+    idx: int = 0
+
+    def __init__(self, states: List[HelloSippyPipeState], pp: "HelloSippyRTPipe"):
+        self.merge(states, pp)
+
+    def merge(self, states: List[HelloSippyPipeState], pp: "HelloSippyRTPipe"):
+        self.dispatch = [s.dispatch for s in states]
+        self.sessions = [s.session for s in states]
+        self.starts_at = torch.cat([s.starts_at for s in states])      # host tensors: no per-session sync later
+        self.ends_at = torch.cat([s.ends_at for s in states])
+        self.slots_host = pp._alloc_slots(len(states))
+        self.slots = torch.tensor(self.slots_host, dtype=torch.int32, device=pp.device)
+        self._release = weakref.finalize(self, pp._free_slots, list(self.slots_host))
+        self.audio = None
+        self.g711 = None
+        self.idx = 0
+        pp.frontend.start(self, states)
+        self.minlen, self.maxlen = pp.frontend.length_bounds(self, pp.minlenratio, pp.maxlenratio)
+
+
+class ScriptedFrontend:
+    """A front half that replays a fixed mel plan (B, N, 80), two frames per decoder step, and scripted stop steps.
+    Stands in for SpeechT5 in tests/benchmarks (the AR decoder is out of scope)."""
+
+    reduction_factor = 2
+    num_mel_bins = 80
+
+    def __init__(self, plan: torch.Tensor, stop_step: Optional[List[int]] = None, maxlen: int = 1 << 30):
+        self.plan, self.stop_step, self.maxlen = plan, stop_step or [1 << 30] * plan.size(0), maxlen
+        self.step_no = 0
+
+    def tokenize(self, text):
+        return torch.zeros(1, 1, dtype=torch.long)
+
+    def start(self, state, states):
+        self.step_no = 0
+
+    def length_bounds(self, state, minlenratio, maxlenratio):
+        return 0, self.maxlen
+
+    def step(self, state):
+        s = self.step_no
+        self.step_no += 1
+        spectrum = self.plan[:, 2 * s:2 * s + 2, :]
+        prob = torch.tensor([[1.0, 1.0] if s >= st else [0.0, 0.0] for st in self.stop_step])
+        return spectrum, prob
+
+    def postnet(self, spectrogram):
+        return spectrogram
+
+
+class SpeechT5Frontend:
+    """The reference's front half on a transformers SpeechT5ForTextToSpeech (context glue, plain torch):
+    encoder once per batch (:111-118), then per step prenet -> wrapped_decoder(KV cache) -> feat_out / prob_out
+    (:195-229) and the postnet (:230)."""
+
+    def __init__(self, model, processor):
+        self.model, self.processor = model, processor
+        self.reduction_factor = model.config.reduction_factor
+        self.num_mel_bins = model.config.num_mel_bins
+
+    def tokenize(self, text):
+        return self.processor(text=text, return_tensors="pt")["input_ids"]
+
+    def start(self, state, states):
+        dev = self.model.device
+        n = max(s.inputs.size(1) for s in states)
+        pad = lambda t: torch.nn.functional.pad(t, (0, n - t.size(1)))
+        state.inputs = torch.cat([pad(s.inputs) for s in states]).to(dev)
+        state.encoder_attention_mask = torch.cat([pad(s.encoder_attention_mask) for s in states]).to(dev)
+        state.speaker_embeddings = torch.cat([s.speaker_embeddings for s in states]).to(dev)
+        enc = self.model.speecht5.encoder(input_values=state.inputs, attention_mask=state.encoder_attention_mask, return_dict=True)
+        state.encoder_last_hidden_state = enc.last_hidden_state
+        state.output_sequence = enc.last_hidden_state.new_zeros(state.inputs.size(0), 1, self.num_mel_bins)
+        state.past_key_values = None
+
+    def length_bounds(self, state, minlenratio, maxlenratio):
+        n = state.encoder_last_hidden_state.size(1)
+        return int(n * minlenratio / self.reduction_factor), int(n * maxlenratio / self.reduction_factor)
+
+    @torch.no_grad()
+    def step(self, state):
+        m = self.model
+        B = state.output_sequence.size(0)
+        hs = m.speecht5.decoder.prenet(state.output_sequence, state.speaker_embeddings)[:, -1:]
+        out = m.speecht5.decoder.wrapped_decoder(hidden_states=hs, attention_mask=None, encoder_hidden_states=state.encoder_last_hidden_state,
+                                                 encoder_attention_mask=state.encoder_attention_mask, past_key_values=state.past_key_values,
+                                                 use_cache=True, output_attentions=False, return_dict=True)
+        last = out.last_hidden_state[:, -1, :]
+        state.past_key_values = out.past_key_values
+        spectrum = m.speech_decoder_postnet.feat_out(last).view(B, self.reduction_factor, self.num_mel_bins)
+        state.output_sequence = torch.cat((state.output_sequence, spectrum[:, -1:, :]), dim=1)
+        prob = m.speech_decoder_postnet.prob_out(last).sigmoid()
+        return spectrum, prob
+
+    @torch.no_grad()
+    def postnet(self, spectrogram):
+        return self.model.speech_decoder_postnet.postnet(spectrogram)
+
+
+class HelloSippyRTPipe:
+    minlenratio: float = 0.0
+    maxlenratio: float = 20.0
+    threshold: float = 0.5
+    chunk_size: int = 8
+    pre_nframes: int = 2
+    post_nframes: int = 2
+    model_sr: int = 16000
+    output_sr: int = 16000
+    default_model = "microsoft/speecht5_tts"
+    cleanup_text: Optional[Callable] = None
+
+    def __init__(self, device, model=default_model, get_processor: Optional[Callable] = None, output_sr: int = output_sr, **kwa):
+        """kwa (beyond the reference's cleanup_text and SpeechT5Config overrides):
+          frontend            object with tokenize/start/length_bounds/step/postnet (default: SpeechT5Frontend on `model`)
+          vocoder_state_dict  SpeechT5HifiGan weights (default: `microsoft/speecht5_hifigan` via transformers, needs the hub)
+          chunker_state_dict  AmendmentNetwork1 weights (default: synthetic when vocoder weights are synthetic)
+          mode                'bf16' (tensor cores, default — the reference runs bf16, :57) or 'fp32'
+          law                 'ulaw' (default) or 'alaw' for state.g711
+          max_sessions        size of the pre_frames slot pool; max_windows: workspace in 12-frame windows
+          fused               False forces the three-callable path of the reference
+          speaker_embeddings  list of (1,512) tensors (default: one zero vector; the x-vector dataset needs the hub)
+        """
+        self.cuda_lock = threading.Lock()          # the reference's process-wide torcher mutex (:156), here per engine
+        self.cleanup_text = kwa.pop("cleanup_text", self.cleanup_text)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("HelloSippyRTPipe (B200) needs a CUDA device; there is no CPU fallback")
+        self.output_sr = output_sr
+        if output_sr not in (8000, 16000):
+            raise RuntimeError("output_sr must be 8000 or 16000")
+        frontend = kwa.pop("frontend", None)
+        voc_sd = kwa.pop("vocoder_state_dict", None)
+        chk_sd = kwa.pop("chunker_state_dict", None)
+        mode = kwa.pop("mode", "bf16")
+        self.law = {"ulaw": LAW_ULAW, "alaw": LAW_ALAW}[kwa.pop("law", "ulaw")]
+        max_sessions = kwa.pop("max_sessions", 64)
+        max_windows = kwa.pop("max_windows", max_sessions * 4)
+        self.fused = kwa.pop("fused", True) and output_sr == 8000
+        self.speaker_embeddings = kwa.pop("speaker_embeddings", None) or [torch.zeros(1, 512)]
+        if frontend is None:
+            frontend = self._load_speecht5(model, get_processor, kwa)
+        self.frontend = frontend
+        self.reduction_factor = frontend.reduction_factor
+        if voc_sd is None:
+            voc_sd = self._load_hub_vocoder()
+        if chk_sd is None:
+            raise RuntimeError("chunker_state_dict is required (sobomax/speecht5-rt.post_vocoder.v2 cannot be fetched offline)")
+        self.tail = TTSTail(self.device, voc_sd, chk_sd, mode=mode, max_sessions=max_sessions, max_windows=max_windows)
+        self.device = self.tail.device
+        # the reference's three plug points (:236, :237, :240)
+        self.vocoder = self.tail.vocoder
+        self.chunker = self.tail.chunker
+        self.resampler = self.tail.resampler if self.model_sr != output_sr else None
+        self._free = list(range(max_sessions - 1, -1, -1))
+        self._slot_lock = threading.Lock()
+
+    # ---- optional loaders (need network / local HF cache; not used by tests) ------------------------------
+    def _load_speecht5(self, model, get_processor, kwa):
+        from transformers import SpeechT5Config, SpeechT5ForTextToSpeech, SpeechT5Processor
+        mc = SpeechT5Config.from_pretrained(model, **kwa)
+        proc = SpeechT5Processor.from_pretrained(model, config=mc) if get_processor is None else get_processor(self.device, model, config=mc)
+        m = SpeechT5ForTextToSpeech.from_pretrained(model, config=mc).to(self.device).to(torch.bfloat16).eval()
+        for p in m.parameters():
+            p.requires_grad = False
+        return SpeechT5Frontend(m, proc)
+
+    def _load_hub_vocoder(self):
+        from transformers import SpeechT5HifiGan
+        return SpeechT5HifiGan.from_pretrained("microsoft/speecht5_hifigan").state_dict()
+
+    # ---- slots ---------------------------------------------------------------------------------------------
+    def _alloc_slots(self, n: int) -> List[int]:
+        with self._slot_lock:
+            if n > len(self._free):
+                raise RuntimeError(f"out of session slots ({n} requested, {len(self._free)} free); raise max_sessions")
+            got = [self._free.pop() for _ in range(n)]
+        self.tail.reset_sessions(got)          # state.pre_frames = zeros (:77)
+        return got
+
+    def _free_slots(self, slots: List[int]) -> None:
+        with self._slot_lock:
+            self._free.extend(slots)
+
+    # ---- the engine ----------------------------------------------------------------------------------------
+    def infer(self, state: HelloSippyPipeStateBatched) -> None:
+        with self.cuda_lock:
+            frames = []
+            nframes = 0
+            eframes = self.pre_nframes + self.post_nframes
+            while nframes < self.chunk_size * 4:
+                spectrum, prob = self.frontend.step(state)
+                frames.append(spectrum)
+                nframes += spectrum.size(1)
+                stop = (prob >= self.threshold).sum(dim=1).cpu() > 0
+                fire = (state.ends_at < 0) & (state.minlen <= state.idx) & (stop | (state.maxlen <= state.idx))
+                state.ends_at = torch.where(fire, state.idx + eframes // self.reduction_factor, state.ends_at)
+                state.idx += 1
+            spectrogram = self.frontend.postnet(torch.cat(frames, dim=1))
+            mel = spectrogram.to(device=self.device, dtype=torch.float32).contiguous()
+            if self.fused:
+                state.g711, state.audio = self.tail.tail(state.slots, mel, law=self.law)
+            else:
+                self._infer_three_callables(state, mel)
+
+    def _infer_three_callables(self, state, mel):
+        """Lines 231-240 of the reference, through self.vocoder / self.chunker / self.resampler."""
+        B = mel.size(0)
+        eframes = self.pre_nframes + self.post_nframes
+        pre = torch.stack([self.tail.get_pre_frames(s) for s in state.slots_host]).to(self.device)
+        spectrogram = torch.cat((pre, mel), dim=1)
+        new_pre = spectrogram[:, -eframes:, :]
+        for s, f in zip(state.slots_host, new_pre.cpu()):
+            self.tail.set_pre_frames(s, f)
+        nchunks = spectrogram.size(1) // self.chunk_size
+        spectrogram = torch.cat([spectrogram[:, i * self.chunk_size:(i + 1) * self.chunk_size + eframes, :] for i in range(nchunks)], dim=0).contiguous()
+        audio = self.vocoder(spectrogram)
+        audio = self.chunker(spectrogram, audio)
+        audio = torch.cat(audio.split(B, dim=0), dim=1)
+        state.audio = self.resampler(audio) if self.resampler else audio
+        state.g711 = None
+
+    def unbatch_and_dispatch(self, state: HelloSippyPipeStateBatched) -> bool:
+        sr_rr = self.model_sr // self.output_sr
+        end_idx = state.idx - 1
+        stepsize = 256 * 2 // sr_rr
+        with self.cuda_lock:
+            audio = state.audio.cpu()                       # one D2H for the whole batch
+            asize = audio.size(1)
+            starts, ends = state.starts_at.tolist(), state.ends_at.tolist()
+            for i, dispatch in enumerate(state.dispatch):
+                if dispatch is None:
+                    continue
+                startoff = max(0, asize - (state.idx - starts[i]) * stepsize)
+                endoff = min(asize, asize - ((state.idx - ends[i]) * stepsize if ends[i] >= 0 else 0))
+                assert startoff <= endoff
+                if startoff != endoff:
+                    dispatch(audio[i][startoff:endoff])
+                if 0 <= ends[i] <= end_idx:
+                    dispatch(None)
+                    state.dispatch[i] = None
+            alive = (state.ends_at < 0) | (state.ends_at > end_idx)
+            if not bool(alive.any()):
+                return False
+        return True
+
+    def get_rand_voice_id(self) -> int:
+        return torch.randint(0, len(self.speaker_embeddings), (1,)).item()
+
+    def get_rand_voice(self):
+        s_index = self.get_rand_voice_id()
+        return (self.speaker_embeddings[s_index], s_index)
+
+    def get_voice(self, s_index: int):
+        return self.speaker_embeddings[s_index]

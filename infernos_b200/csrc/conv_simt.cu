@@ -141,42 +141,76 @@ int launch_conv_simt(const ConvArgs &a, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// conv_post: leaky_relu(0.01) -> Conv1d(32 -> 1, k7, pad 3) -> tanh
+// conv_post: leaky_relu(0.01) -> Conv1d(32 -> 1, k7, pad 3) -> tanh.   Memory-bound (128 B in, 4 B out per sample).
+// One CTA = 512 consecutive samples of one window: the 518 x 32 input patch is read once with coalesced 128-bit
+// loads (leaky-ReLU applied on the way), transposed into shared memory as [channel][time]; each thread then
+// slides over 4 consecutive outputs reading three 128-bit words per channel, conflict-free.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_conv_post(const float *__restrict__ in, const float *__restrict__ wt, const float *__restrict__ bias,
-                                                  float *__restrict__ out, long long M, int T) {
+static constexpr int kPostTile = 512;
+static constexpr int kPostLd = kPostTile + 8;      // [c][4 halo | 512 | 4 halo], 16-byte aligned rows
+
+__global__ void __launch_bounds__(128) k_conv_post(const float *__restrict__ in, const float *__restrict__ wt, const float *__restrict__ bias,
+                                                  float *__restrict__ out, int T, int tiles_per_win) {
+    extern __shared__ __align__(16) float xs[];    // [32][kPostLd]
     __shared__ float ws[7 * 32];
-    if (threadIdx.x < 224) ws[threadIdx.x] = wt[threadIdx.x];
-    __syncthreads();
-    const float b = bias[0];
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += stride) {
-        const int t = (int)(r % T);
-        float acc = 0.0f;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 224; i += 128) ws[i] = wt[i];
+    const int w = blockIdx.x / tiles_per_win;
+    const int t0 = (blockIdx.x - w * tiles_per_win) * kPostTile;
+    const float *inw = in + (long long)w * T * 32;
+    // rows t0-4 .. t0+515 -> xs[c][0 .. 519]
+    for (int rb = warp * 32; rb < kPostLd; rb += 128) {
+        const int rl = rb + lane;
+        const int t = t0 - 4 + rl;
+        const bool ok = rl < kPostLd && t >= 0 && t < T;
 #pragma unroll
-        for (int j = 0; j < 7; j++) {
-            const int tt = t + j - 3;
-            if (tt < 0 || tt >= T) continue;
-            const float4 *p = reinterpret_cast<const float4 *>(in + (r + j - 3) * 32);
-#pragma unroll
-            for (int c4 = 0; c4 < 8; c4++) {
-                const float4 v = __ldg(p + c4);
-                acc = fmaf(ws[j * 32 + c4 * 4 + 0], lrelu(v.x, 0.01f), acc);
-                acc = fmaf(ws[j * 32 + c4 * 4 + 1], lrelu(v.y, 0.01f), acc);
-                acc = fmaf(ws[j * 32 + c4 * 4 + 2], lrelu(v.z, 0.01f), acc);
-                acc = fmaf(ws[j * 32 + c4 * 4 + 3], lrelu(v.w, 0.01f), acc);
+        for (int c4 = 0; c4 < 8; c4++) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) v = __ldg(reinterpret_cast<const float4 *>(inw + (long long)t * 32 + c4 * 4));
+            if (rl < kPostLd) {
+                xs[(c4 * 4 + 0) * kPostLd + rl] = lrelu(v.x, 0.01f);
+                xs[(c4 * 4 + 1) * kPostLd + rl] = lrelu(v.y, 0.01f);
+                xs[(c4 * 4 + 2) * kPostLd + rl] = lrelu(v.z, 0.01f);
+                xs[(c4 * 4 + 3) * kPostLd + rl] = lrelu(v.w, 0.01f);
             }
         }
-        out[r] = tanhf(acc + b);
+    }
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int c = 0; c < 32; c++) {
+        const float *row = xs + c * kPostLd + tid * 4;           // row[4 + e + j - 3] is x[t0 + 4*tid + e + j - 3]
+        const float4 a = *reinterpret_cast<const float4 *>(row);
+        const float4 b = *reinterpret_cast<const float4 *>(row + 4);
+        const float4 d = *reinterpret_cast<const float4 *>(row + 8);
+        const float x[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const float wv = ws[j * 32 + c];
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[e] = fmaf(wv, x[1 + e + j], acc[e]);
+        }
+    }
+    const int t = t0 + tid * 4;
+    if (t < T) {      // T is a multiple of 4 (256 samples per frame)
+        const float b = bias[0];
+        *reinterpret_cast<float4 *>(out + (long long)w * T + t) = make_float4(tanhf(acc[0] + b), tanhf(acc[1] + b), tanhf(acc[2] + b), tanhf(acc[3] + b));
     }
 }
 
 int launch_conv_post(const float *in, const float *wt, const float *bias, float *out, int W, int T, cudaStream_t st) {
-    const long long M = (long long)W * T;
-    if (M <= 0) return 0;
-    long long blocks = (M + 255) / 256;
-    long long cap = (long long)sm_count() * 16;
-    k_conv_post<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(in, wt, bias, out, M, T);
+    if (W <= 0 || T <= 0) return 0;
+    if (T % 4) return set_error("conv_post: T must be a multiple of 4");
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    B2_CUDA_OK(cudaGetDevice(&dev));
+    const size_t smem = (size_t)32 * kPostLd * sizeof(float);
+    if (dev < 64 && !attr_set[dev]) {
+        B2_CUDA_OK(cudaFuncSetAttribute(k_conv_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev] = true;
+    }
+    const int tiles = cdiv(T, kPostTile);
+    k_conv_post<<<(unsigned)((long long)W * tiles), 128, smem, st>>>(in, wt, bias, out, T, tiles);
     B2_LAUNCH_OK("k_conv_post");
     return 0;
 }
