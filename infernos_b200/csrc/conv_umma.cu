@@ -17,6 +17,8 @@
 #include "conv_umma.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
+#include <algorithm>
 #include <mutex>
 
 namespace b2 {
@@ -40,6 +42,9 @@ struct UmmaParams {
     int period;       // row period between the windows of a tile (T + pad), or 1<<30
     int tiles_per_win;// ceil(T / 128) when nseg == 1
     int stages;       // B ring depth
+    int mt;           // 128-row M sub-tiles per CTA (tall tiles for the thin layers: 4 at C=32, 2 at C=64)
+    int flags;        // bit 0: skip the generic->async proxy fence after the A-tile barrier (experiment)
+    unsigned long long m_period, m_tpw, m_ntiles;   // ceil(2^40 / d) for period, tiles_per_win, ntiles (see fdiv)
 };
 
 // ---------------------------------------------------------------------------------------------------- PTX wrappers
@@ -104,6 +109,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
     return d;
 }
 
+// n / d for 0 <= n < 2^24, d < 2^16, with m = ceil(2^40 / d): a multiply and a shift instead of a ~40-instruction division
+__device__ __forceinline__ int fdiv(int n, unsigned long long m) { return (int)(((unsigned long long)(unsigned)n * m) >> 40); }
+
 __device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.0f ? v : v * slope; }
 
 // ---------------------------------------------------------------------------------------------------- kernel
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_umma(const __grid_constant__ 
     // ---- tile coordinates
     int w0, t0;
     if (p.nseg > 1) { w0 = blockIdx.x * p.nseg; t0 = 0; }
-    else { w0 = blockIdx.x / p.tiles_per_win; t0 = (blockIdx.x - w0 * p.tiles_per_win) * 128; }
+    else { w0 = fdiv(blockIdx.x, p.m_tpw); t0 = (blockIdx.x - w0 * p.tiles_per_win) * 128 * p.mt; }
     const int n0 = blockIdx.y * N_TILE;
 
     if (threadIdx.x == 0) {
@@ -138,7 +146,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_umma(const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)N_TILE) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(N_TILE * p.mt)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
@@ -151,13 +159,14 @@ __global__ void __launch_bounds__(kThreads) k_conv_umma(const __grid_constant__ 
         // =========================== A producer: tile rows + halo, once ===========================
         const int tid = threadIdx.x;
         const uint32_t sA_u32 = smem_u32(sA);
-        const int cpr = KB / 8;                       // 16-byte pieces per row per K block
+        const int cshift = (KB == 64) ? 3 : 2;        // 16-byte pieces per row per K block = 1 << cshift
+        const int cpr = 1 << cshift;
         const int pieces = p.R * cpr;
         for (int kb = 0; kb < p.nkb; kb++) {
             for (int q = tid; q < pieces; q += 128) {
-                const int r = q / cpr, c = q - r * cpr;
+                const int r = q >> cshift, c = q & (cpr - 1);
                 const int u = r - p.pad;
-                const int s = (u >= 0) ? u / p.period : 0;
+                const int s = (u >= 0 && p.nseg > 1) ? fdiv(u, p.m_period) : 0;
                 const int t = t0 + (u - s * p.period);
                 const int w = w0 + s;
                 const bool ok = (t >= 0) && (t < p.T) && (s < p.nseg) && (w < p.W);
@@ -169,8 +178,9 @@ __global__ void __launch_bounds__(kThreads) k_conv_umma(const __grid_constant__ 
         // =========================== epilogue ===========================
         mbar_wait(bar_acc, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int m = warp * 32 + lane;
-        const int s = m / p.period;
+        for (int sub = 0; sub < p.mt; sub++) {
+        const int m = sub * 128 + warp * 32 + lane;
+        const int s = (p.nseg > 1) ? fdiv(m, p.m_period) : 0;
         const int t = t0 + (m - s * p.period);
         const int w = w0 + s;
         const bool ok = (t < p.T) && (s < p.nseg) && (w < p.W);
@@ -178,7 +188,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_umma(const __grid_constant__ 
 #pragma unroll 1
         for (int c0 = 0; c0 < N_TILE; c0 += 32) {
             uint32_t acc[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);   // warp-collective: no divergence before it
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * N_TILE + c0), acc);   // warp-collective: no divergence before it
             if (!ok) continue;
             float v[32];
 #pragma unroll
@@ -220,6 +230,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_umma(const __grid_constant__ 
                 }
             }
         }
+        }
     } else if (warp == 4) {
         // =========================== B producer (TMA) ===========================
         if (lane == 0) {
@@ -246,18 +257,19 @@ __global__ void __launch_bounds__(kThreads) k_conv_umma(const __grid_constant__ 
             int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
             for (int kb = 0; kb < p.nkb; kb++) {
                 mbar_wait(bar_a_full + 8 * kb, 0);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA (async proxy) reads
+                if (!(p.flags & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA (async proxy) reads
                 for (int j = 0; j < p.taps; j++) {
                     mbar_wait(bar_b_full + 8 * stage, phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t b_base = smem_u32(sB + (size_t)stage * b_stage_bytes);
-                    for (int ks = 0; ks < ksteps; ks++) {
-                        const uint32_t a_addr = sA_u32 + (uint32_t)((((kb * (KB / 8) + ks * 2) * p.R) + j * p.dil) * 16);
-                        const uint64_t adesc = smem_desc(a_addr, a_lbo, 128u, 0u);
-                        const uint64_t bdesc = smem_desc(b_base + ks * 32, 0u, b_sbo, b_layout);
-                        umma_f16(tmem_base, adesc, bdesc, idesc, accum);
-                        accum = 1;
-                    }
+                    for (int sub = 0; sub < p.mt; sub++)
+                        for (int ks = 0; ks < ksteps; ks++) {
+                            const uint32_t a_addr = sA_u32 + (uint32_t)((((kb * (KB / 8) + ks * 2) * p.R) + sub * 128 + j * p.dil) * 16);
+                            const uint64_t adesc = smem_desc(a_addr, a_lbo, 128u, 0u);
+                            const uint64_t bdesc = smem_desc(b_base + ks * 32, 0u, b_sbo, b_layout);
+                            umma_f16(tmem_base + (uint32_t)(sub * N_TILE), adesc, bdesc, idesc, (accum | (uint32_t)ks) ? 1u : 0u);
+                        }
+                    accum = 1;
                     umma_commit(bar_b_empty + 8 * stage);   // frees the B slot when these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -270,7 +282,269 @@ __global__ void __launch_bounds__(kThreads) k_conv_umma(const __grid_constant__ 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 5) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)N_TILE) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(N_TILE * p.mt)) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- kernel v2
+// Persistent, fully pipelined variant (the default).  One CTA per SM (up to three for the thin layers) loops over tiles;
+// four roles run concurrently on different tiles, connected by mbarrier pipelines:
+//   warps 6-9  A producers : cp.async the next tile's rows+halo into a double-buffered A region (per-K-block full/empty
+//                            barriers, so a K block is refilled as soon as the MMAs that read it have retired)
+//   warp  4    B producer  : TMA weight ring, or -- when all taps of the layer fit -- weights loaded ONCE and kept resident
+//   warp  5    MMA issuer  : tcgen05.mma into one of TWO TMEM accumulators
+//   warps 0-3  epilogue    : tcgen05.ld -> shared-memory transpose -> coalesced 128-bit residual loads / stores
+//                            (8 lanes cover 128 contiguous bytes of one output row), overlapping the next tile's MMAs
+struct UmmaParams2 {
+    UmmaParams b;
+    int mtiles, ntiles, total_tiles;
+    int nA;            // A buffers: 2, or 1 when two do not fit (per-K-block recycling still overlaps the refill)
+    int resident;      // all (K-block, tap) weight tiles stay in shared memory
+    int rows_per_thr;  // A rows handled by one producer thread per K block
+};
+
+static constexpr int kThreads2 = 320;
+static constexpr int kStageLd = 36;                       // floats per staged row (32 + 4 pad: conflict-free 128-bit access)
+static constexpr int kStageBytes = 4 * 32 * kStageLd * 4; // four epilogue warps
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int N_TILE, int MINB>
+__global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_constant__ CUtensorMap tmap_w, const UmmaParams2 pp) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const UmmaParams &p = pp.b;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = p.KB;
+    const uint32_t b_tile_bytes = (uint32_t)N_TILE * KB * 2;
+    const uint32_t a_bytes = ((uint32_t)p.R * p.Cin * 2 + 15) & ~15u;
+    const int nB = pp.resident ? p.nkb * p.taps : p.stages;
+    uint8_t *sB = smem;
+    uint8_t *sA = smem + (size_t)nB * b_tile_bytes;
+    float *sStage = reinterpret_cast<float *>(sA + (size_t)pp.nA * a_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(sStage) + kStageBytes);
+    // barrier map: [0,4) b_full  [4,8) b_empty  [8,24) a_full[2][8]  [24,40) a_empty[2][8]  [40,42) acc_full  [42,44) acc_empty
+    const uint32_t bar0 = smem_u32(bars);
+    auto B_FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto B_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(4 + s); };
+    auto A_FULL = [&](int buf, int kb) { return bar0 + 8u * (uint32_t)(8 + buf * 8 + kb); };
+    auto A_EMPTY = [&](int buf, int kb) { return bar0 + 8u * (uint32_t)(24 + buf * 8 + kb); };
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (uint32_t)(40 + a); };
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (uint32_t)(42 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 44);
+
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
+        for (int s = 0; s < 4; s++) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
+        for (int b = 0; b < 2; b++)
+            for (int k = 0; k < 8; k++) { mbar_init(A_FULL(b, k), 128); mbar_init(A_EMPTY(b, k), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * N_TILE)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto tile_coords = [&](int tile, int &w0, int &t0, int &n0) {
+        const int mt = (pp.ntiles > 1) ? fdiv(tile, p.m_ntiles) : tile;
+        n0 = (tile - mt * pp.ntiles) * N_TILE;
+        if (p.nseg > 1) { w0 = mt * p.nseg; t0 = 0; }
+        else { w0 = fdiv(mt, p.m_tpw); t0 = (mt - w0 * p.tiles_per_win) * 128; }
+    };
+
+    if (warp < 4) {
+        // =========================== epilogue ===========================
+        float *stg = sStage + warp * 32 * kStageLd;
+        const int sub_r = lane >> 3, c4 = lane & 7;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x, ++it) {
+            int w0, t0, n0;
+            tile_coords(tile, w0, t0, n0);
+            const int acc = it & 1, use = it >> 1;
+            const int m = warp * 32 + lane;
+            const int s = (p.nseg > 1) ? fdiv(m, p.m_period) : 0;
+            const int t = t0 + (m - s * p.period);
+            const int w = w0 + s;
+            const int grow_own = ((t < p.T) && (s < p.nseg) && (w < p.W)) ? (w * p.T + t) : -1;
+            int grow[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) grow[i] = __shfl_sync(0xffffffffu, grow_own, i * 4 + sub_r);
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * N_TILE) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                const int col = n0 + c0 + c4 * 4;
+                const float4 bias = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
+                if (c0 == 0) {
+                    mbar_wait(ACC_FULL(acc), (uint32_t)(use & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                {
+                    uint32_t a32[32];
+                    tmem_ld32(tmem_acc + (uint32_t)c0, a32);
+                    if (c0 + 32 >= N_TILE) {
+                        // last read of this accumulator: hand it back to the MMA warp
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        *reinterpret_cast<uint4 *>(stg + lane * kStageLd + i * 4) = make_uint4(a32[4 * i], a32[4 * i + 1], a32[4 * i + 2], a32[4 * i + 3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    float4 res[4], accs[4];
+                    if (p.residual) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            res[i] = grow[h * 4 + i] >= 0 ? *reinterpret_cast<const float4 *>(p.residual + (size_t)grow[h * 4 + i] * p.N + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (p.acc_src) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            accs[i] = grow[h * 4 + i] >= 0 ? *reinterpret_cast<const float4 *>(p.acc_src + (size_t)grow[h * 4 + i] * p.N + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int g = grow[h * 4 + i];
+                        if (g < 0) continue;
+                        float4 v = *reinterpret_cast<const float4 *>(stg + ((h * 4 + i) * 4 + sub_r) * kStageLd + c4 * 4);
+                        v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+                        if (p.residual) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+                        if (p.acc_src) { v.x = accs[i].x + v.x; v.y = accs[i].y + v.y; v.z = accs[i].z + v.z; v.w = accs[i].w + v.w; }
+                        if (p.div != 1.0f) { v.x = __fdiv_rn(v.x, p.div); v.y = __fdiv_rn(v.y, p.div); v.z = __fdiv_rn(v.z, p.div); v.w = __fdiv_rn(v.w, p.div); }
+                        const size_t o = (size_t)g * p.N + col;
+                        if (p.out32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
+                        if (p.outb) {
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
+                            __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
+                            *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 4) {
+        // =========================== B producer (TMA) ===========================
+        if (lane == 0) {
+            if (pp.resident) {
+                mbar_expect_tx(B_FULL(0), (uint32_t)nB * b_tile_bytes);
+                for (int kb = 0; kb < p.nkb; kb++)
+                    for (int j = 0; j < p.taps; j++)
+                        tma_load_3d(smem_u32(sB + (size_t)(kb * p.taps + j) * b_tile_bytes), &tmap_w, B_FULL(0), kb * KB, 0, j);
+            } else {
+                int stage = 0; uint32_t phase = 0;
+                for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x) {
+                    int w0, t0, n0;
+                    tile_coords(tile, w0, t0, n0);
+                    for (int kb = 0; kb < p.nkb; kb++)
+                        for (int j = 0; j < p.taps; j++) {
+                            mbar_wait(B_EMPTY(stage), phase ^ 1);
+                            mbar_expect_tx(B_FULL(stage), b_tile_bytes);
+                            tma_load_3d(smem_u32(sB + (size_t)stage * b_tile_bytes), &tmap_w, B_FULL(stage), kb * KB, n0, j);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t a_lbo = (uint32_t)p.R * 16;
+            const uint32_t b_layout = (KB == 64) ? 2u : 4u;
+            const uint32_t b_sbo = 8u * (uint32_t)KB * 2;
+            const int ksteps = KB / 16;
+            int stage = 0; uint32_t phase = 0;
+            if (pp.resident) { mbar_wait(B_FULL(0), 0); }
+            int it = 0;
+            for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1, use = it >> 1;
+                const int abuf = (pp.nA == 2) ? (it & 1) : 0, ause = (pp.nA == 2) ? (it >> 1) : it;
+                mbar_wait(ACC_EMPTY(acc), (uint32_t)((use & 1) ^ 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sA_u32 = smem_u32(sA + (size_t)abuf * a_bytes);
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * N_TILE);
+                uint32_t accum = 0;
+                for (int kb = 0; kb < p.nkb; kb++) {
+                    mbar_wait(A_FULL(abuf, kb), (uint32_t)(ause & 1));
+                    if (!(p.flags & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    for (int j = 0; j < p.taps; j++) {
+                        uint32_t b_base;
+                        if (pp.resident) b_base = smem_u32(sB + (size_t)(kb * p.taps + j) * b_tile_bytes);
+                        else {
+                            mbar_wait(B_FULL(stage), phase);
+                            b_base = smem_u32(sB + (size_t)stage * b_tile_bytes);
+                        }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        for (int ks = 0; ks < ksteps; ks++) {
+                            const uint32_t a_addr = sA_u32 + (uint32_t)((((kb * (KB / 8) + ks * 2) * p.R) + j * p.dil) * 16);
+                            umma_f16(tmem_acc, smem_desc(a_addr, a_lbo, 128u, 0u), smem_desc(b_base + ks * 32, 0u, b_sbo, b_layout), idesc, accum);
+                            accum = 1;
+                        }
+                        if (!pp.resident) {
+                            umma_commit(B_EMPTY(stage));
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    umma_commit(A_EMPTY(abuf, kb));     // this K block of the A buffer may be refilled once these MMAs retire
+                }
+                umma_commit(ACC_FULL(acc));
+            }
+        }
+        __syncwarp();
+    } else {
+        // =========================== A producers ===========================
+        const int ptid = threadIdx.x - 192;
+        const int cshift = (KB == 64) ? 3 : 2;
+        const int cpr = 1 << cshift;
+        const int rstep = 128 >> cshift;
+        const int r_first = ptid >> cshift, c = ptid & (cpr - 1);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x, ++it) {
+            int w0, t0, n0;
+            tile_coords(tile, w0, t0, n0);
+            const int abuf = (pp.nA == 2) ? (it & 1) : 0, ause = (pp.nA == 2) ? (it >> 1) : it;
+            const uint32_t sA_u32 = smem_u32(sA + (size_t)abuf * a_bytes);
+            int grow[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const int r = r_first + i * rstep;
+                const int u = r - p.pad;
+                const int s = (u >= 0 && p.nseg > 1) ? fdiv(u, p.m_period) : 0;
+                const int t = t0 + (u - s * p.period);
+                const int w = w0 + s;
+                const bool ok = (r < p.R) && (t >= 0) && (t < p.T) && (s < p.nseg) && (w < p.W);
+                grow[i] = ok ? (w * p.T + t) : -1;
+            }
+            for (int kb = 0; kb < p.nkb; kb++) {
+                mbar_wait(A_EMPTY(abuf, kb), (uint32_t)((ause & 1) ^ 1));
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    const int r = r_first + i * rstep;
+                    if (r < p.R) {
+                        const __nv_bfloat16 *src = grow[i] >= 0 ? p.in + (size_t)grow[i] * p.Cin + kb * KB + c * 8 : p.in;
+                        cp_async16(sA_u32 + (uint32_t)(((kb * cpr + c) * p.R + r) * 16), src, grow[i] >= 0 ? 16u : 0u);
+                    }
+                }
+                cp_async_arrive_noinc(A_FULL(abuf, kb));
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * N_TILE)) : "memory");
     }
 }
 
@@ -285,6 +559,11 @@ static bool g_attr_set[64][4] = {};
 static int n_tile_for(const Layer &l) {
     if (l.Cout >= 256) return (l.Cin >= 512) ? 128 : 256;
     return l.Cout;     // 32, 64, 128
+}
+
+static int umma_flags() {
+    static const int f = (getenv("B2_NO_PROXY_FENCE") ? 1 : 0);
+    return f;
 }
 
 int umma_init() {
@@ -336,7 +615,7 @@ static int launch_nt(const CUtensorMap &tm, const UmmaParams &p, dim3 grid, size
     return 0;
 }
 
-int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
+static int launch_conv_umma_v1(const UmmaConvArgs &a, cudaStream_t st) {
     const Layer &l = *a.layer;
     if (!l.tmap || !l.wbf) return set_error("conv_umma: layer has no tensor-core weights (context not in B2_MODE_BF16?)");
     if (a.W <= 0 || a.T <= 0) return 0;
@@ -344,11 +623,21 @@ int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
     UmmaParams p;
     p.in = a.in; p.bias = l.bias; p.residual = a.residual; p.acc_src = a.acc_src; p.out32 = a.out32; p.outb = a.outb;
     p.outb_slope = a.outb_slope; p.div = a.div;
+    p.flags = umma_flags();
     p.W = a.W; p.T = a.T; p.Cin = l.Cin; p.N = l.Cout; p.taps = l.taps; p.dil = l.dil; p.pad = l.pad;
-    p.R = (128 + (l.taps - 1) * l.dil) | 1;
     p.KB = l.Cin >= 64 ? 64 : 32;
     p.nkb = l.Cin / p.KB;
     const int nt = n_tile_for(l);
+    // tall tiles for the thin layers: the per-CTA latency chain (load -> MMA -> epilogue) is amortised over mt x 128 rows
+    static const int mt_env = getenv("B2_UMMA_MT") ? atoi(getenv("B2_UMMA_MT")) : 0;
+    p.mt = 1;
+    if (a.T >= 128 && l.Cout == nt) {
+        int want = (l.Cin <= 32 && nt <= 32) ? 4 : 1;
+        if (mt_env > 0) want = std::min(mt_env, want);
+        while (want > 1 && 128 * want > ((a.T + 127) / 128) * 128) want >>= 1;
+        p.mt = want;
+    }
+    p.R = (128 * p.mt + (l.taps - 1) * l.dil) | 1;
     unsigned mtiles;
     if (a.T < 128) {
         const int G = l.pad;
@@ -357,9 +646,12 @@ int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
         p.tiles_per_win = 1;
         mtiles = (unsigned)cdiv(a.W, p.nseg);
     } else {
-        p.nseg = 1; p.period = 1 << 30; p.tiles_per_win = cdiv(a.T, 128);
+        p.nseg = 1; p.period = 1 << 30; p.tiles_per_win = cdiv(a.T, 128 * p.mt);
         mtiles = (unsigned)((long long)a.W * p.tiles_per_win);
     }
+    p.m_period = ((1ull << 40) + (unsigned long long)p.period - 1) / (unsigned long long)p.period;
+    p.m_tpw = ((1ull << 40) + (unsigned long long)p.tiles_per_win - 1) / (unsigned long long)p.tiles_per_win;
+    p.m_ntiles = 0;
     const size_t a_bytes = ((size_t)p.R * l.Cin * 2 + 15) & ~(size_t)15;
     const size_t b_stage = (size_t)nt * p.KB * 2;
     const size_t tail_bytes = (2 * 8 + kMaxKB + 1) * 8 + 16;
@@ -377,6 +669,96 @@ int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
         case 64: return launch_nt<64>(tm, p, grid, smem, st, 1);
         case 128: return launch_nt<128>(tm, p, grid, smem, st, 2);
         default: return launch_nt<256>(tm, p, grid, smem, st, 3);
+    }
+}
+
+
+static int g_occ2[64][4] = {};
+
+template <int NT, int MINB>
+static int launch_nt2(const CUtensorMap &tm, const UmmaParams2 &p, size_t smem, cudaStream_t st, int slot) {
+    int dev = 0;
+    B2_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 64) return set_error("conv_umma: device index too large");
+    if (!g_occ2[dev][slot]) {
+        B2_CUDA_OK(cudaFuncSetAttribute(k_conv_umma_p<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        g_occ2[dev][slot] = 1;
+    }
+    int occ = 0;
+    B2_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_conv_umma_p<NT, MINB>, kThreads2, smem));
+    occ = std::max(1, std::min(occ, std::min(MINB, 512 / (2 * NT))));
+    const int grid = std::min(p.total_tiles, sm_count() * occ);
+    k_conv_umma_p<NT, MINB><<<grid, kThreads2, smem, st>>>(tm, p);
+    B2_LAUNCH_OK("k_conv_umma_p");
+    return 0;
+}
+
+int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
+    // Two kernels, chosen per layer from the round-1 launch lists (profiles/): the persistent pipelined kernel wins on the
+    // wide layers (stage 0, the upsamplers); the one-tile-per-CTA kernel with many co-resident CTAs wins on the thin ones,
+    // where a tile is too little work to amortise a pipeline hand-off.  B2_UMMA_V1 / B2_UMMA_V2 force one of them.
+    static const bool force_v1 = getenv("B2_UMMA_V1") != nullptr, force_v2 = getenv("B2_UMMA_V2") != nullptr;
+    const Layer &l = *a.layer;
+    const bool wide = l.Cin >= 256 || l.Cout > l.Cin;
+    if (force_v1 || (!force_v2 && !wide)) return launch_conv_umma_v1(a, st);
+    if (!l.tmap || !l.wbf) return set_error("conv_umma: layer has no tensor-core weights (context not in B2_MODE_BF16?)");
+    if (a.W <= 0 || a.T <= 0) return 0;
+    if ((l.taps - 1) * l.dil != 2 * l.pad) return set_error("conv_umma: only 'same' convolutions are supported");
+    UmmaParams2 pp;
+    UmmaParams &p = pp.b;
+    p.in = a.in; p.bias = l.bias; p.residual = a.residual; p.acc_src = a.acc_src; p.out32 = a.out32; p.outb = a.outb;
+    p.outb_slope = a.outb_slope; p.div = a.div;
+    p.flags = umma_flags();
+    p.W = a.W; p.T = a.T; p.Cin = l.Cin; p.N = l.Cout; p.taps = l.taps; p.dil = l.dil; p.pad = l.pad;
+    p.mt = 1;
+    p.R = (128 + (l.taps - 1) * l.dil) | 1;
+    p.KB = l.Cin >= 64 ? 64 : 32;
+    p.nkb = l.Cin / p.KB;
+    const int nt = n_tile_for(l);
+    if (a.T < 128) {
+        const int G = l.pad;
+        p.nseg = std::max(1, (128 + G) / (a.T + G));
+        p.period = a.T + G;
+        p.tiles_per_win = 1;
+        pp.mtiles = cdiv(a.W, p.nseg);
+    } else {
+        p.nseg = 1; p.period = 1 << 30; p.tiles_per_win = cdiv(a.T, 128);
+        pp.mtiles = (int)((long long)a.W * p.tiles_per_win);
+    }
+    p.m_period = ((1ull << 40) + (unsigned long long)p.period - 1) / (unsigned long long)p.period;
+    p.m_tpw = ((1ull << 40) + (unsigned long long)p.tiles_per_win - 1) / (unsigned long long)p.tiles_per_win;
+    pp.ntiles = l.Cout / nt;
+    p.m_ntiles = ((1ull << 40) + (unsigned long long)pp.ntiles - 1) / (unsigned long long)pp.ntiles;
+    pp.total_tiles = pp.mtiles * pp.ntiles;
+    const int cpr = p.KB / 8;
+    pp.rows_per_thr = cdiv(p.R, 128 / cpr);
+    if (pp.rows_per_thr > 12) return set_error("conv_umma: halo too large (%d rows)", p.R);
+    const size_t a_bytes = ((size_t)p.R * l.Cin * 2 + 15) & ~(size_t)15;
+    const size_t b_tile = (size_t)nt * p.KB * 2;
+    const size_t fixed = kStageBytes + 48 * 8 + 16;
+    const size_t budget = 225 * 1024;
+    const size_t all_w = (size_t)p.nkb * l.taps * b_tile;
+    // weights stay resident when the whole CTA then still fits three to an SM; otherwise they stream through a TMA ring
+    pp.resident = (pp.ntiles == 1 && all_w + 2 * a_bytes + fixed <= 72 * 1024) ? 1 : 0;
+    size_t b_bytes;
+    if (pp.resident) { b_bytes = all_w; p.stages = 0; pp.nA = 2; }
+    else {
+        int stages = 4;
+        pp.nA = 2;
+        while (stages > 2 && stages * b_tile + pp.nA * a_bytes + fixed > budget) stages--;
+        if (stages * b_tile + pp.nA * a_bytes + fixed > budget) { pp.nA = 1; stages = 4; }
+        while (stages > 2 && stages * b_tile + pp.nA * a_bytes + fixed > budget) stages--;
+        p.stages = std::min(stages, std::max(1, p.nkb * l.taps));
+        b_bytes = p.stages * b_tile;
+    }
+    const size_t smem = b_bytes + pp.nA * a_bytes + fixed;
+    if (smem > 227 * 1024) return set_error("conv_umma: tile needs %zu bytes of shared memory", smem);
+    const CUtensorMap &tm = *reinterpret_cast<const CUtensorMap *>(l.tmap);
+    switch (nt) {
+        case 32: return launch_nt2<32, 3>(tm, pp, smem, st, 0);
+        case 64: return launch_nt2<64, 2>(tm, pp, smem, st, 1);
+        case 128: return launch_nt2<128, 1>(tm, pp, smem, st, 2);
+        default: return launch_nt2<256, 1>(tm, pp, smem, st, 3);
     }
 }
 
