@@ -302,24 +302,37 @@ static int vocoder_bf16(b2_ctx *c, const float *xn, int W, int T, float *audio, 
             for (int d = 0; d < 3; d++) {
                 const float *x = (d == 0) ? ws.h : ws.r;
                 const __nv_bfloat16 *xb = (d == 0) ? ws.hb : ws.rb;
+                const bool last = d == 2;
+                // epilogue of the pair: next pair's residual + operand, or the MRF mean (modeling_speecht5.py:3069-3072):
+                // s0 = x0; s0 += x1; (s0 + x2) / 3
+                float *o32 = nullptr; __nv_bfloat16 *ob = nullptr; const float *accs = nullptr; float dv = 1.0f;
+                if (!last) { o32 = ws.r; ob = ws.rb; }
+                else {
+                    accs = (j > 0) ? ws.s0 : nullptr;
+                    if (j < 2) o32 = ws.s0;
+                    else {
+                        dv = 3.0f;
+                        if (i < 3) ob = ws.sb;      // operand of the next upsampler
+                        else o32 = ws.s0;           // fp32 input of conv_post
+                    }
+                }
+                if (pair_supported(c->res1[i][j][d], c->res2[i][j][d], Tc)) {
+                    // the fused kernel reads its operand with a halo while other CTAs write theirs, so the bf16 operand
+                    // ping-pongs between rb and yb (yb is otherwise unused when pairs are fused); fp32 x is row-local, in place
+                    PairArgs pa;
+                    const __nv_bfloat16 *pin = (d == 0) ? ws.hb : (d == 1 ? ws.rb : ws.yb);
+                    if (!last) ob = (d == 0) ? ws.rb : ws.yb;
+                    pa.in = pin; pa.residual = x; pa.conv1 = &c->res1[i][j][d]; pa.conv2 = &c->res2[i][j][d];
+                    pa.acc_src = accs; pa.out32 = o32; pa.outb = ob; pa.outb_slope = 0.1f; pa.mid_slope = 0.1f; pa.div = dv; pa.W = W; pa.T = Tc;
+                    PROF(PC_CONV_TC, launch_resblock_pair(pa, st));
+                    continue;
+                }
                 UmmaConvArgs u1;
                 u1.in = xb; u1.layer = &c->res1[i][j][d]; u1.outb = ws.yb; u1.outb_slope = 0.1f; u1.W = W; u1.T = Tc;
                 PROF(PC_CONV_TC, launch_conv_umma(u1, st));
-                const bool last = d == 2;
                 UmmaConvArgs u2;
                 u2.in = ws.yb; u2.layer = &c->res2[i][j][d]; u2.residual = x; u2.W = W; u2.T = Tc;
-                if (!last) {
-                    u2.out32 = ws.r; u2.outb = ws.rb; u2.outb_slope = 0.1f;          // next pair's residual + operand
-                } else {
-                    // MRF mean (modeling_speecht5.py:3069-3072): s0 = x0; s0 += x1; (s0 + x2) / 3
-                    u2.acc_src = (j > 0) ? ws.s0 : nullptr;
-                    if (j < 2) u2.out32 = ws.s0;
-                    else {
-                        u2.div = 3.0f;
-                        if (i < 3) { u2.outb = ws.sb; u2.outb_slope = 0.1f; }     // operand of the next upsampler
-                        else u2.out32 = ws.s0;                                    // fp32 input of conv_post
-                    }
-                }
+                u2.acc_src = accs; u2.out32 = o32; u2.outb = ob; u2.outb_slope = 0.1f; u2.div = dv;
                 PROF(PC_CONV_TC, launch_conv_umma(u2, st));
             }
         }
