@@ -158,6 +158,7 @@ def main_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner must not land on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=dev)
     F = args.frames
     first, S = sharding.shard_range(args.sessions * world, world, rank)      # weak scaling: a fixed block of sessions per GPU

@@ -26,6 +26,8 @@ namespace b2 {
 
 static constexpr int kThreads = 192;
 static constexpr int kMaxKB = 8;      // Cin <= 512 in blocks of 64
+static constexpr int kStageLd = 36;                       // floats per staged row (32 + 4 pad: conflict-free 128-bit access)
+static constexpr int kStageBytes = 4 * 32 * kStageLd * 4; // epilogue transpose staging, four warps
 
 struct UmmaParams {
     const __nv_bfloat16 *in;
@@ -50,12 +52,13 @@ struct UmmaParams {
 
 // ---------------------------------------------------------------------------------------------------- kernel
 template <int N_TILE>
-__global__ void __launch_bounds__(kThreads) k_conv_umma(const __grid_constant__ CUtensorMap tmap_w, const UmmaParams p) {
+__global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128) ? 2 : 1)) k_conv_umma(const __grid_constant__ CUtensorMap tmap_w, const UmmaParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = p.KB;
     const uint32_t b_stage_bytes = (uint32_t)N_TILE * KB * 2;
-    const uint32_t a_bytes = (uint32_t)p.R * p.Cin * 2;
+    const uint32_t a_raw = (uint32_t)p.R * p.Cin * 2;
+    const uint32_t a_bytes = a_raw > (uint32_t)kStageBytes ? a_raw : (uint32_t)kStageBytes;   // doubles as the epilogue staging area
     uint8_t *sB = smem;
     uint8_t *sA = smem + (size_t)p.stages * b_stage_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sA + ((a_bytes + 15) & ~15u));
@@ -105,63 +108,103 @@ __global__ void __launch_bounds__(kThreads) k_conv_umma(const __grid_constant__ 
                 const int w = w0 + s;
                 const bool ok = (t >= 0) && (t < p.T) && (s < p.nseg) && (w < p.W);
                 const __nv_bfloat16 *src = ok ? p.in + ((size_t)w * p.T + t) * p.Cin + kb * KB + c * 8 : p.in;
-                cp_async16(sA_u32 + (uint32_t)(((kb * cpr + c) * p.R + r) * 16), src, ok ? 16u : 0u);
+                cp_async16(sA_u32 + (uint32_t)(((kb * cpr + c) * p.R + r) * 16), src, (ok && !(p.flags & 8)) ? 16u : 0u);
             }
             cp_async_arrive_noinc(bar_a_full + 8 * kb);
         }
         // =========================== epilogue ===========================
         mbar_wait(bar_acc, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int sub = 0; sub < p.mt; sub++) {
-        const int m = sub * 128 + warp * 32 + lane;
-        const int s = (p.nseg > 1) ? fdiv(m, p.m_period) : 0;
-        const int t = t0 + (m - s * p.period);
-        const int w = w0 + s;
-        const bool ok = (t < p.T) && (s < p.nseg) && (w < p.W);
-        const size_t row_off = ((size_t)w * p.T + t) * p.N + n0;
+        // The A buffer is dead once the accumulator barrier has fired (every MMA that read it has retired): it becomes the
+        // staging area of a per-warp transpose, so that global memory is touched with 8 lanes per 128 contiguous bytes of one
+        // output row (4 whole rows per warp instruction) instead of one 16-byte piece per row per lane.  The what-if runs in
+        // profiles/ put 54 % of the round-1 step time on the un-coalesced version of these accesses.
+        if (!p.residual && !p.acc_src && !p.out32) {
+            // bf16-only output (conv1 of a pair): a lane already owns 64 contiguous bytes of its row, written as four
+            // 128-bit stores; the transpose would only add work (measured 1.16x slower at C=32)
+            for (int sub = 0; sub < p.mt; sub++) {
+                const int m = sub * 128 + warp * 32 + lane;
+                const int s = (p.nseg > 1) ? fdiv(m, p.m_period) : 0;
+                const int t = t0 + (m - s * p.period);
+                const int w = w0 + s;
+                const bool ok = (t < p.T) && (s < p.nseg) && (w < p.W) && !(p.flags & 4);
+                const size_t row_off = ((size_t)w * p.T + t) * p.N + n0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-            uint32_t acc[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * N_TILE + c0), acc);   // warp-collective: no divergence before it
-            if (!ok) continue;
-            float v[32];
+                for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                    uint32_t acc[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * N_TILE + c0), acc);
+                    if (!ok) continue;
+                    uint4 *op = reinterpret_cast<uint4 *>(p.outb + row_off + c0);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c0 + i));
-                v[i] = __uint_as_float(acc[i]) + b.x; v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
-                v[i + 2] = __uint_as_float(acc[i + 2]) + b.z; v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
-            }
-            if (p.residual) {
-                const float4 *rp = reinterpret_cast<const float4 *>(p.residual + row_off + c0);
+                    for (int i = 0; i < 4; i++) {
+                        uint32_t pk[4];
 #pragma unroll
-                for (int i = 0; i < 8; i++) { const float4 r4 = rp[i]; v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w; }
-            }
-            if (p.acc_src) {
-                const float4 *ap = reinterpret_cast<const float4 *>(p.acc_src + row_off + c0);
-#pragma unroll
-                for (int i = 0; i < 8; i++) { const float4 r4 = ap[i]; v[4 * i] = r4.x + v[4 * i]; v[4 * i + 1] = r4.y + v[4 * i + 1]; v[4 * i + 2] = r4.z + v[4 * i + 2]; v[4 * i + 3] = r4.w + v[4 * i + 3]; }
-            }
-            if (p.div != 1.0f) {
-#pragma unroll
-                for (int i = 0; i < 32; i++) v[i] = __fdiv_rn(v[i], p.div);
-            }
-            if (p.out32) {
-                float4 *op = reinterpret_cast<float4 *>(p.out32 + row_off + c0);
-#pragma unroll
-                for (int i = 0; i < 8; i++) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-            if (p.outb) {
-                uint4 *op = reinterpret_cast<uint4 *>(p.outb + row_off + c0);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(lrelu_f(v[8 * i + 2 * e], p.outb_slope), lrelu_f(v[8 * i + 2 * e + 1], p.outb_slope));
-                        pk[e] = *reinterpret_cast<uint32_t *>(&h2);
+                        for (int e = 0; e < 4; e++) {
+                            const float2 b = __ldg(reinterpret_cast<const float2 *>(p.bias + n0 + c0 + 8 * i + 2 * e));
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(lrelu_f(__uint_as_float(acc[8 * i + 2 * e]) + b.x, p.outb_slope),
+                                                                      lrelu_f(__uint_as_float(acc[8 * i + 2 * e + 1]) + b.y, p.outb_slope));
+                            pk[e] = *reinterpret_cast<uint32_t *>(&h2);
+                        }
+                        op[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
-                    op[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
+            }
+        } else {
+        float *stg = reinterpret_cast<float *>(sA) + warp * 32 * kStageLd;
+        const int sub_r = lane >> 3, c4 = lane & 7;
+        for (int sub = 0; sub < p.mt; sub++) {
+            const int m = sub * 128 + warp * 32 + lane;
+            const int s = (p.nseg > 1) ? fdiv(m, p.m_period) : 0;
+            const int t = t0 + (m - s * p.period);
+            const int w = w0 + s;
+            const int grow_own = ((t < p.T) && (s < p.nseg) && (w < p.W) && !(p.flags & 4)) ? (w * p.T + t) : -1;
+            int grow[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) grow[i] = __shfl_sync(0xffffffffu, grow_own, i * 4 + sub_r);
+#pragma unroll 1
+            for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                const int col = n0 + c0 + c4 * 4;
+                const float4 bias = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
+                {
+                    uint32_t a32[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * N_TILE + c0), a32);
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        *reinterpret_cast<uint4 *>(stg + lane * kStageLd + i * 4) = make_uint4(a32[4 * i], a32[4 * i + 1], a32[4 * i + 2], a32[4 * i + 3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    float4 res[4], accs[4];
+                    if (p.residual) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            res[i] = grow[h * 4 + i] >= 0 ? *reinterpret_cast<const float4 *>(p.residual + (size_t)grow[h * 4 + i] * p.N + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (p.acc_src) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            accs[i] = grow[h * 4 + i] >= 0 ? *reinterpret_cast<const float4 *>(p.acc_src + (size_t)grow[h * 4 + i] * p.N + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int g = grow[h * 4 + i];
+                        if (g < 0) continue;
+                        float4 v = *reinterpret_cast<const float4 *>(stg + ((h * 4 + i) * 4 + sub_r) * kStageLd + c4 * 4);
+                        v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+                        if (p.residual) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+                        if (p.acc_src) { v.x = accs[i].x + v.x; v.y = accs[i].y + v.y; v.z = accs[i].z + v.z; v.w = accs[i].w + v.w; }
+                        if (p.div != 1.0f) { v.x = __fdiv_rn(v.x, p.div); v.y = __fdiv_rn(v.y, p.div); v.z = __fdiv_rn(v.z, p.div); v.w = __fdiv_rn(v.w, p.div); }
+                        const size_t o = (size_t)g * p.N + col;
+                        if (p.out32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
+                        if (p.outb) {
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
+                            __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
+                            *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                        }
+                    }
+                }
+                __syncwarp();
             }
         }
         }
@@ -201,7 +244,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_umma(const __grid_constant__ 
                             const uint32_t a_addr = sA_u32 + (uint32_t)((((kb * (KB / 8) + ks * 2) * p.R) + sub * 128 + j * p.dil) * 16);
                             const uint64_t adesc = smem_desc(a_addr, a_lbo, 128u, 0u);
                             const uint64_t bdesc = smem_desc(b_base + ks * 32, 0u, b_sbo, b_layout);
-                            umma_f16(tmem_base + (uint32_t)(sub * N_TILE), adesc, bdesc, idesc, (accum | (uint32_t)ks) ? 1u : 0u);
+                            if (!(p.flags & 2)) umma_f16(tmem_base + (uint32_t)(sub * N_TILE), adesc, bdesc, idesc, (accum | (uint32_t)ks) ? 1u : 0u);
                         }
                     accum = 1;
                     umma_commit(bar_b_empty + 8 * stage);   // frees the B slot when these MMAs retire
@@ -238,8 +281,6 @@ struct UmmaParams2 {
 };
 
 static constexpr int kThreads2 = 320;
-static constexpr int kStageLd = 36;                       // floats per staged row (32 + 4 pad: conflict-free 128-bit access)
-static constexpr int kStageBytes = 4 * 32 * kStageLd * 4; // four epilogue warps
 
 template <int N_TILE, int MINB>
 __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_constant__ CUtensorMap tmap_w, const UmmaParams2 pp) {
@@ -492,7 +533,9 @@ static int n_tile_for(const Layer &l) {
 }
 
 static int umma_flags() {
-    static const int f = (getenv("B2_NO_PROXY_FENCE") ? 1 : 0);
+    // bit 0: skip the proxy fence; what-if switches for profiling only (results are wrong with them):
+    // bit 1: issue no MMAs, bit 2: epilogue touches no global memory, bit 3: A producer loads nothing
+    static const int f = (getenv("B2_NO_PROXY_FENCE") ? 1 : 0) | (getenv("B2_UMMA_WHATIF") ? atoi(getenv("B2_UMMA_WHATIF")) << 1 : 0);
     return f;
 }
 
@@ -562,7 +605,9 @@ static int launch_conv_umma_v1(const UmmaConvArgs &a, cudaStream_t st) {
     static const int mt_env = getenv("B2_UMMA_MT") ? atoi(getenv("B2_UMMA_MT")) : 0;
     p.mt = 1;
     if (a.T >= 128 && l.Cout == nt) {
-        int want = (l.Cin <= 32 && nt <= 32) ? 4 : 1;
+        static const int mt32 = getenv("B2_UMMA_MT32") ? atoi(getenv("B2_UMMA_MT32")) : 4;
+        static const int mt64 = getenv("B2_UMMA_MT64") ? atoi(getenv("B2_UMMA_MT64")) : 1;
+        int want = (l.Cin <= 32 && nt <= 32) ? mt32 : ((l.Cin <= 64 && nt <= 64) ? mt64 : 1);
         if (mt_env > 0) want = std::min(mt_env, want);
         while (want > 1 && 128 * want > ((a.T + 127) / 128) * 128) want >>= 1;
         p.mt = want;
@@ -582,7 +627,7 @@ static int launch_conv_umma_v1(const UmmaConvArgs &a, cudaStream_t st) {
     p.m_period = ((1ull << 40) + (unsigned long long)p.period - 1) / (unsigned long long)p.period;
     p.m_tpw = ((1ull << 40) + (unsigned long long)p.tiles_per_win - 1) / (unsigned long long)p.tiles_per_win;
     p.m_ntiles = 0;
-    const size_t a_bytes = ((size_t)p.R * l.Cin * 2 + 15) & ~(size_t)15;
+    const size_t a_bytes = (std::max<size_t>((size_t)p.R * l.Cin * 2, (size_t)kStageBytes) + 15) & ~(size_t)15;
     const size_t b_stage = (size_t)nt * p.KB * 2;
     const size_t tail_bytes = (2 * 8 + kMaxKB + 1) * 8 + 16;
     int stages = 4;

@@ -1,0 +1,19 @@
+#!/usr/bin/env python
+"""A/B timing of the two fused resample+encode kernels (B2_RS_KERNEL=tile|shfl) at several row lengths."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from infernos_b200 import engine
+def timed(fn, iters=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+for rows, L in ((100_000, 320), (100_000, 1600), (20_000, 8192), (4096, 8192), (1024, 8192)):
+    x = (torch.rand(rows, L, device="cuda") * 2 - 1) * 0.9
+    ms = timed(lambda: engine.resample_g711_encode(x))
+    nb = 9.0 * rows * (L // 2)
+    print(os.environ.get("B2_RS_KERNEL", "auto"), rows, L, round(ms, 4), "ms", round(nb / ms / 1e6), "GB/s", round(nb / ms / 1e6 / 6446.6, 3))
