@@ -220,7 +220,8 @@ int launch_conv_post(const float *in, const float *wt, const float *bias, float 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_build_windows(const int32_t *__restrict__ slots, const float *__restrict__ mel, float *__restrict__ pre_pool,
                                                       const float *__restrict__ mean, const float *__restrict__ scale,
-                                                      float *__restrict__ win_raw, float *__restrict__ win_norm, int B, int nframes) {
+                                                      float *__restrict__ win_raw, float *__restrict__ win_norm, __nv_bfloat16 *__restrict__ win_norm_b,
+                                                      int B, int nframes) {
     const int nwin = nframes / 8;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         const int slot = slots[b];
@@ -234,8 +235,13 @@ __global__ void __launch_bounds__(256) k_build_windows(const int32_t *__restrict
             const int f = 8 * i + fr;
             const float v = (f < 4) ? pre[f * 80 + bin] : m[(f - 4) * 80 + bin];
             win_raw[wbase + e] = v;
-            win_norm[wbase + e] = __fdiv_rn(v - mean[bin], scale[bin]);
+            const float nv = __fdiv_rn(v - mean[bin], scale[bin]);
+            win_norm[wbase + e] = nv;
+            if (win_norm_b) win_norm_b[((long long)b * nwin * 12 + i * 12 + fr) * 128 + bin] = __float2bfloat16_rn(nv);
         }
+        if (win_norm_b)
+            for (int e = threadIdx.x; e < nwin * 12 * 48; e += blockDim.x)
+                win_norm_b[((long long)b * nwin * 12 + e / 48) * 128 + 80 + e % 48] = __float2bfloat16_rn(0.0f);
         __syncthreads();   // every read of pre[] is done before it is overwritten
         for (int e = threadIdx.x; e < 320; e += blockDim.x) pre[e] = m[(nframes - 4) * 80 + e];
         __syncthreads();
@@ -243,27 +249,33 @@ __global__ void __launch_bounds__(256) k_build_windows(const int32_t *__restrict
 }
 
 int launch_build_windows(const int32_t *slots, const float *mel, float *pre_pool, const float *mean, const float *scale,
-                         float *win_raw, float *win_norm, int B, int nframes, cudaStream_t st) {
+                         float *win_raw, float *win_norm, __nv_bfloat16 *win_norm_b, int B, int nframes, cudaStream_t st) {
     if (B <= 0) return 0;
-    k_build_windows<<<B, 256, 0, st>>>(slots, mel, pre_pool, mean, scale, win_raw, win_norm, B, nframes);
+    k_build_windows<<<B, 256, 0, st>>>(slots, mel, pre_pool, mean, scale, win_raw, win_norm, win_norm_b, B, nframes);
     B2_LAUNCH_OK("k_build_windows");
     return 0;
 }
 
 __global__ void __launch_bounds__(256) k_normalise(const float *__restrict__ mel, const float *__restrict__ mean, const float *__restrict__ scale,
-                                                  float *__restrict__ out, size_t n) {
+                                                  float *__restrict__ out, __nv_bfloat16 *__restrict__ out_b, size_t n) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int bin = (int)(i % 80);
-        out[i] = __fdiv_rn(mel[i] - mean[bin], scale[bin]);
+        const size_t row = i / 80;
+        const int bin = (int)(i - row * 80);
+        const float nv = __fdiv_rn(mel[i] - mean[bin], scale[bin]);
+        out[i] = nv;
+        if (out_b) {
+            out_b[row * 128 + bin] = __float2bfloat16_rn(nv);
+            if (bin < 48) out_b[row * 128 + 80 + bin] = __float2bfloat16_rn(0.0f);
+        }
     }
 }
 
-int launch_normalise(const float *mel, const float *mean, const float *scale, float *out, size_t rows, cudaStream_t st) {
+int launch_normalise(const float *mel, const float *mean, const float *scale, float *out, __nv_bfloat16 *out_b, size_t rows, cudaStream_t st) {
     size_t n = rows * 80;
     if (n == 0) return 0;
     size_t blocks = (n + 255) / 256, cap = (size_t)sm_count() * 16;
-    k_normalise<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(mel, mean, scale, out, n);
+    k_normalise<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(mel, mean, scale, out, out_b, n);
     B2_LAUNCH_OK("k_normalise");
     return 0;
 }
@@ -276,7 +288,7 @@ int launch_normalise(const float *mel, const float *mean, const float *scale, fl
 __global__ void __launch_bounds__(192) k_chunker_pre(const float *__restrict__ mel, const float *__restrict__ audio,
                                                     const float *__restrict__ wm, const float *__restrict__ bm,
                                                     const float *__restrict__ wa, const float *__restrict__ ba,
-                                                    float *__restrict__ z0, int W) {
+                                                    float *__restrict__ z0, __nv_bfloat16 *__restrict__ z0b, int W) {
     __shared__ __align__(16) float sm[80 * 12];
     __shared__ __align__(16) float sa[256 * 12];
     const int tid = threadIdx.x;
@@ -305,18 +317,25 @@ __global__ void __launch_bounds__(192) k_chunker_pre(const float *__restrict__ m
                 for (int t = 0; t < 12; t++) acc[t] = fmaf(wv, x[t + k], acc[t]);
             }
         }
-        float *o = z0 + (long long)w * 12 * 192 + tid;
+        if (z0) {
+            float *o = z0 + (long long)w * 12 * 192 + tid;
 #pragma unroll
-        for (int t = 0; t < 12; t++) o[t * 192] = acc[t];
+            for (int t = 0; t < 12; t++) o[t * 192] = acc[t];
+        }
+        if (z0b) {
+            __nv_bfloat16 *o = z0b + (long long)w * 12 * 192 + tid;
+#pragma unroll
+            for (int t = 0; t < 12; t++) o[t * 192] = __float2bfloat16_rn(lrelu(acc[t], 0.01f));
+        }
         __syncthreads();
     }
 }
 
 int launch_chunker_pre(const float *mel, const float *audio, const float *wm, const float *bm, const float *wa, const float *ba,
-                       float *z0, int W, cudaStream_t st) {
+                       float *z0, __nv_bfloat16 *z0b, int W, cudaStream_t st) {
     if (W <= 0) return 0;
     int cap = sm_count() * 8;
-    k_chunker_pre<<<W < cap ? W : cap, 192, 0, st>>>(mel, audio, wm, bm, wa, ba, z0, W);
+    k_chunker_pre<<<W < cap ? W : cap, 192, 0, st>>>(mel, audio, wm, bm, wa, ba, z0, z0b, W);
     B2_LAUNCH_OK("k_chunker_pre");
     return 0;
 }

@@ -34,16 +34,18 @@ int launch_conv_post(const float *in, const float *wt, const float *bias, float 
 // HelloSippyRTPipe.py:231-235: cat(pre_frames, mel) -> windows of 12 frames with stride 8; saves the last 4
 // frames back into the session's slot.  Writes the raw windows (chunker input) and the normalised ones
 // ((x - mean) / scale, modeling_speecht5.py:3055-3056), both [B*nwin][12][80], window index = b*nwin + i.
+// win_norm_b (optional): the normalised windows again as bf16 rows padded to 128 bins (operand of conv_pre on tensor cores)
 int launch_build_windows(const int32_t *slots, const float *mel, float *pre_pool, const float *mean, const float *scale,
-                         float *win_raw, float *win_norm, int B, int nframes, cudaStream_t st);
+                         float *win_raw, float *win_norm, __nv_bfloat16 *win_norm_b, int B, int nframes, cudaStream_t st);
 // plain normalisation for the stand-alone vocoder callable: out = (mel - mean) / scale, n rows of 80
-int launch_normalise(const float *mel, const float *mean, const float *scale, float *out, size_t rows, cudaStream_t st);
+int launch_normalise(const float *mel, const float *mean, const float *scale, float *out, __nv_bfloat16 *out_b, size_t rows, cudaStream_t st);
 
 // chunker prologue (HelloSippyRT.py:221-228): conv_pre_m over mel *viewed* as (80,12) and conv_pre_a over audio
 // *viewed* as (256,12), concatenated -> z0 [W][12][192] channels-last (no activation applied).
 // wm packed [3][80][32], wa packed [3][256][160].
+// z0 fp32 and/or z0b = bf16(leaky_relu(z0, 0.01)) (operand of the first chunker upsampler on tensor cores)
 int launch_chunker_pre(const float *mel, const float *audio, const float *wm, const float *bm, const float *wa, const float *ba,
-                       float *z0, int W, cudaStream_t st);
+                       float *z0, __nv_bfloat16 *z0b, int W, cudaStream_t st);
 // chunker epilogue (HelloSippyRT.py:235-237): out[w][i] = tanh(audio[w][512+i] * lrelu(post[w][i%8][i/8], 0.01))
 int launch_chunker_final(const float *audio, const float *post, float *out, int W, cudaStream_t st);
 // vocoder-only trim for calls that bypass the chunker: out[w][i] = audio[w][512+i]

@@ -31,6 +31,8 @@ struct Workspace {
     float *audio = nullptr;                            // [F*256]
     // chunker, per window
     float *z0 = nullptr, *z1 = nullptr, *z2 = nullptr, *zy = nullptr, *z3 = nullptr, *post = nullptr;
+    __nv_bfloat16 *win_norm_b = nullptr;               // [F][128] bf16, bins 80..127 zero (BF16 mode)
+    __nv_bfloat16 *z0b = nullptr, *z1b = nullptr, *z2b = nullptr, *zyb = nullptr;   // chunker operands (BF16 mode)
     float *audio16k = nullptr;                         // [W][2048]
     int32_t *slots = nullptr;                          // device copy for the host entry point
     float *mel_in = nullptr;                           // device staging for the host entry point

@@ -159,7 +159,18 @@ static int finalize(b2_ctx *c) {
     if (!(w = find(c->voc_raw, "scale", {80}))) return 1;
     if (upload(c, &c->scale, w->data)) return 1;
     if (!(w = find(c->voc_raw, "conv_pre.weight", {512, 80, 7})) || !(b = find(c->voc_raw, "conv_pre.bias", {512}))) return 1;
-    if (pack_conv(c, c->conv_pre, *w, *b, 1, 3, 1, false)) return 1;
+    if (!bf) {
+        if (pack_conv(c, c->conv_pre, *w, *b, 1, 3, 1, false)) return 1;
+    } else {
+        // tensor-core conv_pre: K padded from 80 to 128 mel bins (zeros) so that it is two 64-wide K blocks
+        HostTensor wp;
+        wp.shape = {512, 128, 7};
+        wp.data.assign((size_t)512 * 128 * 7, 0.0f);
+        for (int co = 0; co < 512; co++)
+            for (int ci = 0; ci < 80; ci++)
+                for (int j = 0; j < 7; j++) wp.data[((size_t)co * 128 + ci) * 7 + j] = w->data[((size_t)co * 80 + ci) * 7 + j];
+        if (pack_conv(c, c->conv_pre, wp, *b, 1, 3, 1, true)) return 1;
+    }
     int cin = 512;
     for (int i = 0; i < 4; i++) {
         const int C = STAGE_C[i];
@@ -198,13 +209,13 @@ static int finalize(b2_ctx *c) {
         if (pack_conv(c, tmp, *w, *b, 1, 1, 1, false)) return 1;
         c->cwa = tmp.w32; c->cba = tmp.bias;
         if (!(w = find(c->chk_raw, "upsampler.0.weight", {192, 128, 8})) || !(b = find(c->chk_raw, "upsampler.0.bias", {128}))) return 1;
-        if (pack_convT(c, c->c_up[0], *w, *b, false)) return 1;
+        if (pack_convT(c, c->c_up[0], *w, *b, bf)) return 1;
         if (!(w = find(c->chk_raw, "upsampler.1.weight", {128, 64, 8})) || !(b = find(c->chk_raw, "upsampler.1.bias", {64}))) return 1;
-        if (pack_convT(c, c->c_up[1], *w, *b, false)) return 1;
+        if (pack_convT(c, c->c_up[1], *w, *b, bf)) return 1;
         if (!(w = find(c->chk_raw, "resblock.conv1.weight", {64, 64, 3})) || !(b = find(c->chk_raw, "resblock.conv1.bias", {64}))) return 1;
-        if (pack_conv(c, c->c_res1, *w, *b, 1, 1, 1, false)) return 1;
+        if (pack_conv(c, c->c_res1, *w, *b, 1, 1, 1, bf)) return 1;
         if (!(w = find(c->chk_raw, "resblock.conv2.weight", {64, 64, 3})) || !(b = find(c->chk_raw, "resblock.conv2.bias", {64}))) return 1;
-        if (pack_conv(c, c->c_res2, *w, *b, 3, 3, 1, false)) return 1;
+        if (pack_conv(c, c->c_res2, *w, *b, 3, 3, 1, bf)) return 1;
         if (!(w = find(c->chk_raw, "post_conv.weight", {256, 64, 8})) || !(b = find(c->chk_raw, "post_conv.bias", {256}))) return 1;
         if (pack_conv(c, c->c_post, *w, *b, 1, 0, 24, false)) return 1;
     }
@@ -214,6 +225,9 @@ static int finalize(b2_ctx *c) {
     if (dev_alloc(c, &ws.win_raw, F * 80) || dev_alloc(c, &ws.win_norm, F * 80)) return 1;
     if (dev_alloc(c, &ws.h, F * 8192) || dev_alloc(c, &ws.r, F * 8192) || dev_alloc(c, &ws.s0, F * 8192)) return 1;
     if (bf) {
+        if (dev_alloc(c, &ws.win_norm_b, F * 128)) return 1;
+        if (!c->chk_raw.empty() && (dev_alloc(c, &ws.z0b, Wn * 12 * 192) || dev_alloc(c, &ws.z1b, Wn * 48 * 128) ||
+                                    dev_alloc(c, &ws.z2b, Wn * 192 * 64) || dev_alloc(c, &ws.zyb, Wn * 192 * 64))) return 1;
         if (dev_alloc(c, &ws.c0b, F * 512) || dev_alloc(c, &ws.hb, F * 8192) || dev_alloc(c, &ws.yb, F * 8192) ||
             dev_alloc(c, &ws.rb, F * 8192) || dev_alloc(c, &ws.sb, F * 4096)) return 1;
     } else {
@@ -286,11 +300,13 @@ static int vocoder_fp32(b2_ctx *c, const float *xn, int W, int T, float *audio, 
 
 static int vocoder_bf16(b2_ctx *c, const float *xn, int W, int T, float *audio, cudaStream_t st) {
     Workspace &ws = c->ws;
-    // conv_pre on CUDA cores in fp32 (0.2 % of the FLOPs, K = 560 is not a tensor-core shape); its epilogue writes the
-    // leaky_relu(0.1)'d bf16 operand of the first upsampler directly
-    ConvArgs a = conv_args(c->conv_pre, xn, nullptr, W, T, T, 1.0f);
-    a.out_bf16 = ws.c0b; a.bf16_slope = 0.1f;
-    PROF(PC_CONV_F32, launch_conv_simt(a, st));
+    // conv_pre on tensor cores as well: the normalised mel is handed over as bf16 rows padded to 128 bins; the epilogue
+    // writes the leaky_relu(0.1)'d bf16 operand of the first upsampler
+    {
+        UmmaConvArgs u;
+        u.in = ws.win_norm_b; u.layer = &c->conv_pre; u.outb = ws.c0b; u.outb_slope = 0.1f; u.W = W; u.T = T;
+        PROF(PC_CONV_TC, launch_conv_umma(u, st));
+    }
     const __nv_bfloat16 *stage_in = ws.c0b;
     int Tc = T;
     for (int i = 0; i < 4; i++) {
@@ -350,16 +366,34 @@ static int vocoder_any(b2_ctx *c, const float *xn, int W, int T, float *audio, c
 static int chunker_fwd(b2_ctx *c, const float *win_raw, const float *audio, int W, float *out, cudaStream_t st) {
     Workspace &ws = c->ws;
     if (!c->cwm) return set_error("chunker weights were not loaded into this context");
-    PROF(PC_OTHER, launch_chunker_pre(win_raw, audio, c->cwm, c->cbm, c->cwa, c->cba, ws.z0, W, st));
-    ConvArgs a = conv_args(c->c_up[0], ws.z0, ws.z1, W, 12, 12, 0.01f);
-    PROF(PC_CONV_F32, launch_conv_simt(a, st));
-    a = conv_args(c->c_up[1], ws.z1, ws.z2, W, 48, 48, 0.01f);
-    PROF(PC_CONV_F32, launch_conv_simt(a, st));
-    a = conv_args(c->c_res1, ws.z2, ws.zy, W, 192, 192, 0.01f);
-    PROF(PC_CONV_F32, launch_conv_simt(a, st));
-    a = conv_args(c->c_res2, ws.zy, ws.z3, W, 192, 192, 0.01f);
-    a.residual = ws.z2;
-    PROF(PC_CONV_F32, launch_conv_simt(a, st));
+    if (c->mode == B2_MODE_BF16) {
+        // middle of the chunker on tensor cores (bf16 operands, fp32 accumulate, fp32 residual): 2 upsamplers + the ResBlock
+        PROF(PC_OTHER, launch_chunker_pre(win_raw, audio, c->cwm, c->cbm, c->cwa, c->cba, nullptr, ws.z0b, W, st));
+        UmmaConvArgs u;
+        u.in = ws.z0b; u.layer = &c->c_up[0]; u.outb = ws.z1b; u.outb_slope = 0.01f; u.W = W; u.T = 12;
+        PROF(PC_CONV_TC, launch_conv_umma(u, st));
+        u = UmmaConvArgs();
+        u.in = ws.z1b; u.layer = &c->c_up[1]; u.out32 = ws.z2; u.outb = ws.z2b; u.outb_slope = 0.01f; u.W = W; u.T = 48;
+        PROF(PC_CONV_TC, launch_conv_umma(u, st));
+        u = UmmaConvArgs();
+        u.in = ws.z2b; u.layer = &c->c_res1; u.outb = ws.zyb; u.outb_slope = 0.01f; u.W = W; u.T = 192;
+        PROF(PC_CONV_TC, launch_conv_umma(u, st));
+        u = UmmaConvArgs();
+        u.in = ws.zyb; u.layer = &c->c_res2; u.residual = ws.z2; u.out32 = ws.z3; u.W = W; u.T = 192;
+        PROF(PC_CONV_TC, launch_conv_umma(u, st));
+    } else {
+    PROF(PC_OTHER, launch_chunker_pre(win_raw, audio, c->cwm, c->cbm, c->cwa, c->cba, ws.z0, nullptr, W, st));
+    ConvArgs a0 = conv_args(c->c_up[0], ws.z0, ws.z1, W, 12, 12, 0.01f);
+    PROF(PC_CONV_F32, launch_conv_simt(a0, st));
+    a0 = conv_args(c->c_up[1], ws.z1, ws.z2, W, 48, 48, 0.01f);
+    PROF(PC_CONV_F32, launch_conv_simt(a0, st));
+    a0 = conv_args(c->c_res1, ws.z2, ws.zy, W, 192, 192, 0.01f);
+    PROF(PC_CONV_F32, launch_conv_simt(a0, st));
+    a0 = conv_args(c->c_res2, ws.zy, ws.z3, W, 192, 192, 0.01f);
+    a0.residual = ws.z2;
+    PROF(PC_CONV_F32, launch_conv_simt(a0, st));
+    }
+    ConvArgs a;
     a = conv_args(c->c_post, ws.z3, ws.post, W, 192, 8, 0.01f);
     PROF(PC_CONV_F32, launch_conv_simt(a, st));
     PROF(PC_OTHER, launch_chunker_final(audio, ws.post, out, W, st));
@@ -376,7 +410,7 @@ static int tail_device(b2_ctx *c, const int32_t *d_slots, const float *d_mel, in
         const int W = nb * nwin;
         Workspace &ws = c->ws;
         PROF(PC_OTHER, launch_build_windows(d_slots + b0, d_mel + (size_t)b0 * nframes * 80, c->pre_pool, c->mean, c->scale,
-                                            ws.win_raw, ws.win_norm, nb, nframes, st));
+                                            ws.win_raw, ws.win_norm, ws.win_norm_b, nb, nframes, st));
         if (vocoder_any(c, ws.win_norm, W, 12, ws.audio, st)) return 1;
         if (c->cwm) { if (chunker_fwd(c, ws.win_raw, ws.audio, W, ws.audio16k, st)) return 1; }
         else { PROF(PC_OTHER, launch_trim(ws.audio, ws.audio16k, W, 3072, 512, 2048, st)); }
@@ -496,7 +530,7 @@ int b2_vocoder_forward(b2_ctx *c, const float *d_mel, int W, int T, float *d_aud
     const int w_per_pass = (int)std::max<long long>(1, cap / T);
     for (int w0 = 0; w0 < W; w0 += w_per_pass) {
         const int nw = std::min(w_per_pass, W - w0);
-        if (launch_normalise(d_mel + (size_t)w0 * T * 80, c->mean, c->scale, c->ws.win_norm, (size_t)nw * T, st)) return 1;
+        if (launch_normalise(d_mel + (size_t)w0 * T * 80, c->mean, c->scale, c->ws.win_norm, c->ws.win_norm_b, (size_t)nw * T, st)) return 1;
         if (vocoder_any(c, c->ws.win_norm, nw, T, d_audio + (size_t)w0 * T * 256, st)) return 1;
     }
     return 0;
