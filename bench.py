@@ -27,7 +27,8 @@ if ROOT not in sys.path:
 
 AUDIO_S_PER_FRAME = 256 / 16000.0
 # algorithmic work per 12-frame window
-FLOP_PER_WINDOW_TC = 12 * 2 * (4 * 33.030144e6 + 4 * 1.048576e6)     # upsamplers + ResBlocks, the tcgen05 kernels
+FLOP_PER_WINDOW_TC = 12 * 2 * (4 * 33.030144e6 + 4 * 1.048576e6 + 0.28672e6) + 2 * 10.22e6   # tcgen05 kernels: upsamplers, ResBlocks,
+                                                                                            # conv_pre, chunker upsamplers + ResBlock
 FLOP_PER_WINDOW_ALL = 12 * 273.318e6 + 25.68e6 + 0.057e6 * 4
 CODEC_BYTES_PER_OUT = 9.0                                            # 2 fp32 in + 1 byte out per 8 kHz sample
 
@@ -224,7 +225,7 @@ def main_b200(args, rank, local_rank, world):
     roofline = codec_roof = None
     if tc_ms > 0:
         tf = FLOP_PER_WINDOW_TC * W_step * psteps / (tc_ms / 1e3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "k_conv_umma (76 launches per sub-batch: 4 upsamplers + 72 ResBlock convs)" if args.mode == "bf16" else "k_conv_simt",
+        roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels k_conv_umma / k_conv_umma_p (81 launches per sub-batch: conv_pre, 4 upsamplers, 72 ResBlock convs, 4 chunker convs)" if args.mode == "bf16" else "k_conv_simt",
                     "achieved": round(tf, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(tf / peaks["tf_sustained"], 4),
                     "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)", "traffic": None,
                     "launches": tc_n, "avg_launch_ms": round(tc_ms / max(tc_n, 1), 4), "share_of_step": round(tc_ms / max(sum(ms_cls.values()), 1e-9), 4)}

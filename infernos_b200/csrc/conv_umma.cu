@@ -75,18 +75,45 @@ __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128
     else { w0 = fdiv(blockIdx.x, p.m_tpw); t0 = (blockIdx.x - w0 * p.tiles_per_win) * 128 * p.mt; }
     const int n0 = blockIdx.y * N_TILE;
 
-    if (threadIdx.x == 0) {
+    // Prologue, arranged so that nothing waits for anything it does not need: the TMA thread initialises the barriers and
+    // starts streaming weights at once, the producer warps start the first K block of the A tile, warp 5 allocates TMEM;
+    // only then does the CTA synchronise.  (what-if runs: this fixed per-CTA cost was 43 % of the thin layers' time.)
+    const int total_b = p.nkb * p.taps;
+    int b_issued = 0;
+    if (warp == 4 && lane == 0) {
         if (smem_u32(smem) & 1023u) __trap();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
         for (int s = 0; s < p.stages; s++) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
         for (int k = 0; k < kMaxKB; k++) mbar_init(bar_a_full + 8 * k, 128);
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (; b_issued < p.stages && b_issued < total_b; b_issued++) {        // first round of the ring: every slot is free
+            const int kb = b_issued / p.taps, j = b_issued - kb * p.taps;
+            mbar_expect_tx(bar_b_full + 8 * b_issued, b_stage_bytes);
+            tma_load_3d(smem_u32(sB + (size_t)b_issued * b_stage_bytes), &tmap_w, bar_b_full + 8 * b_issued, kb * KB, n0, j);
+        }
     }
     if (warp == 5) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(N_TILE * p.mt)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    const int cshift = (KB == 64) ? 3 : 2;        // 16-byte pieces per row per K block = 1 << cshift
+    const int cpr = 1 << cshift;
+    const int pieces = p.R * cpr;
+    auto load_a_block = [&](int kb) {
+        const uint32_t sA_u32 = smem_u32(sA);
+        for (int q = threadIdx.x; q < pieces; q += 128) {
+            const int r = q >> cshift, c = q & (cpr - 1);
+            const int u = r - p.pad;
+            const int s = (u >= 0 && p.nseg > 1) ? fdiv(u, p.m_period) : 0;
+            const int t = t0 + (u - s * p.period);
+            const int w = w0 + s;
+            const bool ok = (t >= 0) && (t < p.T) && (s < p.nseg) && (w < p.W);
+            const __nv_bfloat16 *src = ok ? p.in + ((size_t)w * p.T + t) * p.Cin + kb * KB + c * 8 : p.in;
+            cp_async16(sA_u32 + (uint32_t)(((kb * cpr + c) * p.R + r) * 16), src, (ok && !(p.flags & 8)) ? 16u : 0u);
+        }
+    };
+    if (warp < 4) load_a_block(0);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -94,22 +121,9 @@ __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128
 
     if (warp < 4) {
         // =========================== A producer: tile rows + halo, once ===========================
-        const int tid = threadIdx.x;
-        const uint32_t sA_u32 = smem_u32(sA);
-        const int cshift = (KB == 64) ? 3 : 2;        // 16-byte pieces per row per K block = 1 << cshift
-        const int cpr = 1 << cshift;
-        const int pieces = p.R * cpr;
-        for (int kb = 0; kb < p.nkb; kb++) {
-            for (int q = tid; q < pieces; q += 128) {
-                const int r = q >> cshift, c = q & (cpr - 1);
-                const int u = r - p.pad;
-                const int s = (u >= 0 && p.nseg > 1) ? fdiv(u, p.m_period) : 0;
-                const int t = t0 + (u - s * p.period);
-                const int w = w0 + s;
-                const bool ok = (t >= 0) && (t < p.T) && (s < p.nseg) && (w < p.W);
-                const __nv_bfloat16 *src = ok ? p.in + ((size_t)w * p.T + t) * p.Cin + kb * KB + c * 8 : p.in;
-                cp_async16(sA_u32 + (uint32_t)(((kb * cpr + c) * p.R + r) * 16), src, (ok && !(p.flags & 8)) ? 16u : 0u);
-            }
+        cp_async_arrive_noinc(bar_a_full);
+        for (int kb = 1; kb < p.nkb; kb++) {
+            load_a_block(kb);
             cp_async_arrive_noinc(bar_a_full + 8 * kb);
         }
         // =========================== epilogue ===========================
@@ -211,14 +225,15 @@ __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128
     } else if (warp == 4) {
         // =========================== B producer (TMA) ===========================
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int kb = 0; kb < p.nkb; kb++) {
-                for (int j = 0; j < p.taps; j++) {
-                    mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(bar_b_full + 8 * stage, b_stage_bytes);
-                    tma_load_3d(smem_u32(sB + (size_t)stage * b_stage_bytes), &tmap_w, bar_b_full + 8 * stage, kb * KB, n0, j);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                }
+            // the first p.stages loads were issued in the prologue; the ring wraps from here on
+            int stage = (b_issued == p.stages) ? 0 : b_issued;
+            uint32_t phase = (b_issued == p.stages) ? 1 : 0;
+            for (int i = b_issued; i < total_b; i++) {
+                const int kb = i / p.taps, j = i - kb * p.taps;
+                mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+                mbar_expect_tx(bar_b_full + 8 * stage, b_stage_bytes);
+                tma_load_3d(smem_u32(sB + (size_t)stage * b_stage_bytes), &tmap_w, bar_b_full + 8 * stage, kb * KB, n0, j);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -629,8 +644,13 @@ static int launch_conv_umma_v1(const UmmaConvArgs &a, cudaStream_t st) {
     p.m_ntiles = 0;
     const size_t a_bytes = (std::max<size_t>((size_t)p.R * l.Cin * 2, (size_t)kStageBytes) + 15) & ~(size_t)15;
     const size_t b_stage = (size_t)nt * p.KB * 2;
-    const size_t tail_bytes = (2 * 8 + kMaxKB + 1) * 8 + 16;
-    int stages = 4;
+    const size_t tail_bytes = (2 * 16 + kMaxKB + 1) * 8 + 16;
+    // Weight ring depth.  On the thin layers a tap is little MMA work (0.3 us) against a ~1 us TMA round trip, so the ring
+    // is made deep enough to have every tap of the layer in flight at once; the wide layers keep 4 stages (smem).
+    static const int st32 = getenv("B2_UMMA_STAGES32") ? atoi(getenv("B2_UMMA_STAGES32")) : 4;
+    static const int st64 = getenv("B2_UMMA_STAGES64") ? atoi(getenv("B2_UMMA_STAGES64")) : 4;
+    int stages = (nt <= 32 && l.Cin <= 32) ? st32 : ((nt <= 64 && l.Cin <= 64) ? st64 : 4);
+    stages = std::max(2, std::min(stages, 16));
     while (stages > 2 && stages * b_stage + a_bytes + tail_bytes > 200 * 1024) stages--;
     const int total_b = p.nkb * l.taps;
     if (stages > total_b) stages = std::max(1, total_b);
