@@ -231,7 +231,7 @@ def main_b200(args, rank, local_rank, world):
                     "launches": tc_n, "avg_launch_ms": round(tc_ms / max(tc_n, 1), 4), "share_of_step": round(tc_ms / max(sum(ms_cls.values()), 1e-9), 4)}
     if ms_cls["resample_g711"] > 0:
         gbs = CODEC_BYTES_PER_OUT * S * F * 128 * psteps / (ms_cls["resample_g711"] / 1e3) / 1e9
-        codec_roof = {"bound": "hbm", "kernel": "k_resample_2to1_vec (fused 16k->8k + G.711)", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"],
+        codec_roof = {"bound": "hbm", "kernel": "k_resample_2to1_shfl (fused 16k->8k + G.711, warp-shuffle taps)", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"],
                       "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 4), "peak_source": peaks["source"], "traffic": None,
                       "avg_launch_ms": round(ms_cls["resample_g711"] / max(n_cls["resample_g711"], 1), 4)}
 

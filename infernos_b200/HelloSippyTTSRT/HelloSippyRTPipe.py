@@ -54,8 +54,12 @@ class HelloSippyPlayRequest(SessDispatchCmd):
     speaker: torch.Tensor
     dispatch: Callable
 
-    def __init__(self, session_id: uuid.UUID, text: str, speaker: torch.Tensor, dispatch: Callable):
-        self.text, self.speaker, self.dispatch = text, speaker, dispatch
+    def __init__(self, session_id: uuid.UUID, text: str, speaker: torch.Tensor, dispatch: Callable,
+                 dispatch_g711: Optional[Callable] = None):
+        """dispatch_g711 (extension): called with the G.711 payload `bytes` of exactly the samples
+        handed to `dispatch`, encoded on the GPU in the same pass, so a single-track call can skip the CPU encoder of
+        RTP/RTPOutputWorker.py:118."""
+        self.text, self.speaker, self.dispatch, self.dispatch_g711 = text, speaker, dispatch, dispatch_g711
         super().__init__(session_id)
 
 
@@ -68,6 +72,7 @@ class HelloSippyPipeState:
 
     def __init__(self, pp: "HelloSippyRTPipe", req: HelloSippyPlayRequest):
         self.session, self.dispatch = req.session, req.dispatch
+        self.dispatch_g711 = getattr(req, "dispatch_g711", None)
         text = req.text if pp.cleanup_text is None else pp.cleanup_text(req.text)
         self.text = text
         self.inputs = pp.frontend.tokenize(text)
@@ -86,6 +91,7 @@ class HelloSippyPipeStateBatched:
 
     def merge(self, states: List[HelloSippyPipeState], pp: "HelloSippyRTPipe"):
         self.dispatch = [s.dispatch for s in states]
+        self.dispatch_g711 = [getattr(s, "dispatch_g711", None) for s in states]
         self.sessions = [s.session for s in states]
         self.starts_at = torch.cat([s.starts_at for s in states])      # host tensors: no per-session sync later
         self.ends_at = torch.cat([s.ends_at for s in states])
@@ -307,6 +313,8 @@ class HelloSippyRTPipe:
         stepsize = 256 * 2 // sr_rr
         with self.cuda_lock:
             audio = state.audio.cpu()                       # one D2H for the whole batch
+            want_bytes = state.g711 is not None and any(cb is not None for cb in getattr(state, "dispatch_g711", []))
+            g711 = state.g711.cpu().numpy() if want_bytes else None
             asize = audio.size(1)
             starts, ends = state.starts_at.tolist(), state.ends_at.tolist()
             for i, dispatch in enumerate(state.dispatch):
@@ -317,6 +325,8 @@ class HelloSippyRTPipe:
                 assert startoff <= endoff
                 if startoff != endoff:
                     dispatch(audio[i][startoff:endoff])
+                    if g711 is not None and state.dispatch_g711[i] is not None:
+                        state.dispatch_g711[i](g711[i, startoff:endoff].tobytes())
                 if 0 <= ends[i] <= end_idx:
                     dispatch(None)
                     state.dispatch[i] = None

@@ -46,7 +46,8 @@ def test_engine_replays_real_infer(fused):
     pp = HelloSippyRTPipe("cuda:0", output_sr=8000, fused=fused, **_engine_kwargs(d))
     assert (pp.chunk_size, pp.pre_nframes, pp.post_nframes, pp.model_sr) == (8, 2, 2, 16000)
     got, ended, cbs = _collect(B)
-    reqs = [HelloSippyPlayRequest(uuid.uuid4(), "hello", pp.get_voice(0), cbs[i]) for i in range(B)]
+    payload = [bytearray() for _ in range(B)]
+    reqs = [HelloSippyPlayRequest(uuid.uuid4(), "hello", pp.get_voice(0), cbs[i], dispatch_g711=payload[i].extend) for i in range(B)]
     state = HelloSippyPipeStateBatched([HelloSippyPipeState(pp, r) for r in reqs], pp)
     calls = 0
     while True:
@@ -66,6 +67,8 @@ def test_engine_replays_real_infer(fused):
         full = torch.cat(got[i]).numpy()
         assert full.shape == d[f"session{i}_audio"].shape
         assert np.abs(full - d[f"session{i}_audio"]).max() < 1e-4
+        if fused:      # the GPU-encoded payload handed to dispatch_g711 is exactly the G.711 code of the dispatched samples
+            assert bytes(payload[i]) == ocodec.encode_f32(full, 0).tobytes()
 
 
 def test_worker_thread_end_to_end_and_codec():

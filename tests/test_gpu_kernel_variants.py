@@ -1,0 +1,49 @@
+"""GPU: the alternative tcgen05 code paths stay correct.  The library picks a kernel per layer (conv_umma.cu:launch_conv_umma);
+environment switches force the others.  They are read once per process, so each variant runs in a subprocess and must
+reproduce the default path's audio to fp32-summation-order noise (same bf16 operand rounding everywhere)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from infernos_b200 import synth
+from infernos_b200.engine import TTSTail
+t = TTSTail("cuda:0", synth.hifigan_state_dict(), synth.chunker_state_dict(), mode="bf16", max_sessions=8, max_windows=32)
+mel = synth.synth_mel(5, 32, seed=314)
+g, a = t.tail(torch.arange(5, dtype=torch.int32).cuda(), mel.cuda())
+torch.cuda.synchronize()
+np.savez(sys.argv[1], audio=a.cpu().numpy(), g711=g.cpu().numpy())
+""" % ROOT
+
+
+def _run(tmp_path, name, env):
+    out = str(tmp_path / f"{name}.npz")
+    e = dict(os.environ)
+    e.update(env)
+    subprocess.run([sys.executable, "-c", SCRIPT, out], check=True, env=e, timeout=300)
+    return np.load(out)
+
+
+@pytest.mark.parametrize("name,env", [
+    ("one_tile_kernel_everywhere", {"B2_UMMA_V1": "1"}),
+    ("persistent_kernel_everywhere", {"B2_UMMA_V2": "1"}),
+    ("fused_resblock_pairs", {"B2_PAIR_FUSION": "1"}),
+    ("single_subtile", {"B2_UMMA_MT": "1"}),
+])
+def test_variant_matches_default(tmp_path, name, env):
+    ref = _run(tmp_path, "default", {})
+    got = _run(tmp_path, name, env)
+    err = np.abs(got["audio"] - ref["audio"]).max()
+    snr = 10 * np.log10((ref["audio"] ** 2).sum() / max(((ref["audio"] - got["audio"]) ** 2).sum(), 1e-30))
+    # identical operand rounding; only the fp32 accumulation order (tile shapes) differs, which can flip a bf16 rounding
+    # of an intermediate now and then
+    assert snr > 50.0, (name, snr, err)
+    assert (got["g711"] != ref["g711"]).mean() < 0.05
