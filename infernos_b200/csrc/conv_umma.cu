@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <mutex>
+#include <vector>
 
 namespace b2 {
 
@@ -47,10 +48,14 @@ struct UmmaParams {
     int stages;       // B ring depth
     int mt;           // 128-row M sub-tiles per CTA (tall tiles for the thin layers: 4 at C=32, 2 at C=64)
     int flags;        // bit 0: skip the generic->async proxy fence after the A-tile barrier (experiment)
+    unsigned long long *dbg;   // optional per-CTA phase timestamps (analysis builds)
+    int stagger_ns, sm_count;  // first-wave phase offset between the CTAs that share an SM (0 = off)
     unsigned long long m_period, m_tpw, m_ntiles;   // ceil(2^40 / d) for period, tiles_per_win, ntiles (see fdiv)
 };
 
 // ---------------------------------------------------------------------------------------------------- kernel
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define DBG(k) do { if (p.dbg && blockIdx.x < 8192 && blockIdx.y == 0) p.dbg[(size_t)blockIdx.x * 8 + (k)] = gtime(); } while (0)
 template <int N_TILE>
 __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128) ? 2 : 1)) k_conv_umma(const __grid_constant__ CUtensorMap tmap_w, const UmmaParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -78,6 +83,17 @@ __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128
     // Prologue, arranged so that nothing waits for anything it does not need: the TMA thread initialises the barriers and
     // starts streaming weights at once, the producer warps start the first K block of the A tile, warp 5 allocates TMEM;
     // only then does the CTA synchronise.  (what-if runs: this fixed per-CTA cost was 43 % of the thin layers' time.)
+    if (threadIdx.x == 0) DBG(0);
+    // CTAs of one wave would otherwise march in lockstep: all in their MMA phase (tensor pipe saturated, HBM idle), then all
+    // in their epilogue (HBM saturated, tensor pipe idle).  Offsetting the co-resident CTAs of the FIRST wave by a fraction of
+    // a CTA lifetime keeps the phases interleaved for the rest of the launch.
+    if (p.stagger_ns > 0 && blockIdx.y == 0) {
+        const int grp = (int)(blockIdx.x / (unsigned)p.sm_count);
+        if (grp > 0 && grp < 4) {
+            const unsigned long long until = gtime() + (unsigned long long)grp * (unsigned long long)p.stagger_ns;
+            while (gtime() < until) __nanosleep(500);
+        }
+    }
     const int total_b = p.nkb * p.taps;
     int b_issued = 0;
     if (warp == 4 && lane == 0) {
@@ -118,6 +134,7 @@ __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) DBG(1);
 
     if (warp < 4) {
         // =========================== A producer: tile rows + halo, once ===========================
@@ -126,8 +143,10 @@ __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128
             load_a_block(kb);
             cp_async_arrive_noinc(bar_a_full + 8 * kb);
         }
+        if (threadIdx.x == 0) DBG(2);
         // =========================== epilogue ===========================
         mbar_wait(bar_acc, 0);
+        if (threadIdx.x == 0) DBG(3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // The A buffer is dead once the accumulator barrier has fired (every MMA that read it has retired): it becomes the
         // staging area of a per-warp transpose, so that global memory is touched with 8 lanes per 128 contiguous bytes of one
@@ -222,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128
             }
         }
         }
+        if (threadIdx.x == 0) DBG(4);
     } else if (warp == 4) {
         // =========================== B producer (TMA) ===========================
         if (lane == 0) {
@@ -238,41 +258,51 @@ __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128
         }
     } else {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // The whole warp runs the loop so that barrier addresses and descriptors are computed warp-uniformly (they stay in
+        // uniform registers, which is what UTCHMMA takes); one elected lane issues the MMAs and commits.  Issuing from inside
+        // an `if (lane == 0)` region made the compiler wrap every MMA in a register->uniform-register broadcast loop
+        // (~26 instructions per MMA; the issue loop was ~40 % of a thin-layer CTA's lifetime).
+        {
+            const bool leader = elect_one();
             // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N = N_TILE, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t sA_u32 = smem_u32(sA);
-            const uint32_t a_lbo = (uint32_t)p.R * 16;                  // between the two 8-channel chunks of one K=16 step
             const uint32_t b_layout = (KB == 64) ? 2u : 4u;             // SWIZZLE_128B : SWIZZLE_64B
-            const uint32_t b_sbo = 8u * (uint32_t)KB * 2;               // 8 rows of KB bf16
+            // descriptors differ only in the 14-bit start-address field (units of 16 bytes): build them once, then add
+            const uint64_t adesc0 = smem_desc(sA_u32, (uint32_t)p.R * 16, 128u, 0u);
+            const uint64_t bdesc0 = smem_desc(smem_u32(sB), 0u, 8u * (uint32_t)KB * 2, b_layout);
+            const uint32_t b_stage_16 = b_stage_bytes >> 4;
             const int ksteps = KB / 16;
             int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
             for (int kb = 0; kb < p.nkb; kb++) {
                 mbar_wait(bar_a_full + 8 * kb, 0);
+                if (kb == 0 && leader) DBG(6);
                 if (!(p.flags & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA (async proxy) reads
                 for (int j = 0; j < p.taps; j++) {
                     mbar_wait(bar_b_full + 8 * stage, phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t b_base = smem_u32(sB + (size_t)stage * b_stage_bytes);
+                    const uint64_t bdesc_s = bdesc0 + (uint64_t)((uint32_t)stage * b_stage_16);
+                    const uint32_t a_row = (uint32_t)(kb * (KB / 8) * p.R + j * p.dil);     // in rows (= 16-byte units)
                     for (int sub = 0; sub < p.mt; sub++)
                         for (int ks = 0; ks < ksteps; ks++) {
-                            const uint32_t a_addr = sA_u32 + (uint32_t)((((kb * (KB / 8) + ks * 2) * p.R) + sub * 128 + j * p.dil) * 16);
-                            const uint64_t adesc = smem_desc(a_addr, a_lbo, 128u, 0u);
-                            const uint64_t bdesc = smem_desc(b_base + ks * 32, 0u, b_sbo, b_layout);
-                            if (!(p.flags & 2)) umma_f16(tmem_base + (uint32_t)(sub * N_TILE), adesc, bdesc, idesc, (accum | (uint32_t)ks) ? 1u : 0u);
+                            const uint64_t adesc = adesc0 + (uint64_t)(a_row + (uint32_t)(ks * 2 * p.R + sub * 128));
+                            const uint64_t bdesc = bdesc_s + (uint64_t)(ks * 2);
+                            if (leader && !(p.flags & 2)) umma_f16(tmem_base + (uint32_t)(sub * N_TILE), adesc, bdesc, idesc, (accum | (uint32_t)ks) ? 1u : 0u);
                         }
                     accum = 1;
-                    umma_commit(bar_b_empty + 8 * stage);   // frees the B slot when these MMAs retire
+                    if (leader) umma_commit(bar_b_empty + 8 * stage);   // frees the B slot when these MMAs retire
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
-            umma_commit(bar_acc);
+            if (leader) { umma_commit(bar_acc); DBG(5); }
         }
         __syncwarp();
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) DBG(7);
     if (warp == 5) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(N_TILE * p.mt)) : "memory");
     }
@@ -444,11 +474,14 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
         }
     } else if (warp == 5) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // whole warp runs the loop (warp-uniform barrier addresses and descriptors), one elected lane issues: see k_conv_umma
+        {
+            const bool leader = elect_one();
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t a_lbo = (uint32_t)p.R * 16;
             const uint32_t b_layout = (KB == 64) ? 2u : 4u;
-            const uint32_t b_sbo = 8u * (uint32_t)KB * 2;
+            const uint64_t adesc0 = smem_desc(smem_u32(sA), (uint32_t)p.R * 16, 128u, 0u);
+            const uint64_t bdesc0 = smem_desc(smem_u32(sB), 0u, 8u * (uint32_t)KB * 2, b_layout);
+            const uint32_t b_tile_16 = b_tile_bytes >> 4, a_buf_16 = a_bytes >> 4;
             const int ksteps = KB / 16;
             int stage = 0; uint32_t phase = 0;
             if (pp.resident) { mbar_wait(B_FULL(0), 0); }
@@ -458,33 +491,35 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                 const int abuf = (pp.nA == 2) ? (it & 1) : 0, ause = (pp.nA == 2) ? (it >> 1) : it;
                 mbar_wait(ACC_EMPTY(acc), (uint32_t)((use & 1) ^ 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sA_u32 = smem_u32(sA + (size_t)abuf * a_bytes);
+                const uint64_t adesc_t = adesc0 + (uint64_t)((uint32_t)abuf * a_buf_16);
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * N_TILE);
                 uint32_t accum = 0;
                 for (int kb = 0; kb < p.nkb; kb++) {
                     mbar_wait(A_FULL(abuf, kb), (uint32_t)(ause & 1));
                     if (!(p.flags & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     for (int j = 0; j < p.taps; j++) {
-                        uint32_t b_base;
-                        if (pp.resident) b_base = smem_u32(sB + (size_t)(kb * p.taps + j) * b_tile_bytes);
+                        uint64_t bdesc_s;
+                        if (pp.resident) bdesc_s = bdesc0 + (uint64_t)((uint32_t)(kb * p.taps + j) * b_tile_16);
                         else {
                             mbar_wait(B_FULL(stage), phase);
-                            b_base = smem_u32(sB + (size_t)stage * b_tile_bytes);
+                            bdesc_s = bdesc0 + (uint64_t)((uint32_t)stage * b_tile_16);
                         }
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_row = (uint32_t)(kb * (KB / 8) * p.R + j * p.dil);
                         for (int ks = 0; ks < ksteps; ks++) {
-                            const uint32_t a_addr = sA_u32 + (uint32_t)((((kb * (KB / 8) + ks * 2) * p.R) + j * p.dil) * 16);
-                            umma_f16(tmem_acc, smem_desc(a_addr, a_lbo, 128u, 0u), smem_desc(b_base + ks * 32, 0u, b_sbo, b_layout), idesc, accum);
+                            if (leader && !(p.flags & 2)) umma_f16(tmem_acc, adesc_t + (uint64_t)(a_row + (uint32_t)(ks * 2 * p.R)), bdesc_s + (uint64_t)(ks * 2), idesc, accum);
                             accum = 1;
                         }
                         if (!pp.resident) {
-                            umma_commit(B_EMPTY(stage));
+                            if (leader) umma_commit(B_EMPTY(stage));
                             if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         }
+                        __syncwarp();
                     }
-                    umma_commit(A_EMPTY(abuf, kb));     // this K block of the A buffer may be refilled once these MMAs retire
+                    if (leader) umma_commit(A_EMPTY(abuf, kb));     // this K block of the A buffer may be refilled once these MMAs retire
                 }
-                umma_commit(ACC_FULL(acc));
+                if (leader) umma_commit(ACC_FULL(acc));
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -612,6 +647,13 @@ static int launch_conv_umma_v1(const UmmaConvArgs &a, cudaStream_t st) {
     p.in = a.in; p.bias = l.bias; p.residual = a.residual; p.acc_src = a.acc_src; p.out32 = a.out32; p.outb = a.outb;
     p.outb_slope = a.outb_slope; p.div = a.div;
     p.flags = umma_flags();
+    static const int stagger_env = getenv("B2_UMMA_STAGGER_NS") ? atoi(getenv("B2_UMMA_STAGGER_NS")) : 0;
+    p.stagger_ns = stagger_env; p.sm_count = sm_count();
+    static const bool dbg_on = getenv("B2_UMMA_DBG") != nullptr;
+    static unsigned long long *dbg_buf = nullptr;
+    if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, 8192 * 8 * 8);
+    p.dbg = dbg_on ? dbg_buf : nullptr;
+    if (dbg_on) cudaMemsetAsync(dbg_buf, 0, 8192 * 8 * 8, st);
     p.W = a.W; p.T = a.T; p.Cin = l.Cin; p.N = l.Cout; p.taps = l.taps; p.dil = l.dil; p.pad = l.pad;
     p.KB = l.Cin >= 64 ? 64 : 32;
     p.nkb = l.Cin / p.KB;
@@ -659,12 +701,39 @@ static int launch_conv_umma_v1(const UmmaConvArgs &a, cudaStream_t st) {
     if (smem > 227 * 1024) return set_error("conv_umma: tile needs %zu bytes of shared memory", smem);
     dim3 grid(mtiles, (unsigned)(l.Cout / nt));
     const CUtensorMap &tm = *reinterpret_cast<const CUtensorMap *>(l.tmap);
+    int rc;
     switch (nt) {
-        case 32: return launch_nt<32>(tm, p, grid, smem, st, 0);
-        case 64: return launch_nt<64>(tm, p, grid, smem, st, 1);
-        case 128: return launch_nt<128>(tm, p, grid, smem, st, 2);
-        default: return launch_nt<256>(tm, p, grid, smem, st, 3);
+        case 32: rc = launch_nt<32>(tm, p, grid, smem, st, 0); break;
+        case 64: rc = launch_nt<64>(tm, p, grid, smem, st, 1); break;
+        case 128: rc = launch_nt<128>(tm, p, grid, smem, st, 2); break;
+        default: rc = launch_nt<256>(tm, p, grid, smem, st, 3); break;
     }
+    if (dbg_on && !rc) {
+        cudaStreamSynchronize(st);
+        static std::vector<unsigned long long> h(8192 * 8);
+        cudaMemcpy(h.data(), dbg_buf, h.size() * 8, cudaMemcpyDeviceToHost);
+        const int n = std::min<int>(8192, (int)grid.x);
+        double d[8] = {0}; int cnt = 0;
+        unsigned long long tmin = ~0ull, tmax = 0;
+        for (int i = 0; i < n; i++) {
+            const unsigned long long *r = &h[(size_t)i * 8];
+            if (!r[0] || !r[7]) continue;
+            cnt++;
+            tmin = std::min(tmin, r[0]); tmax = std::max(tmax, r[7]);
+            d[0] += (double)(r[1] - r[0]);   // setup: start -> after sync
+            d[1] += (double)(r[2] - r[1]);   // A issue
+            d[2] += (double)(r[6] - r[1]);   // sync -> A(kb0) landed (seen by MMA thread)
+            d[3] += (double)(r[5] - r[6]);   // MMA issue loop (incl. waiting for weights)
+            d[4] += (double)(r[3] - r[5]);   // last commit -> accumulator barrier seen by epilogue
+            d[5] += (double)(r[4] - r[3]);   // epilogue
+            d[6] += (double)(r[7] - r[4]);   // teardown sync
+            d[7] += (double)(r[7] - r[0]);   // CTA lifetime
+        }
+        if (cnt) fprintf(stderr, "[umma dbg] N=%d Cin=%d taps=%d dil=%d mt=%d grid=%u res=%d out32=%d | ns: setup %.0f, A-issue %.0f, A-landed %.0f, mma-loop %.0f, commit->epi %.0f, epilogue %.0f, teardown %.0f, lifetime %.0f | span %.1f us for %d CTAs\n",
+                         nt, l.Cin, l.taps, l.dil, p.mt, grid.x, a.residual != nullptr, a.out32 != nullptr, d[0] / cnt, d[1] / cnt, d[2] / cnt, d[3] / cnt, d[4] / cnt, d[5] / cnt, d[6] / cnt, d[7] / cnt,
+                         (double)(tmax - tmin) / 1e3, cnt);
+    }
+    return rc;
 }
 
 
@@ -706,6 +775,7 @@ int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
     p.flags = umma_flags();
     p.W = a.W; p.T = a.T; p.Cin = l.Cin; p.N = l.Cout; p.taps = l.taps; p.dil = l.dil; p.pad = l.pad;
     p.mt = 1;
+    p.dbg = nullptr; p.stagger_ns = 0; p.sm_count = sm_count();
     p.R = (128 + (l.taps - 1) * l.dil) | 1;
     p.KB = l.Cin >= 64 ? 64 : 32;
     p.nkb = l.Cin / p.KB;

@@ -74,6 +74,13 @@ __device__ __forceinline__ int fdiv(int n, unsigned long long m) { return (int)(
 __device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.0f ? v : v * slope; }
 
 
+// one lane of a fully active warp (the same lane every time): the thread that issues tcgen05.mma / tcgen05.commit
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
