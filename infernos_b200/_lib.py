@@ -45,6 +45,8 @@ SIGNATURES = {
     "b2_resample_1to2": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "b2_conv1d_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]),
     "b2_conv1d_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]),
+    "b2_resblock_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                               c_float, c_float, c_float, c_void_p]),
     "b2_kernel_launch_count": (c_uint64, []),
     "b2_profile_begin": (c_int, [c_void_p]),
     "b2_profile_end": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint64)]),

@@ -1,0 +1,479 @@
+// One whole HiFiGAN ResBlock per launch on tcgen05 (modeling_speecht5.py:2903-2962):
+//
+//     for d in (d0, d1, d2):   x = x + conv2_d( lrelu( conv1_d( lrelu(x) ) ) )            six convolutions, k taps each
+//
+// The un-fused path (conv_umma.cu) moves ~16 bytes per element per conv pair through HBM (bf16 operands, fp32 residual
+// stream in and out) and at 1,024 sessions the thin stages (C = 32, 64) are bound by exactly that traffic.  Here a CTA
+// keeps a 512-row slab of one window on chip for all six convolutions:
+//
+//   X  (TMEM, fp32, kS x C columns)  the residual stream.  It is initialised with x by tcgen05.st, and every conv2 simply
+//                                    ACCUMULATES into it (the residual add is the accumulator's own "+="); conv2's biases
+//                                    are not written back but carried as a running per-channel offset added on read.
+//   T1 (TMEM, fp32, kS x C columns)  conv1's accumulator.
+//   A1, A2 (shared, bf16)            the operands lrelu(x) and lrelu(conv1(..)+b1) in the un-swizzled K-major interleaved UMMA
+//                                    layout [channel/8][row][8 ch] (rows 16 bytes apart), so a filter tap is the same buffer
+//                                    read through a descriptor advanced by j*dil rows (as in conv_umma.cu).  Each epilogue
+//                                    writes the NEXT convolution's operand straight from TMEM: nothing goes back to HBM.
+//   weights                          streamed by TMA in groups of `tps` taps through an mbarrier ring (they live in L2).
+//
+// The slab carries a halo: with buffer rows r <-> time t_base + r, every conv invalidates `pad` more rows at each end, so
+// after the six convs rows [H, 512 - H) are exact, H = (k-1)/2 * (d0 + d1 + d2 + 3); tiles advance by V <= 512 - 2H rows.
+// Rows outside the window are forced to zero in every operand (the reference pads each conv with zeros at the window edge).
+//
+// Pipelining inside a CTA is by 128-row sub-tile: the MMA warp issues   for tap group: for sub-tile: taps x K-steps   and
+// commits a sub-tile's accumulator in the last group, so the epilogue of sub-tile s overlaps the MMAs of s+1..; the next
+// conv starts as soon as the operand rows of its first two sub-tiles exist.  Two CTAs share an SM at C = 32.
+//
+// Warp roles (192 threads): 0-3 slab load + all epilogues (TMEM lanes 32*warp..), 4 TMA weight ring, 5 TMEM alloc + MMA issue.
+#include "conv_umma.cuh"
+#include "umma_ptx.cuh"
+
+#include <cuda.h>
+#include <stdlib.h>
+#include <algorithm>
+#include <vector>
+
+namespace b2 {
+
+static constexpr int kRbThreads = 192;
+static constexpr int kS = 4;                               // 128-row sub-tiles per CTA
+static constexpr int kRows = 128 * kS;                     // slab rows
+static constexpr int kGuard = 26;                          // zero rows either side of the slab (>= largest pad, 5*5)
+static constexpr int kRtot = kGuard + kRows + kGuard + 1;  // rows of an operand buffer (odd: K-chunks land on different banks)
+static constexpr int kRbStageLd = 36;                      // floats per staged row of the output transpose (32 + 4 pad)
+
+struct RbParams {
+    const float *x;          // [W][T][C] fp32
+    const float *bias1;      // [3][C]   conv1 biases
+    const float *cbias;      // [3][C]   running sum of conv2 biases: cbias[i] = b2[0] + .. + b2[i]
+    const float *acc_src;    // optional fp32 [W][T][C] added to the result (MRF sum); may alias out32
+    float *out32;            // optional
+    __nv_bfloat16 *outb;     // optional: bf16(lrelu(result, outb_slope))
+    float slope, outb_slope, div;
+    int W, T, taps, H, V, tiles_per_win, tps, ngroups, nslots;
+    int dil0, dil1, dil2;
+    unsigned long long m_tpw;
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+
+// 32 consecutive channels [c0, c0+32) of buffer row r -> bf16(lrelu(v + bias)) (or zeros) in the interleaved operand layout
+template <int C>
+__device__ __forceinline__ void write_operand_row(uint32_t sA_u32, int r, int c0, const uint32_t (&v)[32], const float *bias, float slope, bool keep) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int c = 8 * i + 2 * e;
+            float b0 = 0.0f, b1 = 0.0f;
+            if (bias) { const float2 b = __ldg(reinterpret_cast<const float2 *>(bias + c0 + c)); b0 = b.x; b1 = b.y; }
+            float v0 = lrelu_f(__uint_as_float(v[c]) + b0, slope);
+            float v1 = lrelu_f(__uint_as_float(v[c + 1]) + b1, slope);
+            if (!keep) { v0 = 0.0f; v1 = 0.0f; }
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+            pk[e] = *reinterpret_cast<uint32_t *>(&h2);
+        }
+        const uint32_t dst = sA_u32 + (uint32_t)(((((c0 >> 3) + i) * kRtot) + kGuard + r) * 16);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kRbThreads, (C == 32) ? 2 : 1) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const RbParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t kTapBytes = (uint32_t)C * C * 2;
+    constexpr uint32_t kABytes = ((uint32_t)kRtot * C * 2 + 1023u) & ~1023u;
+    const uint32_t slot_bytes = (uint32_t)p.tps * kTapBytes;
+    uint8_t *sW = smem;
+    uint8_t *sA1 = smem + (size_t)p.nslots * slot_bytes;
+    uint8_t *sA2 = sA1 + kABytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA2 + kABytes);
+    // barriers: [0,4) w_full  [4,8) w_empty  [8,12) a1_ready[s]  [12,16) t1_full[s]  [16,20) a2_ready[s]  [20,24) x_full[s]
+    const uint32_t bar0 = smem_u32(bars);
+#define W_FULL(s) (bar0 + 8u * (uint32_t)(s))
+#define W_EMPTY(s) (bar0 + 8u * (uint32_t)(4 + (s)))
+#define A1_READY(s) (bar0 + 8u * (uint32_t)(8 + (s)))
+#define T1_FULL(s) (bar0 + 8u * (uint32_t)(12 + (s)))
+#define A2_READY(s) (bar0 + 8u * (uint32_t)(16 + (s)))
+#define X_FULL(s) (bar0 + 8u * (uint32_t)(20 + (s)))
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
+
+    const int w = fdiv(blockIdx.x, p.m_tpw);
+    const int tile = blockIdx.x - w * p.tiles_per_win;
+    const int t_base = tile * p.V - p.H;               // time of slab row 0
+
+    // ---- prologue: the weight ring starts at once; barriers, TMEM and the zero guard rows are set up under it
+    if (warp == 4 && lane == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+        for (int s = 0; s < 4; s++) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kS; s++) { mbar_init(A1_READY(s), 128); mbar_init(T1_FULL(s), 1); mbar_init(A2_READY(s), 128); mbar_init(X_FULL(s), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * kS * C)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {
+        // guard rows [0, kGuard) and [kGuard + kRows, kRtot) of both operand buffers
+        constexpr int kGuardRows = kRtot - kRows;
+        const uint32_t a1 = smem_u32(sA1), a2 = smem_u32(sA2);
+        for (int q = threadIdx.x; q < kGuardRows * (C / 8); q += kRbThreads) {
+            const int ch = q / kGuardRows, g = q - ch * kGuardRows;
+            const int row = (g < kGuard) ? g : (kRows + g);
+            const uint32_t off = (uint32_t)((ch * kRtot + row) * 16);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a1 + off), "r"(0u) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a2 + off), "r"(0u) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_X = *tmem_slot;
+    const uint32_t tmem_T1 = tmem_X + (uint32_t)(kS * C);
+
+    if (warp < 4) {
+        // ======================================================================================= slab load + epilogues
+        const int rq = warp * 32 + lane;                       // row inside a sub-tile == TMEM lane
+        const uint32_t tm_lane = (uint32_t)(warp * 32) << 16;
+        const uint32_t a1_u32 = smem_u32(sA1), a2_u32 = smem_u32(sA2);
+        const float *xw = p.x + (size_t)w * p.T * C;
+        uint32_t inside_mask = 0;                              // bit s: this lane's row of sub-tile s lies inside the window
+#pragma unroll
+        for (int s = 0; s < kS; s++) { const int t = t_base + s * 128 + rq; inside_mask |= ((t >= 0) && (t < p.T)) ? (1u << s) : 0u; }
+#define inside(s) (((inside_mask >> (s)) & 1u) != 0u)
+
+        // ---- x -> X (TMEM) and lrelu(x) -> A1.  A lane owns a row: it reads the row's 128-byte pieces itself.
+#pragma unroll
+        for (int s = 0; s < kS; s++) {
+            const int r = s * 128 + rq;
+            const float *src = xw + (size_t)(t_base + r) * C;
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                uint32_t v[32];
+                if (inside(s)) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src + c0) + i);
+                        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) v[i] = 0u;
+                }
+                tmem_st32(tmem_X + tm_lane + (uint32_t)(s * C + c0), v);
+                write_operand_row<C>(a1_u32, r, c0, v, nullptr, p.slope, true);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(A1_READY(s));
+        }
+
+        for (int i = 0; i < 3; i++) {
+            const uint32_t par = (uint32_t)(i & 1);
+            // ---- epilogue 1: T1 -> lrelu(. + b1) -> A2
+#pragma unroll
+            for (int s = 0; s < kS; s++) {
+                mbar_wait(T1_FULL(s), par);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int c0 = 0; c0 < C; c0 += 32) {
+                    uint32_t acc[32];
+                    tmem_ld32(tmem_T1 + tm_lane + (uint32_t)(s * C + c0), acc);
+                    write_operand_row<C>(a2_u32, s * 128 + rq, c0, acc, p.bias1 + i * C, p.slope, inside(s));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(A2_READY(s));
+            }
+            if (i < 2) {
+                // ---- epilogue 2: X (+ running conv2 bias) -> lrelu -> A1 of the next pair
+#pragma unroll
+                for (int s = 0; s < kS; s++) {
+                    mbar_wait(X_FULL(s), par);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                    for (int c0 = 0; c0 < C; c0 += 32) {
+                        uint32_t acc[32];
+                        tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C + c0), acc);
+                        write_operand_row<C>(a1_u32, s * 128 + rq, c0, acc, p.cbias + i * C, p.slope, inside(s));
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(A1_READY(s));
+                }
+            } else {
+                // ---- final epilogue: rows [H, H+V) of the slab leave through a per-warp transpose (A1 is dead: every conv1
+                // has retired), 8 lanes per 128 contiguous bytes of an output row
+                float *stg = reinterpret_cast<float *>(sA1) + warp * 32 * kRbStageLd;
+                const int sub_r = lane >> 3, c4 = lane & 7;
+                const float *cb = p.cbias + 2 * C;
+#pragma unroll 1
+                for (int s = 0; s < kS; s++) {
+                    mbar_wait(X_FULL(s), par);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const int r = s * 128 + rq;
+                    const int t = t_base + r;
+                    const int grow_own = (r >= p.H && r < p.H + p.V && t < p.T) ? (w * p.T + t) : -1;
+                    int grow[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) grow[j] = __shfl_sync(0xffffffffu, grow_own, j * 4 + sub_r);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < C; c0 += 32) {
+                        const int col = c0 + c4 * 4;
+                        const float4 bias = __ldg(reinterpret_cast<const float4 *>(cb + col));
+                        {
+                            uint32_t a32[32];
+                            tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C + c0), a32);
+#pragma unroll
+                            for (int j = 0; j < 8; j++)
+                                *reinterpret_cast<uint4 *>(stg + lane * kRbStageLd + j * 4) = make_uint4(a32[4 * j], a32[4 * j + 1], a32[4 * j + 2], a32[4 * j + 3]);
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            float4 accs[4];
+                            if (p.acc_src) {
+#pragma unroll
+                                for (int j = 0; j < 4; j++)
+                                    accs[j] = grow[h * 4 + j] >= 0 ? *reinterpret_cast<const float4 *>(p.acc_src + (size_t)grow[h * 4 + j] * C + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const int g = grow[h * 4 + j];
+                                if (g < 0) continue;
+                                float4 v = *reinterpret_cast<const float4 *>(stg + ((h * 4 + j) * 4 + sub_r) * kRbStageLd + c4 * 4);
+                                v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+                                if (p.acc_src) { v.x = accs[j].x + v.x; v.y = accs[j].y + v.y; v.z = accs[j].z + v.z; v.w = accs[j].w + v.w; }
+                                if (p.div != 1.0f) { v.x = __fdiv_rn(v.x, p.div); v.y = __fdiv_rn(v.y, p.div); v.z = __fdiv_rn(v.z, p.div); v.w = __fdiv_rn(v.w, p.div); }
+                                const size_t o = (size_t)g * C + col;
+                                if (p.out32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
+                                if (p.outb) {
+                                    __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
+                                    __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
+                                    *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ======================================================================================= weight ring (TMA)
+        if (lane == 0) {
+            int slot = 0; uint32_t phase = 0;
+            for (int c = 0; c < 6; c++)
+                for (int g = 0; g < p.ngroups; g++) {
+                    mbar_wait(W_EMPTY(slot), phase ^ 1);
+                    mbar_expect_tx(W_FULL(slot), slot_bytes);
+                    tma_load_3d(smem_u32(sW + (size_t)slot * slot_bytes), &tmap_w, W_FULL(slot), 0, 0, c * p.taps + g * p.tps);
+                    if (++slot == p.nslots) { slot = 0; phase ^= 1; }
+                }
+        }
+    } else {
+        // ======================================================================================= MMA issuer
+        const bool leader = elect_one();
+        // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = C, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t b_layout = (C == 64) ? 2u : 4u;                 // SWIZZLE_128B : SWIZZLE_64B (a weight row is C bf16)
+        const uint64_t adesc_1 = smem_desc(smem_u32(sA1), (uint32_t)kRtot * 16, 128u, 0u);
+        const uint64_t adesc_2 = smem_desc(smem_u32(sA2), (uint32_t)kRtot * 16, 128u, 0u);
+        const uint64_t bdesc0 = smem_desc(smem_u32(sW), 0u, 8u * (uint32_t)C * 2, b_layout);
+        const uint32_t slot_16 = slot_bytes >> 4, tap_16 = kTapBytes >> 4;
+        constexpr int ksteps = C / 16;
+        int slot = 0; uint32_t phase = 0;
+        for (int i = 0; i < 3; i++) {
+            const uint32_t par = (uint32_t)(i & 1);
+            for (int cv = 0; cv < 2; cv++) {
+                const int dil = cv ? 1 : (i == 0 ? p.dil0 : (i == 1 ? p.dil1 : p.dil2));
+                const int pad = ((p.taps - 1) >> 1) * dil;
+                const uint64_t adesc_c = (cv ? adesc_2 : adesc_1) + (uint64_t)(uint32_t)(kGuard - pad);
+                const uint32_t acc_base = cv ? tmem_X : tmem_T1;
+                for (int g = 0; g < p.ngroups; g++) {
+                    mbar_wait(W_FULL(slot), phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t bdesc_s = bdesc0 + (uint64_t)((uint32_t)slot * slot_16);
+                    const int ntap = min(p.tps, p.taps - g * p.tps);
+                    for (int s = 0; s < kS; s++) {
+                        if (g == 0) {
+                            // operand rows of sub-tiles s-1 .. s+1 (the taps reach at most 25 rows out)
+                            if (s == 0) mbar_wait(cv ? A2_READY(0) : A1_READY(0), par);
+                            if (s + 1 < kS) mbar_wait(cv ? A2_READY(s + 1) : A1_READY(s + 1), par);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+                        const uint32_t tacc = acc_base + (uint32_t)(s * C);
+                        for (int tt = 0; tt < ntap; tt++) {
+                            const uint32_t a_row = (uint32_t)(s * 128 + (g * p.tps + tt) * dil);
+                            for (int ks = 0; ks < ksteps; ks++) {
+                                const uint64_t adesc = adesc_c + (uint64_t)(a_row + (uint32_t)(ks * 2 * kRtot));
+                                const uint64_t bdesc = bdesc_s + (uint64_t)((uint32_t)tt * tap_16 + (uint32_t)(ks * 2));
+                                const uint32_t accum = (cv || g || tt || ks) ? 1u : 0u;     // conv2 always adds to the residual stream
+                                if (leader) umma_f16(tacc, adesc, bdesc, idesc, accum);
+                            }
+                        }
+                        if (g == p.ngroups - 1) {
+                            if (leader) umma_commit(cv ? X_FULL(s) : T1_FULL(s));
+                        }
+                        __syncwarp();
+                    }
+                    if (leader) umma_commit(W_EMPTY(slot));
+                    __syncwarp();
+                    if (++slot == p.nslots) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_X), "r"((uint32_t)(2 * kS * C)) : "memory");
+    }
+}
+
+#undef W_FULL
+#undef W_EMPTY
+#undef A1_READY
+#undef T1_FULL
+#undef A2_READY
+#undef X_FULL
+#undef inside
+
+// ---------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int tps_for(int C) { return 4; }
+static int nslots_for(int C) { return C == 32 ? 4 : 2; }
+
+bool resblock_supported(int C, int taps) { return (C == 32 || C == 64) && (taps & 1) && taps >= 3 && taps <= 11; }
+
+int resblock_pack(const Layer *const conv1[3], const Layer *const conv2[3], ResBlockPack &out, std::vector<void *> &allocs, size_t &bytes) {
+    const int C = conv1[0]->Cin, k = conv1[0]->taps;
+    if (!resblock_supported(C, k)) return set_error("resblock: unsupported C=%d k=%d", C, k);
+    for (int i = 0; i < 3; i++) {
+        const Layer *ls[2] = {conv1[i], conv2[i]};
+        for (const Layer *l : ls)
+            if (l->Cin != C || l->Cout != C || l->taps != k || !l->wbf || l->pad * 2 != (k - 1) * l->dil)
+                return set_error("resblock: the six convolutions must share C and k and have bf16 weights");
+        if (conv2[i]->dil != 1) return set_error("resblock: conv2 must have dilation 1");
+        if (((k - 1) / 2) * conv1[i]->dil >= kGuard) return set_error("resblock: dilation %d too large", conv1[i]->dil);
+        out.dil[i] = conv1[i]->dil;
+    }
+    out.C = C; out.taps = k;
+    const int tps = tps_for(C);
+    const size_t per_conv = (size_t)k * C * C;
+    const size_t total = (6 * (size_t)k + tps) * C * C;              // + tps zero taps: the last TMA box stays in bounds
+    void *q = nullptr;
+    B2_CUDA_OK(cudaMalloc(&q, total * sizeof(__nv_bfloat16)));
+    allocs.push_back(q); bytes += total * sizeof(__nv_bfloat16);
+    out.w = reinterpret_cast<__nv_bfloat16 *>(q);
+    B2_CUDA_OK(cudaMemset(q, 0, total * sizeof(__nv_bfloat16)));
+    std::vector<float> hb((size_t)6 * C), b1((size_t)3 * C), cb((size_t)3 * C);
+    for (int i = 0; i < 3; i++) {
+        B2_CUDA_OK(cudaMemcpy(out.w + (size_t)(2 * i) * per_conv, conv1[i]->wbf, per_conv * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice));
+        B2_CUDA_OK(cudaMemcpy(out.w + (size_t)(2 * i + 1) * per_conv, conv2[i]->wbf, per_conv * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice));
+        B2_CUDA_OK(cudaMemcpy(hb.data() + (size_t)(2 * i) * C, conv1[i]->bias, C * sizeof(float), cudaMemcpyDeviceToHost));
+        B2_CUDA_OK(cudaMemcpy(hb.data() + (size_t)(2 * i + 1) * C, conv2[i]->bias, C * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    for (int i = 0; i < 3; i++)
+        for (int c = 0; c < C; c++) {
+            b1[(size_t)i * C + c] = hb[(size_t)(2 * i) * C + c];
+            cb[(size_t)i * C + c] = hb[(size_t)(2 * i + 1) * C + c] + (i ? cb[(size_t)(i - 1) * C + c] : 0.0f);
+        }
+    B2_CUDA_OK(cudaMalloc(&q, 6 * (size_t)C * sizeof(float)));
+    allocs.push_back(q); bytes += 6 * (size_t)C * sizeof(float);
+    out.bias1 = reinterpret_cast<float *>(q);
+    out.cbias = out.bias1 + 3 * C;
+    B2_CUDA_OK(cudaMemcpy(out.bias1, b1.data(), 3 * (size_t)C * sizeof(float), cudaMemcpyHostToDevice));
+    B2_CUDA_OK(cudaMemcpy(out.cbias, cb.data(), 3 * (size_t)C * sizeof(float), cudaMemcpyHostToDevice));
+
+    if (umma_init()) return 1;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return set_error("cuTensorMapEncodeTiled is not available from the driver");
+    CUtensorMap *tm = new CUtensorMap();
+    cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)C, (cuuint64_t)(6 * k + tps)};
+    cuuint64_t gstr[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * C * 2};
+    cuuint32_t box[3] = {(cuuint32_t)C, (cuuint32_t)C, (cuuint32_t)tps};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)out.w, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                     C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { delete tm; return set_error("resblock: cuTensorMapEncodeTiled failed with CUresult %d (C %d k %d)", (int)r, C, k); }
+    out.tmap = tm;
+    return 0;
+}
+
+void resblock_free(ResBlockPack &p) {
+    if (p.tmap) { delete reinterpret_cast<CUtensorMap *>(p.tmap); p.tmap = nullptr; }
+}
+
+static bool g_rb_attr[64][2] = {};
+
+template <int C>
+static int launch_rb(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int slot) {
+    int dev = 0;
+    B2_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 64 && !g_rb_attr[dev][slot]) {
+        B2_CUDA_OK(cudaFuncSetAttribute(k_resblock<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        g_rb_attr[dev][slot] = true;
+    }
+    k_resblock<C><<<grid, kRbThreads, smem, st>>>(tm, p);
+    B2_LAUNCH_OK("k_resblock");
+    return 0;
+}
+
+int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
+    const ResBlockPack &pk = *a.pack;
+    if (!pk.tmap || !pk.w) return set_error("resblock: weights were not packed");
+    if (!a.x || (!a.out32 && !a.outb)) return set_error("resblock: null input or no output");
+    if (a.W <= 0 || a.T <= 0) return 0;
+    RbParams p;
+    p.x = a.x; p.bias1 = pk.bias1; p.cbias = pk.cbias; p.acc_src = a.acc_src; p.out32 = a.out32; p.outb = a.outb;
+    p.slope = a.slope; p.outb_slope = a.outb_slope; p.div = a.div;
+    p.W = a.W; p.T = a.T; p.taps = pk.taps;
+    int dsum = 0;
+    for (int i = 0; i < 3; i++) dsum += pk.dil[i] + 1;
+    p.dil0 = pk.dil[0]; p.dil1 = pk.dil[1]; p.dil2 = pk.dil[2];
+    p.H = ((pk.taps - 1) / 2) * dsum;
+    const int vmax = kRows - 2 * p.H;
+    if (vmax < 64) return set_error("resblock: halo %d leaves no room in a %d-row slab", p.H, kRows);
+    p.tiles_per_win = cdiv(a.T, vmax);
+    p.V = cdiv(a.T, p.tiles_per_win);
+    p.m_tpw = ((1ull << 40) + (unsigned long long)p.tiles_per_win - 1) / (unsigned long long)p.tiles_per_win;
+    p.tps = tps_for(pk.C);
+    p.ngroups = cdiv(pk.taps, p.tps);
+    p.nslots = nslots_for(pk.C);
+    const long long nct = (long long)a.W * p.tiles_per_win;
+    if (nct >= (1ll << 24)) return set_error("resblock: too many tiles (%lld)", nct);
+    const size_t a_bytes = ((size_t)kRtot * pk.C * 2 + 1023) & ~(size_t)1023;
+    const size_t smem = (size_t)p.nslots * p.tps * pk.C * pk.C * 2 + 2 * a_bytes + 24 * 8 + 16;
+    if (smem > 227 * 1024) return set_error("resblock: needs %zu bytes of shared memory", smem);
+    const CUtensorMap &tm = *reinterpret_cast<const CUtensorMap *>(pk.tmap);
+    if (pk.C == 32) return launch_rb<32>(tm, p, (unsigned)nct, smem, st, 0);
+    return launch_rb<64>(tm, p, (unsigned)nct, smem, st, 1);
+}
+
+}  // namespace b2

@@ -37,6 +37,23 @@ struct PairArgs {
 };
 bool pair_supported(const Layer &conv1, const Layer &conv2, int T);
 int launch_resblock_pair(const PairArgs &a, cudaStream_t st);
+// One whole ResBlock (three conv pairs, dilations d0..d2) in a single launch (conv_resblock.cu).
+//   result = x3, where x_{n+1} = x_n + conv2_n(lrelu(conv1_n(lrelu(x_n, slope)), slope));
+//   v = result; v = acc_src + v; v /= div; out32 = v; outb = bf16(lrelu(v, outb_slope))
+struct ResBlockArgs {
+    const float *x = nullptr;              // fp32 channels-last [W][T][C]
+    const ResBlockPack *pack = nullptr;
+    const float *acc_src = nullptr;        // may alias out32
+    float *out32 = nullptr;
+    __nv_bfloat16 *outb = nullptr;
+    float slope = 0.1f, outb_slope = 1.0f, div = 1.0f;
+    int W = 0, T = 0;
+};
+bool resblock_supported(int C, int taps);
+// gathers the six convolutions' bf16 weights into one TMA-addressable buffer (device allocations are appended to `allocs`)
+int resblock_pack(const Layer *const conv1[3], const Layer *const conv2[3], ResBlockPack &out, std::vector<void *> &allocs, size_t &bytes);
+void resblock_free(ResBlockPack &p);
+int launch_resblock(const ResBlockArgs &a, cudaStream_t st);
 // builds the TMA descriptor of a layer's bf16 weights; called once from b2_weights_finalize
 int umma_prepare_layer(Layer &l);
 void umma_free_layer(Layer &l);

@@ -21,6 +21,15 @@ struct Layer {
     void *tmap = nullptr;            // host copy of the CUtensorMap for wbf (tensor-core path)
 };
 
+// the six convolutions of one ResBlock packed for the fused kernel (conv_resblock.cu)
+struct ResBlockPack {
+    int C = 0, taps = 0, dil[3] = {1, 1, 1};
+    __nv_bfloat16 *w = nullptr;      // [6*taps (+pad)][C][C] bf16: pair0.conv1, pair0.conv2, pair1.conv1, ...
+    float *bias1 = nullptr;          // [3][C]
+    float *cbias = nullptr;          // [3][C] running sums of the conv2 biases
+    void *tmap = nullptr;            // host copy of the CUtensorMap over w
+};
+
 struct Workspace {
     // sized for `cap_frames` mel frames in flight (12 per window)
     float *win_raw = nullptr, *win_norm = nullptr;     // [F][80]
@@ -69,6 +78,7 @@ struct b2_ctx {
 
     float *mean = nullptr, *scale = nullptr;
     b2::Layer conv_pre, up[4], res1[4][3][3], res2[4][3][3];
+    b2::ResBlockPack rb[4][3];                         // fused-ResBlock packs (BF16 mode, stages the fused kernel covers)
     float *post_w = nullptr, *post_b = nullptr;        // conv_post [7][32], [1]
     // chunker
     float *cwm = nullptr, *cbm = nullptr, *cwa = nullptr, *cba = nullptr;

@@ -190,6 +190,14 @@ static int finalize(b2_ctx *c) {
                 if (!(w = find(c->voc_raw, k1, {C, C, k})) || !(b = find(c->voc_raw, k2, {C}))) return 1;
                 if (pack_conv(c, c->res2[i][j][d], *w, *b, 1, (k - 1) / 2, 1, bf)) return 1;
             }
+        if (bf) {
+            for (int j = 0; j < 3; j++) {
+                if (!resblock_supported(C, RES_K[j])) continue;
+                const Layer *l1[3] = {&c->res1[i][j][0], &c->res1[i][j][1], &c->res1[i][j][2]};
+                const Layer *l2[3] = {&c->res2[i][j][0], &c->res2[i][j][1], &c->res2[i][j][2]};
+                if (resblock_pack(l1, l2, c->rb[i][j], c->allocs, c->device_bytes)) return 1;
+            }
+        }
         cin = C;
     }
     if (!(w = find(c->voc_raw, "conv_post.weight", {1, 32, 7})) || !(b = find(c->voc_raw, "conv_post.bias", {1}))) return 1;
@@ -310,10 +318,31 @@ static int vocoder_bf16(b2_ctx *c, const float *xn, int W, int T, float *audio, 
     const __nv_bfloat16 *stage_in = ws.c0b;
     int Tc = T;
     for (int i = 0; i < 4; i++) {
+        // One launch per ResBlock where the fused kernel covers the stage (conv_resblock.cu); B2_RESBLOCK_FUSION=0 keeps the
+        // conv-by-conv path everywhere.
+        static const bool fusion_on = !(getenv("B2_RESBLOCK_FUSION") && atoi(getenv("B2_RESBLOCK_FUSION")) == 0);
+        const bool fused = fusion_on && c->rb[i][0].tmap && c->rb[i][1].tmap && c->rb[i][2].tmap;
         UmmaConvArgs u;
-        u.in = stage_in; u.layer = &c->up[i]; u.out32 = ws.h; u.outb = ws.hb; u.outb_slope = 0.1f; u.W = W; u.T = Tc;
+        u.in = stage_in; u.layer = &c->up[i]; u.out32 = ws.h; u.outb = fused ? nullptr : ws.hb; u.outb_slope = 0.1f; u.W = W; u.T = Tc;
         PROF(PC_CONV_TC, launch_conv_umma(u, st));
         Tc *= 4;
+        if (fused) {
+            // MRF mean (modeling_speecht5.py:3069-3072): s0 = rb0(x); s0 += rb1(x); (s0 + rb2(x)) / 3
+            for (int j = 0; j < 3; j++) {
+                ResBlockArgs ra;
+                ra.x = ws.h; ra.pack = &c->rb[i][j]; ra.W = W; ra.T = Tc; ra.slope = 0.1f; ra.outb_slope = 0.1f;
+                ra.acc_src = (j > 0) ? ws.s0 : nullptr;
+                if (j < 2) ra.out32 = ws.s0;
+                else {
+                    ra.div = 3.0f;
+                    if (i < 3) ra.outb = ws.sb;
+                    else ra.out32 = ws.s0;
+                }
+                PROF(PC_CONV_TC, launch_resblock(ra, st));
+            }
+            stage_in = ws.sb;
+            continue;
+        }
         for (int j = 0; j < 3; j++) {
             for (int d = 0; d < 3; d++) {
                 const float *x = (d == 0) ? ws.h : ws.r;
@@ -468,7 +497,10 @@ void b2_ctx_destroy(b2_ctx *c) {
         umma_free_layer(c->up[i]);
         for (int j = 0; j < 3; j++)
             for (int d = 0; d < 3; d++) { umma_free_layer(c->res1[i][j][d]); umma_free_layer(c->res2[i][j][d]); }
+        for (int j = 0; j < 3; j++) resblock_free(c->rb[i][j]);
     }
+    umma_free_layer(c->conv_pre);
+    umma_free_layer(c->c_up[0]); umma_free_layer(c->c_up[1]); umma_free_layer(c->c_res1); umma_free_layer(c->c_res2);
     delete c;
 }
 
@@ -629,6 +661,48 @@ int b2_conv1d_tc(const void *d_in_bf16, const float *h_weight, const float *h_bi
 int b2_conv1d_f32(const float *d_in, const float *h_weight, const float *h_bias, int W, int T, int Cin, int Cout, int k, int dil,
                   float pre_slope, const float *d_residual, float *d_out32, void *d_outb, float slope, float div, void *stream) {
     return single_layer(d_in, h_weight, h_bias, W, T, Cin, Cout, k, dil, pre_slope, d_residual, d_out32, d_outb, slope, div, false, (cudaStream_t)stream);
+}
+
+int b2_resblock_tc(const float *d_x, const float *h_weights, const float *h_biases, int W, int T, int C, int k, int d0, int d1, int d2,
+                   const float *d_acc, float *d_out32, void *d_outb, float slope, float outb_slope, float div, void *stream) {
+    if (!d_x || !h_weights || !h_biases || W < 1 || T < 1) return set_error("b2_resblock_tc: bad arguments");
+    if (!resblock_supported(C, k)) return set_error("b2_resblock_tc: unsupported C=%d k=%d", C, k);
+    cudaStream_t st = (cudaStream_t)stream;
+    b2_ctx tmp;
+    int dev = 0;
+    B2_CUDA_OK(cudaGetDevice(&dev));
+    tmp.device = dev;
+    const int dils[3] = {d0, d1, d2};
+    Layer l1[3], l2[3];
+    int rc = 0;
+    for (int i = 0; i < 3 && !rc; i++)
+        for (int cv = 0; cv < 2 && !rc; cv++) {
+            HostTensor w, b;
+            w.shape = {C, C, k};
+            const float *hw = h_weights + (size_t)(2 * i + cv) * C * C * k;
+            w.data.assign(hw, hw + (size_t)C * C * k);
+            b.shape = {C};
+            b.data.assign(h_biases + (size_t)(2 * i + cv) * C, h_biases + (size_t)(2 * i + cv + 1) * C);
+            const int dil = cv ? 1 : dils[i];
+            rc = pack_conv(&tmp, cv ? l2[i] : l1[i], w, b, dil, (k - 1) * dil / 2, 1, true);
+        }
+    ResBlockPack pk;
+    if (!rc) {
+        const Layer *p1[3] = {&l1[0], &l1[1], &l1[2]}, *p2[3] = {&l2[0], &l2[1], &l2[2]};
+        rc = resblock_pack(p1, p2, pk, tmp.allocs, tmp.device_bytes);
+    }
+    if (!rc) {
+        ResBlockArgs ra;
+        ra.x = d_x; ra.pack = &pk; ra.acc_src = d_acc; ra.out32 = d_out32; ra.outb = reinterpret_cast<__nv_bfloat16 *>(d_outb);
+        ra.slope = slope; ra.outb_slope = outb_slope; ra.div = div; ra.W = W; ra.T = T;
+        rc = launch_resblock(ra, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (!rc && e != cudaSuccess) rc = set_error("b2_resblock_tc: %s", cudaGetErrorString(e));
+    for (void *q : tmp.allocs) cudaFree(q);
+    for (int i = 0; i < 3; i++) { umma_free_layer(l1[i]); umma_free_layer(l2[i]); }
+    resblock_free(pk);
+    return rc;
 }
 
 int b2_session_reset(b2_ctx *c, const int32_t *h_slots, int n, void *stream) {
