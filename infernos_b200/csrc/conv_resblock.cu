@@ -35,17 +35,15 @@
 
 namespace b2 {
 
-static constexpr int kRbThreads = 192;
 static constexpr int kS = 4;                               // 128-row sub-tiles per CTA
 static constexpr int kRows = 128 * kS;                     // slab rows
 static constexpr int kGuard = 26;                          // zero rows either side of the slab (>= largest pad, 5*5)
 static constexpr int kRtot = kGuard + kRows + kGuard + 1;  // rows of an operand buffer (odd: K-chunks land on different banks)
 static constexpr int kRbStageLd = 36;                      // floats per staged row of the output transpose (32 + 4 pad)
+static constexpr int kRbMaxC = 64;
 
 struct RbParams {
     const float *x;          // [W][T][C] fp32
-    const float *bias1;      // [3][C]   conv1 biases
-    const float *cbias;      // [3][C]   running sum of conv2 biases: cbias[i] = b2[0] + .. + b2[i]
     const float *acc_src;    // optional fp32 [W][T][C] added to the result (MRF sum); may alias out32
     float *out32;            // optional
     __nv_bfloat16 *outb;     // optional: bf16(lrelu(result, outb_slope))
@@ -53,6 +51,9 @@ struct RbParams {
     int W, T, taps, H, V, tiles_per_win, tps, ngroups, nslots;
     int dil0, dil1, dil2;
     unsigned long long m_tpw;
+    unsigned long long *dbg;   // optional per-CTA phase timestamps (B2_RB_DBG analysis runs)
+    float bias1[3 * kRbMaxC];  // conv1 biases                                         (constant bank: uniform loads)
+    float cbias[3 * kRbMaxC];  // running sum of conv2 biases: cbias[i] = b2[0] + .. + b2[i]
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -67,8 +68,22 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         : "memory");
 }
 
-// 32 consecutive channels [c0, c0+32) of buffer row r -> bf16(lrelu(v + bias)) (or zeros) in the interleaved operand layout
-template <int C>
+// 32 consecutive fp32 of one row (128 bytes) -> registers; zeros when the row is not wanted
+__device__ __forceinline__ void ld_row32(const float *src, bool ok, uint32_t (&v)[32]) {
+    if (ok) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+            v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = 0u;
+    }
+}
+
+// 32 consecutive channels [c0, c0+32) of buffer row r -> bf16(lrelu(v + bias)) (zeros when !keep) in the interleaved operand
+// layout.  slope is in (0, 1), so leaky_relu(v) == max(v, slope * v).
 __device__ __forceinline__ void write_operand_row(uint32_t sA_u32, int r, int c0, const uint32_t (&v)[32], const float *bias, float slope, bool keep) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -76,23 +91,40 @@ __device__ __forceinline__ void write_operand_row(uint32_t sA_u32, int r, int c0
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const int c = 8 * i + 2 * e;
-            float b0 = 0.0f, b1 = 0.0f;
-            if (bias) { const float2 b = __ldg(reinterpret_cast<const float2 *>(bias + c0 + c)); b0 = b.x; b1 = b.y; }
-            float v0 = lrelu_f(__uint_as_float(v[c]) + b0, slope);
-            float v1 = lrelu_f(__uint_as_float(v[c + 1]) + b1, slope);
-            if (!keep) { v0 = 0.0f; v1 = 0.0f; }
+            float v0 = __uint_as_float(v[c]), v1 = __uint_as_float(v[c + 1]);
+            if (bias) { v0 += bias[c]; v1 += bias[c + 1]; }
+            v0 = fmaxf(v0, v0 * slope);
+            v1 = fmaxf(v1, v1 * slope);
             __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-            pk[e] = *reinterpret_cast<uint32_t *>(&h2);
+            pk[e] = keep ? *reinterpret_cast<uint32_t *>(&h2) : 0u;
         }
         const uint32_t dst = sA_u32 + (uint32_t)(((((c0 >> 3) + i) * kRtot) + kGuard + r) * 16);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
     }
 }
 
-template <int C>
-__global__ void __launch_bounds__(kRbThreads, (C == 32) ? 2 : 1) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const RbParams p) {
+// this thread's shared-memory operand writes and TMEM reads/writes are done: publish them to the MMA warps (one arrival per warp)
+__device__ __forceinline__ void publish_rows(uint32_t bar, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> UMMA (async proxy) reads
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+static constexpr int kRbDbgEvents = 48, kRbDbgCtas = 4096;
+#define RB_DBG(k) do { if (p.dbg && blockIdx.x < kRbDbgCtas) p.dbg[(size_t)blockIdx.x * kRbDbgEvents + (k)] = clock64(); } while (0)
+
+// Warp roles: 0-3 slab load + all epilogues (TMEM lanes 32*warp..), 4 TMEM alloc + TMA weight ring, 5.. MMA issuers.
+// One warp cannot issue these small MMAs fast enough (an M128 x N32 x K16 MMA occupies the tensor pipe for 40 cycles, its issue
+// sequence -- descriptors through R2UR -- costs ~130): NMW warps issue in parallel, each owning kS / NMW sub-tiles.
+template <int C, int NMW>
+__global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ RbParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kThreads = (5 + NMW) * 32;
+    constexpr int CH = C / 32;                                  // 32-column chunks per row
+    constexpr int NCH = kS * CH;
+    constexpr int SPW = kS / NMW;                               // sub-tiles per MMA warp
     constexpr uint32_t kTapBytes = (uint32_t)C * C * 2;
     constexpr uint32_t kABytes = ((uint32_t)kRtot * C * 2 + 1023u) & ~1023u;
     const uint32_t slot_bytes = (uint32_t)p.tps * kTapBytes;
@@ -114,18 +146,17 @@ __global__ void __launch_bounds__(kRbThreads, (C == 32) ? 2 : 1) k_resblock(cons
     const int tile = blockIdx.x - w * p.tiles_per_win;
     const int t_base = tile * p.V - p.H;               // time of slab row 0
 
-    // ---- prologue: the weight ring starts at once; barriers, TMEM and the zero guard rows are set up under it
-    if (warp == 4 && lane == 0) {
-        if (smem_u32(smem) & 1023u) __trap();
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
-        for (int s = 0; s < 4; s++) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kS; s++) { mbar_init(A1_READY(s), 128); mbar_init(T1_FULL(s), 1); mbar_init(A2_READY(s), 128); mbar_init(X_FULL(s), 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 5) {
+    if (threadIdx.x == 0) RB_DBG(0);
+    // ---- prologue
+    if (warp == 4) {
+        if (lane == 0) {
+            if (smem_u32(smem) & 1023u) __trap();
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+            for (int s = 0; s < 4; s++) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), NMW); }
+            for (int s = 0; s < kS; s++) { mbar_init(A1_READY(s), 4); mbar_init(T1_FULL(s), 1); mbar_init(A2_READY(s), 4); mbar_init(X_FULL(s), 1); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * kS * C)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -133,7 +164,7 @@ __global__ void __launch_bounds__(kRbThreads, (C == 32) ? 2 : 1) k_resblock(cons
         // guard rows [0, kGuard) and [kGuard + kRows, kRtot) of both operand buffers
         constexpr int kGuardRows = kRtot - kRows;
         const uint32_t a1 = smem_u32(sA1), a2 = smem_u32(sA2);
-        for (int q = threadIdx.x; q < kGuardRows * (C / 8); q += kRbThreads) {
+        for (int q = threadIdx.x; q < kGuardRows * (C / 8); q += kThreads) {
             const int ch = q / kGuardRows, g = q - ch * kGuardRows;
             const int row = (g < kGuard) ? g : (kRows + g);
             const uint32_t off = (uint32_t)((ch * kRtot + row) * 16);
@@ -147,45 +178,48 @@ __global__ void __launch_bounds__(kRbThreads, (C == 32) ? 2 : 1) k_resblock(cons
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_X = *tmem_slot;
     const uint32_t tmem_T1 = tmem_X + (uint32_t)(kS * C);
+    if (threadIdx.x == 0) RB_DBG(1);
 
     if (warp < 4) {
         // ======================================================================================= slab load + epilogues
         const int rq = warp * 32 + lane;                       // row inside a sub-tile == TMEM lane
         const uint32_t tm_lane = (uint32_t)(warp * 32) << 16;
         const uint32_t a1_u32 = smem_u32(sA1), a2_u32 = smem_u32(sA2);
-        const float *xw = p.x + (size_t)w * p.T * C;
-        uint32_t inside_mask = 0;                              // bit s: this lane's row of sub-tile s lies inside the window
-#pragma unroll
-        for (int s = 0; s < kS; s++) { const int t = t_base + s * 128 + rq; inside_mask |= ((t >= 0) && (t < p.T)) ? (1u << s) : 0u; }
-#define inside(s) (((inside_mask >> (s)) & 1u) != 0u)
-
-        // ---- x -> X (TMEM) and lrelu(x) -> A1.  A lane owns a row: it reads the row's 128-byte pieces itself.
+        const float *xrow = p.x + ((size_t)w * p.T + (t_base + rq)) * C;          // row rq of sub-tile 0 (may lie outside: guarded)
+        uint32_t inside_mask = 0, out_mask = 0;                 // bit s: this lane's row of sub-tile s is inside the window / is an output row
 #pragma unroll
         for (int s = 0; s < kS; s++) {
-            const int r = s * 128 + rq;
-            const float *src = xw + (size_t)(t_base + r) * C;
-#pragma unroll 1
-            for (int c0 = 0; c0 < C; c0 += 32) {
-                uint32_t v[32];
-                if (inside(s)) {
+            const int r = s * 128 + rq, t = t_base + r;
+            inside_mask |= ((t >= 0) && (t < p.T)) ? (1u << s) : 0u;
+            out_mask |= (r >= p.H && r < p.H + p.V && t < p.T) ? (1u << s) : 0u;
+        }
+#define inside(s) (((inside_mask >> (s)) & 1u) != 0u)
+#define is_out(s) (((out_mask >> (s)) & 1u) != 0u)
+
+        // ---- x -> X (TMEM) and lrelu(x) -> A1.  A lane owns a row and reads the row's 128-byte pieces itself, one piece ahead.
+        {
+            uint32_t bufA[32], bufB[32];
+            ld_row32(xrow, inside(0), bufA);
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src + c0) + i);
-                        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; i++) v[i] = 0u;
+            for (int q = 0; q < NCH; q++) {
+                const int s = q / CH, c0 = (q % CH) * 32;
+                uint32_t (&v)[32] = (q & 1) ? bufB : bufA;
+                uint32_t (&nx)[32] = (q & 1) ? bufA : bufB;
+                if (q + 1 < NCH) {
+                    const int s1 = (q + 1) / CH, c1 = ((q + 1) % CH) * 32;
+                    ld_row32(xrow + (size_t)s1 * 128 * C + c1, inside(s1), nx);
                 }
                 tmem_st32(tmem_X + tm_lane + (uint32_t)(s * C + c0), v);
-                write_operand_row<C>(a1_u32, r, c0, v, nullptr, p.slope, true);
+                write_operand_row(a1_u32, s * 128 + rq, c0, v, nullptr, p.slope, true);
+                if (c0 + 32 == C) {
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    publish_rows(A1_READY(s), lane);
+                }
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(A1_READY(s));
         }
+        if (threadIdx.x == 0) RB_DBG(2);
 
+#pragma unroll 1
         for (int i = 0; i < 3; i++) {
             const uint32_t par = (uint32_t)(i & 1);
             // ---- epilogue 1: T1 -> lrelu(. + b1) -> A2
@@ -193,88 +227,106 @@ __global__ void __launch_bounds__(kRbThreads, (C == 32) ? 2 : 1) k_resblock(cons
             for (int s = 0; s < kS; s++) {
                 mbar_wait(T1_FULL(s), par);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
+                if (threadIdx.x == 0 && s == 0) RB_DBG(3 + 4 * i);
+#pragma unroll
                 for (int c0 = 0; c0 < C; c0 += 32) {
                     uint32_t acc[32];
                     tmem_ld32(tmem_T1 + tm_lane + (uint32_t)(s * C + c0), acc);
-                    write_operand_row<C>(a2_u32, s * 128 + rq, c0, acc, p.bias1 + i * C, p.slope, inside(s));
+                    write_operand_row(a2_u32, s * 128 + rq, c0, acc, p.bias1 + i * C + c0, p.slope, inside(s));
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(A2_READY(s));
+                publish_rows(A2_READY(s), lane);
             }
+            if (threadIdx.x == 0) RB_DBG(4 + 4 * i);
             if (i < 2) {
                 // ---- epilogue 2: X (+ running conv2 bias) -> lrelu -> A1 of the next pair
 #pragma unroll
                 for (int s = 0; s < kS; s++) {
                     mbar_wait(X_FULL(s), par);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
+                    if (threadIdx.x == 0 && s == 0) RB_DBG(5 + 4 * i);
+#pragma unroll
                     for (int c0 = 0; c0 < C; c0 += 32) {
                         uint32_t acc[32];
                         tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C + c0), acc);
-                        write_operand_row<C>(a1_u32, s * 128 + rq, c0, acc, p.cbias + i * C, p.slope, inside(s));
+                        write_operand_row(a1_u32, s * 128 + rq, c0, acc, p.cbias + i * C + c0, p.slope, inside(s));
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(A1_READY(s));
+                    publish_rows(A1_READY(s), lane);
                 }
+                if (threadIdx.x == 0) RB_DBG(6 + 4 * i);
             } else {
+                // ---- while the last conv2 runs: T1 is idle from here on, so the MRF partial sum (acc_src) of this lane's output
+                // rows is parked there; the final epilogue then never waits on global memory
+                if (p.acc_src) {
+                    const float *arow = p.acc_src + ((size_t)w * p.T + (t_base + rq)) * C;
+                    uint32_t bufA[32], bufB[32];
+                    ld_row32(arow, is_out(0), bufA);
+#pragma unroll
+                    for (int q = 0; q < NCH; q++) {
+                        const int s = q / CH, c0 = (q % CH) * 32;
+                        uint32_t (&v)[32] = (q & 1) ? bufB : bufA;
+                        uint32_t (&nx)[32] = (q & 1) ? bufA : bufB;
+                        if (q + 1 < NCH) {
+                            const int s1 = (q + 1) / CH, c1 = ((q + 1) % CH) * 32;
+                            ld_row32(arow + (size_t)s1 * 128 * C + c1, is_out(s1), nx);
+                        }
+                        tmem_st32(tmem_T1 + tm_lane + (uint32_t)(s * C + c0), v);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
                 // ---- final epilogue: rows [H, H+V) of the slab leave through a per-warp transpose (A1 is dead: every conv1
                 // has retired), 8 lanes per 128 contiguous bytes of an output row
                 float *stg = reinterpret_cast<float *>(sA1) + warp * 32 * kRbStageLd;
                 const int sub_r = lane >> 3, c4 = lane & 7;
-                const float *cb = p.cbias + 2 * C;
 #pragma unroll 1
                 for (int s = 0; s < kS; s++) {
                     mbar_wait(X_FULL(s), par);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const int r = s * 128 + rq;
-                    const int t = t_base + r;
-                    const int grow_own = (r >= p.H && r < p.H + p.V && t < p.T) ? (w * p.T + t) : -1;
+                    if (threadIdx.x == 0 && s == 0) RB_DBG(5 + 4 * i);
+                    const int grow_own = is_out(s) ? (w * p.T + t_base + s * 128 + rq) : -1;
                     int grow[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) grow[j] = __shfl_sync(0xffffffffu, grow_own, j * 4 + sub_r);
 #pragma unroll 1
                     for (int c0 = 0; c0 < C; c0 += 32) {
-                        const int col = c0 + c4 * 4;
-                        const float4 bias = __ldg(reinterpret_cast<const float4 *>(cb + col));
                         {
                             uint32_t a32[32];
                             tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C + c0), a32);
+                            const float *cb = p.cbias + 2 * C + c0;
+#pragma unroll
+                            for (int j = 0; j < 32; j++) a32[j] = __float_as_uint(__uint_as_float(a32[j]) + cb[j]);
+                            if (p.acc_src) {
+                                uint32_t b32[32];
+                                tmem_ld32(tmem_T1 + tm_lane + (uint32_t)(s * C + c0), b32);
+#pragma unroll
+                                for (int j = 0; j < 32; j++) a32[j] = __float_as_uint(__uint_as_float(b32[j]) + __uint_as_float(a32[j]));
+                            }
+                            if (p.div != 1.0f) {
+#pragma unroll
+                                for (int j = 0; j < 32; j++) a32[j] = __float_as_uint(__fdiv_rn(__uint_as_float(a32[j]), p.div));
+                            }
 #pragma unroll
                             for (int j = 0; j < 8; j++)
                                 *reinterpret_cast<uint4 *>(stg + lane * kRbStageLd + j * 4) = make_uint4(a32[4 * j], a32[4 * j + 1], a32[4 * j + 2], a32[4 * j + 3]);
                         }
                         __syncwarp();
+                        const int col = c0 + c4 * 4;
 #pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            float4 accs[4];
-                            if (p.acc_src) {
-#pragma unroll
-                                for (int j = 0; j < 4; j++)
-                                    accs[j] = grow[h * 4 + j] >= 0 ? *reinterpret_cast<const float4 *>(p.acc_src + (size_t)grow[h * 4 + j] * C + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const int g = grow[h * 4 + j];
-                                if (g < 0) continue;
-                                float4 v = *reinterpret_cast<const float4 *>(stg + ((h * 4 + j) * 4 + sub_r) * kRbStageLd + c4 * 4);
-                                v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
-                                if (p.acc_src) { v.x = accs[j].x + v.x; v.y = accs[j].y + v.y; v.z = accs[j].z + v.z; v.w = accs[j].w + v.w; }
-                                if (p.div != 1.0f) { v.x = __fdiv_rn(v.x, p.div); v.y = __fdiv_rn(v.y, p.div); v.z = __fdiv_rn(v.z, p.div); v.w = __fdiv_rn(v.w, p.div); }
-                                const size_t o = (size_t)g * C + col;
-                                if (p.out32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
-                                if (p.outb) {
-                                    __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
-                                    __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
-                                    *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
-                                }
+                        for (int j = 0; j < 8; j++) {
+                            const int g = grow[j];
+                            if (g < 0) continue;
+                            const float4 v = *reinterpret_cast<const float4 *>(stg + (j * 4 + sub_r) * kRbStageLd + c4 * 4);
+                            const size_t o = (size_t)g * C + col;
+                            if (p.out32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
+                            if (p.outb) {
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
+                                __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
+                                *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
                             }
                         }
                         __syncwarp();
                     }
                 }
+                if (threadIdx.x == 0) RB_DBG(6 + 4 * i);
             }
         }
     } else if (warp == 4) {
@@ -289,8 +341,11 @@ __global__ void __launch_bounds__(kRbThreads, (C == 32) ? 2 : 1) k_resblock(cons
                     if (++slot == p.nslots) { slot = 0; phase ^= 1; }
                 }
         }
+        __syncwarp();
     } else {
-        // ======================================================================================= MMA issuer
+        // ======================================================================================= MMA issuers
+        const int mw = warp - 5;
+        const int s_first = mw * SPW;
         const bool leader = elect_one();
         // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = C, M = 128
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
@@ -301,51 +356,68 @@ __global__ void __launch_bounds__(kRbThreads, (C == 32) ? 2 : 1) k_resblock(cons
         const uint32_t slot_16 = slot_bytes >> 4, tap_16 = kTapBytes >> 4;
         constexpr int ksteps = C / 16;
         int slot = 0; uint32_t phase = 0;
+#pragma unroll 1
         for (int i = 0; i < 3; i++) {
             const uint32_t par = (uint32_t)(i & 1);
+#pragma unroll 1
             for (int cv = 0; cv < 2; cv++) {
                 const int dil = cv ? 1 : (i == 0 ? p.dil0 : (i == 1 ? p.dil1 : p.dil2));
                 const int pad = ((p.taps - 1) >> 1) * dil;
                 const uint64_t adesc_c = (cv ? adesc_2 : adesc_1) + (uint64_t)(uint32_t)(kGuard - pad);
                 const uint32_t acc_base = cv ? tmem_X : tmem_T1;
+                const uint32_t ready0 = cv ? A2_READY(0) : A1_READY(0);
+                const uint32_t done0 = cv ? X_FULL(0) : T1_FULL(0);
+#pragma unroll 1
                 for (int g = 0; g < p.ngroups; g++) {
                     mbar_wait(W_FULL(slot), phase);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t bdesc_s = bdesc0 + (uint64_t)((uint32_t)slot * slot_16);
-                    const int ntap = min(p.tps, p.taps - g * p.tps);
-                    for (int s = 0; s < kS; s++) {
+                    const uint64_t bdesc_g = bdesc0 + (uint64_t)((uint32_t)slot * slot_16);
+                    const int j0 = g * p.tps;
+                    const int ntap = min(p.tps, p.taps - j0);
+#pragma unroll 1
+                    for (int ss = 0; ss < SPW; ss++) {
+                        const int s = s_first + ss;
                         if (g == 0) {
                             // operand rows of sub-tiles s-1 .. s+1 (the taps reach at most 25 rows out)
-                            if (s == 0) mbar_wait(cv ? A2_READY(0) : A1_READY(0), par);
-                            if (s + 1 < kS) mbar_wait(cv ? A2_READY(s + 1) : A1_READY(s + 1), par);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        }
-                        const uint32_t tacc = acc_base + (uint32_t)(s * C);
-                        for (int tt = 0; tt < ntap; tt++) {
-                            const uint32_t a_row = (uint32_t)(s * 128 + (g * p.tps + tt) * dil);
-                            for (int ks = 0; ks < ksteps; ks++) {
-                                const uint64_t adesc = adesc_c + (uint64_t)(a_row + (uint32_t)(ks * 2 * kRtot));
-                                const uint64_t bdesc = bdesc_s + (uint64_t)((uint32_t)tt * tap_16 + (uint32_t)(ks * 2));
-                                const uint32_t accum = (cv || g || tt || ks) ? 1u : 0u;     // conv2 always adds to the residual stream
-                                if (leader) umma_f16(tacc, adesc, bdesc, idesc, accum);
+                            if (ss == 0) {
+                                if (s > 0) mbar_wait(ready0 + 8u * (uint32_t)(s - 1), par);
+                                mbar_wait(ready0 + 8u * (uint32_t)s, par);
                             }
+                            if (s + 1 < kS) mbar_wait(ready0 + 8u * (uint32_t)(s + 1), par);
+                        }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (mw == 0 && g == 0 && ss == 0 && leader) RB_DBG(16 + 2 * (2 * i + cv));
+                        const uint32_t tacc = acc_base + (uint32_t)(s * C);
+                        uint64_t ad = adesc_c + (uint64_t)(uint32_t)(s * 128 + j0 * dil);
+                        uint64_t bd = bdesc_g;
+                        for (int tt = 0; tt < ntap; tt++) {
+                            if (leader) {
+#pragma unroll
+                                for (int ks = 0; ks < ksteps; ks++)
+                                    umma_f16(tacc, ad + (uint64_t)(uint32_t)(ks * 2 * kRtot), bd + (uint64_t)(uint32_t)(ks * 2), idesc,
+                                             (ks || cv || g || tt) ? 1u : 0u);          // conv2 always adds to the residual stream
+                            }
+                            __syncwarp();
+                            ad += (uint64_t)(uint32_t)dil;
+                            bd += (uint64_t)tap_16;
                         }
                         if (g == p.ngroups - 1) {
-                            if (leader) umma_commit(cv ? X_FULL(s) : T1_FULL(s));
+                            if (leader) umma_commit(done0 + 8u * (uint32_t)s);
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
                     if (leader) umma_commit(W_EMPTY(slot));
                     __syncwarp();
                     if (++slot == p.nslots) { slot = 0; phase ^= 1; }
                 }
+                if (mw == 0 && leader) RB_DBG(17 + 2 * (2 * i + cv));
             }
         }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 5) {
+    if (threadIdx.x == 0) RB_DBG(28);
+    if (warp == 4) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_X), "r"((uint32_t)(2 * kS * C)) : "memory");
     }
 }
@@ -357,6 +429,8 @@ __global__ void __launch_bounds__(kRbThreads, (C == 32) ? 2 : 1) k_resblock(cons
 #undef A2_READY
 #undef X_FULL
 #undef inside
+#undef is_out
+#undef RB_DBG
 
 // ---------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -401,12 +475,8 @@ int resblock_pack(const Layer *const conv1[3], const Layer *const conv2[3], ResB
             b1[(size_t)i * C + c] = hb[(size_t)(2 * i) * C + c];
             cb[(size_t)i * C + c] = hb[(size_t)(2 * i + 1) * C + c] + (i ? cb[(size_t)(i - 1) * C + c] : 0.0f);
         }
-    B2_CUDA_OK(cudaMalloc(&q, 6 * (size_t)C * sizeof(float)));
-    allocs.push_back(q); bytes += 6 * (size_t)C * sizeof(float);
-    out.bias1 = reinterpret_cast<float *>(q);
-    out.cbias = out.bias1 + 3 * C;
-    B2_CUDA_OK(cudaMemcpy(out.bias1, b1.data(), 3 * (size_t)C * sizeof(float), cudaMemcpyHostToDevice));
-    B2_CUDA_OK(cudaMemcpy(out.cbias, cb.data(), 3 * (size_t)C * sizeof(float), cudaMemcpyHostToDevice));
+    out.h_bias1 = b1;          // the biases travel as kernel parameters (constant bank)
+    out.h_cbias = cb;
 
     if (umma_init()) return 1;
     void *fn = nullptr;
@@ -432,15 +502,15 @@ void resblock_free(ResBlockPack &p) {
 
 static bool g_rb_attr[64][2] = {};
 
-template <int C>
+template <int C, int NMW>
 static int launch_rb(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int slot) {
     int dev = 0;
     B2_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 64 && !g_rb_attr[dev][slot]) {
-        B2_CUDA_OK(cudaFuncSetAttribute(k_resblock<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B2_CUDA_OK(cudaFuncSetAttribute(k_resblock<C, NMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         g_rb_attr[dev][slot] = true;
     }
-    k_resblock<C><<<grid, kRbThreads, smem, st>>>(tm, p);
+    k_resblock<C, NMW><<<grid, (5 + NMW) * 32, smem, st>>>(tm, p);
     B2_LAUNCH_OK("k_resblock");
     return 0;
 }
@@ -451,9 +521,11 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     if (!a.x || (!a.out32 && !a.outb)) return set_error("resblock: null input or no output");
     if (a.W <= 0 || a.T <= 0) return 0;
     RbParams p;
-    p.x = a.x; p.bias1 = pk.bias1; p.cbias = pk.cbias; p.acc_src = a.acc_src; p.out32 = a.out32; p.outb = a.outb;
+    p.x = a.x; p.acc_src = a.acc_src; p.out32 = a.out32; p.outb = a.outb;
     p.slope = a.slope; p.outb_slope = a.outb_slope; p.div = a.div;
     p.W = a.W; p.T = a.T; p.taps = pk.taps;
+    for (int i = 0; i < 3 * kRbMaxC; i++) { p.bias1[i] = 0.0f; p.cbias[i] = 0.0f; }
+    for (int i = 0; i < 3 * pk.C; i++) { p.bias1[i] = pk.h_bias1[i]; p.cbias[i] = pk.h_cbias[i]; }
     int dsum = 0;
     for (int i = 0; i < 3; i++) dsum += pk.dil[i] + 1;
     p.dil0 = pk.dil[0]; p.dil1 = pk.dil[1]; p.dil2 = pk.dil[2];
@@ -472,8 +544,38 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     const size_t smem = (size_t)p.nslots * p.tps * pk.C * pk.C * 2 + 2 * a_bytes + 24 * 8 + 16;
     if (smem > 227 * 1024) return set_error("resblock: needs %zu bytes of shared memory", smem);
     const CUtensorMap &tm = *reinterpret_cast<const CUtensorMap *>(pk.tmap);
-    if (pk.C == 32) return launch_rb<32>(tm, p, (unsigned)nct, smem, st, 0);
-    return launch_rb<64>(tm, p, (unsigned)nct, smem, st, 1);
+    static const bool dbg_on = getenv("B2_RB_DBG") != nullptr;
+    static unsigned long long *dbg_buf = nullptr;
+    const size_t dbg_n = (size_t)kRbDbgCtas * kRbDbgEvents;
+    if (dbg_on && !dbg_buf) B2_CUDA_OK(cudaMalloc(&dbg_buf, dbg_n * 8));
+    p.dbg = dbg_on ? dbg_buf : nullptr;
+    if (dbg_on) B2_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, dbg_n * 8, st));
+    const int rc = (pk.C == 32) ? launch_rb<32, 2>(tm, p, (unsigned)nct, smem, st, 0) : launch_rb<64, 4>(tm, p, (unsigned)nct, smem, st, 1);
+    if (dbg_on && !rc) {
+        // per-phase averages over the first CTAs of the launch (cycles of the SM clock)
+        B2_CUDA_OK(cudaStreamSynchronize(st));
+        static std::vector<unsigned long long> h;
+        h.resize(dbg_n);
+        B2_CUDA_OK(cudaMemcpy(h.data(), dbg_buf, dbg_n * 8, cudaMemcpyDeviceToHost));
+        const int n = (int)std::min<long long>(kRbDbgCtas, nct);
+        double ev[kRbDbgEvents] = {0};
+        int cnt = 0;
+        for (int b = 0; b < n; b++) {
+            const unsigned long long *r = &h[(size_t)b * kRbDbgEvents];
+            if (!r[0] || !r[28]) continue;
+            cnt++;
+            for (int k = 0; k < kRbDbgEvents; k++) ev[k] += r[k] ? (double)(r[k] - r[0]) : 0.0;
+        }
+        if (cnt) {
+            for (int k = 0; k < kRbDbgEvents; k++) ev[k] /= cnt;
+            fprintf(stderr, "[rb dbg] C=%d k=%d T=%d ctas=%lld (avg of %d) cycles since CTA start: setup %.0f | load done %.0f | end %.0f\n", pk.C, pk.taps, a.T, nct, cnt, ev[1], ev[2], ev[28]);
+            for (int i = 0; i < 3; i++)
+                fprintf(stderr, "[rb dbg]   pair %d: conv1 issue %.0f..%.0f (%.0f) | epi1 first-ready %.0f done %.0f | conv2 issue %.0f..%.0f (%.0f) | epi2 first-ready %.0f done %.0f\n", i,
+                        ev[16 + 4 * i], ev[17 + 4 * i], ev[17 + 4 * i] - ev[16 + 4 * i], ev[3 + 4 * i], ev[4 + 4 * i],
+                        ev[18 + 4 * i], ev[19 + 4 * i], ev[19 + 4 * i] - ev[18 + 4 * i], ev[5 + 4 * i], ev[6 + 4 * i]);
+        }
+    }
+    return rc;
 }
 
 }  // namespace b2

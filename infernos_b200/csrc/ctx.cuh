@@ -25,8 +25,8 @@ struct Layer {
 struct ResBlockPack {
     int C = 0, taps = 0, dil[3] = {1, 1, 1};
     __nv_bfloat16 *w = nullptr;      // [6*taps (+pad)][C][C] bf16: pair0.conv1, pair0.conv2, pair1.conv1, ...
-    float *bias1 = nullptr;          // [3][C]
-    float *cbias = nullptr;          // [3][C] running sums of the conv2 biases
+    std::vector<float> h_bias1;      // [3][C] conv1 biases (host: passed as kernel parameters)
+    std::vector<float> h_cbias;      // [3][C] running sums of the conv2 biases
     void *tmap = nullptr;            // host copy of the CUtensorMap over w
 };
 
