@@ -47,7 +47,7 @@ struct RbParams {
     const float *acc_src;    // optional fp32 [W][T][C] added to the result (MRF sum); may alias out32
     float *out32;            // optional
     __nv_bfloat16 *outb;     // optional: bf16(lrelu(result, outb_slope))
-    float slope, outb_slope, div;
+    float slope, outb_slope, div, rdiv;
     int W, T, taps, H, V, tiles_per_win, tps, ngroups, nslots;
     int dil0, dil1, dil2;
     unsigned long long m_tpw;
@@ -301,8 +301,15 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
                                 for (int j = 0; j < 32; j++) a32[j] = __float_as_uint(__uint_as_float(b32[j]) + __uint_as_float(a32[j]));
                             }
                             if (p.div != 1.0f) {
+                                // v / div as a reciprocal multiply plus one Newton correction (correctly rounded away from
+                                // denormals; __fdiv_rn was 9 % of this kernel's stall samples)
+                                const float rcp = p.rdiv, nd = -p.div;
 #pragma unroll
-                                for (int j = 0; j < 32; j++) a32[j] = __float_as_uint(__fdiv_rn(__uint_as_float(a32[j]), p.div));
+                                for (int j = 0; j < 32; j++) {
+                                    const float v = __uint_as_float(a32[j]);
+                                    const float q = v * rcp;
+                                    a32[j] = __float_as_uint(fmaf(fmaf(nd, q, v), rcp, q));
+                                }
                             }
 #pragma unroll
                             for (int j = 0; j < 8; j++)
@@ -344,74 +351,74 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
         __syncwarp();
     } else {
         // ======================================================================================= MMA issuers
-        const int mw = warp - 5;
-        const int s_first = mw * SPW;
-        const bool leader = elect_one();
-        // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = C, M = 128
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t b_layout = (C == 64) ? 2u : 4u;                 // SWIZZLE_128B : SWIZZLE_64B (a weight row is C bf16)
-        const uint64_t adesc_1 = smem_desc(smem_u32(sA1), (uint32_t)kRtot * 16, 128u, 0u);
-        const uint64_t adesc_2 = smem_desc(smem_u32(sA2), (uint32_t)kRtot * 16, 128u, 0u);
-        const uint64_t bdesc0 = smem_desc(smem_u32(sW), 0u, 8u * (uint32_t)C * 2, b_layout);
-        const uint32_t slot_16 = slot_bytes >> 4, tap_16 = kTapBytes >> 4;
-        constexpr int ksteps = C / 16;
-        int slot = 0; uint32_t phase = 0;
+        // Everything that feeds tcgen05.mma has to live in UNIFORM registers.  The warp index and the TMEM base are therefore
+        // taken through a lane-0 broadcast (which the compiler knows to be warp-uniform) and the whole issue loop runs inside
+        // one elected thread: descriptors are then computed on the uniform datapath, with no per-MMA R2UR traffic.
+        const int mw = __shfl_sync(0xffffffffu, warp, 0) - 5;
+        const uint32_t tX = __shfl_sync(0xffffffffu, tmem_X, 0);
+        if (elect_one()) {
+            const int s_first = mw * SPW;
+            // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = C, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t b_layout = (C == 64) ? 2u : 4u;                 // SWIZZLE_128B : SWIZZLE_64B (a weight row is C bf16)
+            const uint64_t adesc_1 = smem_desc(smem_u32(sA1), (uint32_t)kRtot * 16, 128u, 0u);
+            const uint64_t adesc_2 = smem_desc(smem_u32(sA2), (uint32_t)kRtot * 16, 128u, 0u);
+            const uint64_t bdesc0 = smem_desc(smem_u32(sW), 0u, 8u * (uint32_t)C * 2, b_layout);
+            const uint32_t slot_16 = slot_bytes >> 4, tap_16 = kTapBytes >> 4;
+            constexpr int ksteps = C / 16;
+            int slot = 0; uint32_t phase = 0;
 #pragma unroll 1
-        for (int i = 0; i < 3; i++) {
-            const uint32_t par = (uint32_t)(i & 1);
+            for (int i = 0; i < 3; i++) {
+                const uint32_t par = (uint32_t)(i & 1);
 #pragma unroll 1
-            for (int cv = 0; cv < 2; cv++) {
-                const int dil = cv ? 1 : (i == 0 ? p.dil0 : (i == 1 ? p.dil1 : p.dil2));
-                const int pad = ((p.taps - 1) >> 1) * dil;
-                const uint64_t adesc_c = (cv ? adesc_2 : adesc_1) + (uint64_t)(uint32_t)(kGuard - pad);
-                const uint32_t acc_base = cv ? tmem_X : tmem_T1;
-                const uint32_t ready0 = cv ? A2_READY(0) : A1_READY(0);
-                const uint32_t done0 = cv ? X_FULL(0) : T1_FULL(0);
+                for (int cv = 0; cv < 2; cv++) {
+                    const int dil = cv ? 1 : (i == 0 ? p.dil0 : (i == 1 ? p.dil1 : p.dil2));
+                    const int pad = ((p.taps - 1) >> 1) * dil;
+                    const uint64_t adesc_c = (cv ? adesc_2 : adesc_1) + (uint64_t)(uint32_t)(kGuard - pad);
+                    const uint32_t acc_base = cv ? tX : tX + (uint32_t)(kS * C);
+                    const uint32_t ready0 = cv ? A2_READY(0) : A1_READY(0);
+                    const uint32_t done0 = cv ? X_FULL(0) : T1_FULL(0);
 #pragma unroll 1
-                for (int g = 0; g < p.ngroups; g++) {
-                    mbar_wait(W_FULL(slot), phase);
-                    const uint64_t bdesc_g = bdesc0 + (uint64_t)((uint32_t)slot * slot_16);
-                    const int j0 = g * p.tps;
-                    const int ntap = min(p.tps, p.taps - j0);
+                    for (int g = 0; g < p.ngroups; g++) {
+                        mbar_wait(W_FULL(slot), phase);
+                        const uint64_t bdesc_g = bdesc0 + (uint64_t)((uint32_t)slot * slot_16);
+                        const int j0 = g * p.tps;
+                        const int ntap = min(p.tps, p.taps - j0);
 #pragma unroll 1
-                    for (int ss = 0; ss < SPW; ss++) {
-                        const int s = s_first + ss;
-                        if (g == 0) {
-                            // operand rows of sub-tiles s-1 .. s+1 (the taps reach at most 25 rows out)
-                            if (ss == 0) {
-                                if (s > 0) mbar_wait(ready0 + 8u * (uint32_t)(s - 1), par);
-                                mbar_wait(ready0 + 8u * (uint32_t)s, par);
+                        for (int ss = 0; ss < SPW; ss++) {
+                            const int s = s_first + ss;
+                            if (g == 0) {
+                                // operand rows of sub-tiles s-1 .. s+1 (the taps reach at most 25 rows out)
+                                if (ss == 0) {
+                                    if (s > 0) mbar_wait(ready0 + 8u * (uint32_t)(s - 1), par);
+                                    mbar_wait(ready0 + 8u * (uint32_t)s, par);
+                                }
+                                if (s + 1 < kS) mbar_wait(ready0 + 8u * (uint32_t)(s + 1), par);
                             }
-                            if (s + 1 < kS) mbar_wait(ready0 + 8u * (uint32_t)(s + 1), par);
-                        }
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        if (mw == 0 && g == 0 && ss == 0 && leader) RB_DBG(16 + 2 * (2 * i + cv));
-                        const uint32_t tacc = acc_base + (uint32_t)(s * C);
-                        uint64_t ad = adesc_c + (uint64_t)(uint32_t)(s * 128 + j0 * dil);
-                        uint64_t bd = bdesc_g;
-                        for (int tt = 0; tt < ntap; tt++) {
-                            if (leader) {
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            if (mw == 0 && g == 0 && ss == 0) RB_DBG(16 + 2 * (2 * i + cv));
+                            const uint32_t tacc = acc_base + (uint32_t)(s * C);
+                            uint64_t ad = adesc_c + (uint64_t)(uint32_t)(s * 128 + j0 * dil);
+                            uint64_t bd = bdesc_g;
+#pragma unroll 1
+                            for (int tt = 0; tt < ntap; tt++) {
 #pragma unroll
                                 for (int ks = 0; ks < ksteps; ks++)
                                     umma_f16(tacc, ad + (uint64_t)(uint32_t)(ks * 2 * kRtot), bd + (uint64_t)(uint32_t)(ks * 2), idesc,
                                              (ks || cv || g || tt) ? 1u : 0u);          // conv2 always adds to the residual stream
+                                ad += (uint64_t)(uint32_t)dil;
+                                bd += (uint64_t)tap_16;
                             }
-                            __syncwarp();
-                            ad += (uint64_t)(uint32_t)dil;
-                            bd += (uint64_t)tap_16;
+                            if (g == p.ngroups - 1) umma_commit(done0 + 8u * (uint32_t)s);
                         }
-                        if (g == p.ngroups - 1) {
-                            if (leader) umma_commit(done0 + 8u * (uint32_t)s);
-                            __syncwarp();
-                        }
+                        umma_commit(W_EMPTY(slot));
+                        if (++slot == p.nslots) { slot = 0; phase ^= 1; }
                     }
-                    if (leader) umma_commit(W_EMPTY(slot));
-                    __syncwarp();
-                    if (++slot == p.nslots) { slot = 0; phase ^= 1; }
+                    if (mw == 0) RB_DBG(17 + 2 * (2 * i + cv));
                 }
-                if (mw == 0 && leader) RB_DBG(17 + 2 * (2 * i + cv));
             }
         }
+        __syncwarp();
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -522,7 +529,7 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     if (a.W <= 0 || a.T <= 0) return 0;
     RbParams p;
     p.x = a.x; p.acc_src = a.acc_src; p.out32 = a.out32; p.outb = a.outb;
-    p.slope = a.slope; p.outb_slope = a.outb_slope; p.div = a.div;
+    p.slope = a.slope; p.outb_slope = a.outb_slope; p.div = a.div; p.rdiv = 1.0f / a.div;
     p.W = a.W; p.T = a.T; p.taps = pk.taps;
     for (int i = 0; i < 3 * kRbMaxC; i++) { p.bias1[i] = 0.0f; p.cbias[i] = 0.0f; }
     for (int i = 0; i < 3 * pk.C; i++) { p.bias1[i] = pk.h_bias1[i]; p.cbias[i] = pk.h_cbias[i]; }
