@@ -214,6 +214,7 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
                 if (c0 + 32 == C) {
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     publish_rows(A1_READY(s), lane);
+                    if (threadIdx.x == 0) RB_DBG(44 + s);
                 }
             }
         }
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
+                if (threadIdx.x == 0) RB_DBG(40);
                 // ---- final epilogue: rows [H, H+V) of the slab leave through a per-warp transpose (A1 is dead: every conv1
                 // has retired), 8 lanes per 128 contiguous bytes of an output row
                 float *stg = reinterpret_cast<float *>(sA1) + warp * 32 * kRbStageLd;
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
                     mbar_wait(X_FULL(s), par);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (threadIdx.x == 0 && s == 0) RB_DBG(5 + 4 * i);
+                    if (threadIdx.x == 0) RB_DBG(32 + s);
                     const int grow_own = is_out(s) ? (w * p.T + t_base + s * 128 + rq) : -1;
                     int grow[8];
 #pragma unroll
@@ -332,6 +335,7 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
                         }
                         __syncwarp();
                     }
+                    if (threadIdx.x == 0) RB_DBG(36 + s);
                 }
                 if (threadIdx.x == 0) RB_DBG(6 + 4 * i);
             }
@@ -576,6 +580,8 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
         if (cnt) {
             for (int k = 0; k < kRbDbgEvents; k++) ev[k] /= cnt;
             fprintf(stderr, "[rb dbg] C=%d k=%d T=%d ctas=%lld (avg of %d) cycles since CTA start: setup %.0f | load done %.0f | end %.0f\n", pk.C, pk.taps, a.T, nct, cnt, ev[1], ev[2], ev[28]);
+            fprintf(stderr, "[rb dbg]   load done per sub-tile %.0f %.0f %.0f %.0f | acc parked %.0f | final: ready/done per sub-tile %.0f/%.0f %.0f/%.0f %.0f/%.0f %.0f/%.0f\n",
+                    ev[44], ev[45], ev[46], ev[47], ev[40], ev[32], ev[36], ev[33], ev[37], ev[34], ev[38], ev[35], ev[39]);
             for (int i = 0; i < 3; i++)
                 fprintf(stderr, "[rb dbg]   pair %d: conv1 issue %.0f..%.0f (%.0f) | epi1 first-ready %.0f done %.0f | conv2 issue %.0f..%.0f (%.0f) | epi2 first-ready %.0f done %.0f\n", i,
                         ev[16 + 4 * i], ev[17 + 4 * i], ev[17 + 4 * i] - ev[16 + 4 * i], ev[3 + 4 * i], ev[4 + 4 * i],

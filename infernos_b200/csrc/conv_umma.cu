@@ -258,12 +258,12 @@ __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128
         }
     } else {
         // =========================== MMA issuer ===========================
-        // The whole warp runs the loop so that barrier addresses and descriptors are computed warp-uniformly (they stay in
-        // uniform registers, which is what UTCHMMA takes); one elected lane issues the MMAs and commits.  Issuing from inside
-        // an `if (lane == 0)` region made the compiler wrap every MMA in a register->uniform-register broadcast loop
-        // (~26 instructions per MMA; the issue loop was ~40 % of a thin-layer CTA's lifetime).
-        {
-            const bool leader = elect_one();
+        // Everything that feeds tcgen05.mma has to live in UNIFORM registers: the TMEM base goes through a lane-0 broadcast
+        // (which the compiler knows to be warp-uniform) and the whole issue loop runs inside one elected thread, so that the
+        // descriptors are computed on the uniform datapath.  (With per-lane values every MMA cost ~9 R2UR moves and ~130
+        // cycles of issue time against 40-128 cycles of tensor-pipe time.)
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        if (elect_one()) {
             // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N = N_TILE, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t sA_u32 = smem_u32(sA);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128
             int stage = 0; uint32_t phase = 0; uint32_t accum = 0;
             for (int kb = 0; kb < p.nkb; kb++) {
                 mbar_wait(bar_a_full + 8 * kb, 0);
-                if (kb == 0 && leader) DBG(6);
+                if (kb == 0) DBG(6);
                 if (!(p.flags & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA (async proxy) reads
                 for (int j = 0; j < p.taps; j++) {
                     mbar_wait(bar_b_full + 8 * stage, phase);
@@ -287,15 +287,15 @@ __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128
                         for (int ks = 0; ks < ksteps; ks++) {
                             const uint64_t adesc = adesc0 + (uint64_t)(a_row + (uint32_t)(ks * 2 * p.R + sub * 128));
                             const uint64_t bdesc = bdesc_s + (uint64_t)(ks * 2);
-                            if (leader && !(p.flags & 2)) umma_f16(tmem_base + (uint32_t)(sub * N_TILE), adesc, bdesc, idesc, (accum | (uint32_t)ks) ? 1u : 0u);
+                            if (!(p.flags & 2)) umma_f16(tb + (uint32_t)(sub * N_TILE), adesc, bdesc, idesc, (accum | (uint32_t)ks) ? 1u : 0u);
                         }
                     accum = 1;
-                    if (leader) umma_commit(bar_b_empty + 8 * stage);   // frees the B slot when these MMAs retire
-                    __syncwarp();
+                    umma_commit(bar_b_empty + 8 * stage);   // frees the B slot when these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
-            if (leader) { umma_commit(bar_acc); DBG(5); }
+            umma_commit(bar_acc);
+            DBG(5);
         }
         __syncwarp();
     }
@@ -474,9 +474,9 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
         }
     } else if (warp == 5) {
         // =========================== MMA issuer ===========================
-        // whole warp runs the loop (warp-uniform barrier addresses and descriptors), one elected lane issues: see k_conv_umma
-        {
-            const bool leader = elect_one();
+        // the issue loop runs in one elected thread on the uniform datapath: see k_conv_umma
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        if (elect_one()) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t b_layout = (KB == 64) ? 2u : 4u;
             const uint64_t adesc0 = smem_desc(smem_u32(sA), (uint32_t)p.R * 16, 128u, 0u);
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                 mbar_wait(ACC_EMPTY(acc), (uint32_t)((use & 1) ^ 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t adesc_t = adesc0 + (uint64_t)((uint32_t)abuf * a_buf_16);
-                const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * N_TILE);
+                const uint32_t tmem_acc = tb + (uint32_t)(acc * N_TILE);
                 uint32_t accum = 0;
                 for (int kb = 0; kb < p.nkb; kb++) {
                     mbar_wait(A_FULL(abuf, kb), (uint32_t)(ause & 1));
@@ -507,19 +507,17 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t a_row = (uint32_t)(kb * (KB / 8) * p.R + j * p.dil);
                         for (int ks = 0; ks < ksteps; ks++) {
-                            if (leader && !(p.flags & 2)) umma_f16(tmem_acc, adesc_t + (uint64_t)(a_row + (uint32_t)(ks * 2 * p.R)), bdesc_s + (uint64_t)(ks * 2), idesc, accum);
+                            if (!(p.flags & 2)) umma_f16(tmem_acc, adesc_t + (uint64_t)(a_row + (uint32_t)(ks * 2 * p.R)), bdesc_s + (uint64_t)(ks * 2), idesc, accum);
                             accum = 1;
                         }
                         if (!pp.resident) {
-                            if (leader) umma_commit(B_EMPTY(stage));
+                            umma_commit(B_EMPTY(stage));
                             if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         }
-                        __syncwarp();
                     }
-                    if (leader) umma_commit(A_EMPTY(abuf, kb));     // this K block of the A buffer may be refilled once these MMAs retire
+                    umma_commit(A_EMPTY(abuf, kb));     // this K block of the A buffer may be refilled once these MMAs retire
                 }
-                if (leader) umma_commit(ACC_FULL(acc));
-                __syncwarp();
+                umma_commit(ACC_FULL(acc));
             }
         }
         __syncwarp();
