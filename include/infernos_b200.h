@@ -122,7 +122,7 @@ B2_API int b2_conv1d_f32(const float *d_in, const float *h_weight, const float *
 /* One whole HiFiGAN ResBlock (modeling_speecht5.py:2903-2962) in a single fused tcgen05 launch:
  *   for d in (d0, d1, d2): x = x + conv2(lrelu(conv1_dil_d(lrelu(x, slope)), slope));   v = (d_acc + x) / div
  * d_x fp32 [W][T][C]; h_weights [6][C][C][k] torch layout in the order pair0.conv1, pair0.conv2, pair1.conv1, ...; h_biases [6][C];
- * d_acc optional fp32 [W][T][C]; d_out32 fp32 / d_outb bf16(lrelu(v, outb_slope)) [W][T][C], either may be NULL.  C in {32, 64}. */
+ * d_acc optional fp32 [W][T][C]; d_out32 fp32 / d_outb bf16(lrelu(v, outb_slope)) [W][T][C], either may be NULL.  C in {32, 64, 128}. */
 B2_API int b2_resblock_tc(const float *d_x, const float *h_weights, const float *h_biases, int W, int T, int C, int k, int d0, int d1, int d2,
                           const float *d_acc, float *d_out32, void *d_outb, float slope, float outb_slope, float div, void *stream);
 

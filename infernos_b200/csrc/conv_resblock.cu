@@ -35,12 +35,19 @@
 
 namespace b2 {
 
-static constexpr int kS = 4;                               // 128-row sub-tiles per CTA
-static constexpr int kRows = 128 * kS;                     // slab rows
 static constexpr int kGuard = 26;                          // zero rows either side of the slab (>= largest pad, 5*5)
-static constexpr int kRtot = kGuard + kRows + kGuard + 1;  // rows of an operand buffer (odd: K-chunks land on different banks)
 static constexpr int kRbStageLd = 36;                      // floats per staged row of the output transpose (32 + 4 pad)
-static constexpr int kRbMaxC = 64;
+static constexpr int kRbMaxC = 128;
+
+// per-width geometry: TMEM holds X and T1 (2 * kS * C fp32 columns <= 512), so a CTA owns 4 sub-tiles up to C = 64 and 2 at C = 128
+template <int C> struct RbGeom {
+    static constexpr int kS = (C <= 64) ? 4 : 2;               // 128-row sub-tiles per CTA
+    static constexpr int kRows = 128 * kS;                     // slab rows
+    static constexpr int kRtot = kGuard + kRows + kGuard + 1;  // rows of an operand buffer (odd: K-chunks land on different banks)
+    static constexpr int KB = (C >= 64) ? 64 : 32;             // K block of a weight tile (one swizzle span)
+    static constexpr int NKB = C / KB;
+    static constexpr uint32_t kABytes = ((uint32_t)kRtot * C * 2 + 1023u) & ~1023u;
+};
 
 struct RbParams {
     const float *x;          // [W][T][C] fp32
@@ -83,7 +90,8 @@ __device__ __forceinline__ void ld_row32(const float *src, bool ok, uint32_t (&v
 }
 
 // 32 consecutive channels [c0, c0+32) of buffer row r -> bf16(lrelu(v + bias)) (zeros when !keep) in the interleaved operand
-// layout.  slope is in (0, 1), so leaky_relu(v) == max(v, slope * v).
+// layout (RT rows per 8-channel chunk).  slope is in (0, 1), so leaky_relu(v) == max(v, slope * v).
+template <int RT>
 __device__ __forceinline__ void write_operand_row(uint32_t sA_u32, int r, int c0, const uint32_t (&v)[32], const float *bias, float slope, bool keep) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -98,7 +106,7 @@ __device__ __forceinline__ void write_operand_row(uint32_t sA_u32, int r, int c0
             __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
             pk[e] = keep ? *reinterpret_cast<uint32_t *>(&h2) : 0u;
         }
-        const uint32_t dst = sA_u32 + (uint32_t)(((((c0 >> 3) + i) * kRtot) + kGuard + r) * 16);
+        const uint32_t dst = sA_u32 + (uint32_t)(((((c0 >> 3) + i) * RT) + kGuard + r) * 16);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
     }
 }
@@ -114,20 +122,24 @@ __device__ __forceinline__ void publish_rows(uint32_t bar, int lane) {
 static constexpr int kRbDbgEvents = 48, kRbDbgCtas = 4096;
 #define RB_DBG(k) do { if (p.dbg && blockIdx.x < kRbDbgCtas) p.dbg[(size_t)blockIdx.x * kRbDbgEvents + (k)] = clock64(); } while (0)
 
-// Warp roles: 0-3 slab load + all epilogues (TMEM lanes 32*warp..), 4 TMEM alloc + TMA weight ring, 5.. MMA issuers.
-// One warp cannot issue these small MMAs fast enough (an M128 x N32 x K16 MMA occupies the tensor pipe for 40 cycles, its issue
-// sequence -- descriptors through R2UR -- costs ~130): NMW warps issue in parallel, each owning kS / NMW sub-tiles.
-template <int C, int NMW>
-__global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ RbParams p) {
+// Warp roles: [0, NEW) slab load + all epilogues (warp e: TMEM lane quadrant e % 4, column slice e / 4), warp NEW = TMEM alloc +
+// TMA weight ring, then NMW MMA-issuing warps, each owning kS / NMW sub-tiles (a sub-tile's accumulator is only ever touched by
+// one issuing thread, so the summation order is fixed).
+template <int C, int NEW, int NMW>
+__global__ void __launch_bounds__((NEW + 1 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ RbParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    using G = RbGeom<C>;
+    constexpr int kS = G::kS, kRows = G::kRows, kRtot = G::kRtot, KB = G::KB, NKB = G::NKB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int kThreads = (5 + NMW) * 32;
+    constexpr int kThreads = (NEW + 1 + NMW) * 32;
     constexpr int CH = C / 32;                                  // 32-column chunks per row
-    constexpr int NCH = kS * CH;
+    constexpr int CHW = CH / (NEW / 4);                         // ... of which one epilogue warp handles CHW
+    constexpr int NCHW = kS * CHW;
     constexpr int SPW = kS / NMW;                               // sub-tiles per MMA warp
-    constexpr uint32_t kTapBytes = (uint32_t)C * C * 2;
-    constexpr uint32_t kABytes = ((uint32_t)kRtot * C * 2 + 1023u) & ~1023u;
-    const uint32_t slot_bytes = (uint32_t)p.tps * kTapBytes;
+    constexpr uint32_t kTapKbBytes = (uint32_t)C * KB * 2;      // one tap, one K block
+    constexpr uint32_t kABytes = G::kABytes;
+    static_assert(CH % (NEW / 4) == 0 && kS % NMW == 0 && 2 * kS * C <= 512, "unsupported geometry");
+    const uint32_t slot_bytes = (uint32_t)p.tps * kTapKbBytes;
     uint8_t *sW = smem;
     uint8_t *sA1 = smem + (size_t)p.nslots * slot_bytes;
     uint8_t *sA2 = sA1 + kABytes;
@@ -148,12 +160,12 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
 
     if (threadIdx.x == 0) RB_DBG(0);
     // ---- prologue
-    if (warp == 4) {
+    if (warp == NEW) {
         if (lane == 0) {
             if (smem_u32(smem) & 1023u) __trap();
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
             for (int s = 0; s < 4; s++) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), NMW); }
-            for (int s = 0; s < kS; s++) { mbar_init(A1_READY(s), 4); mbar_init(T1_FULL(s), 1); mbar_init(A2_READY(s), 4); mbar_init(X_FULL(s), 1); }
+            for (int s = 0; s < kS; s++) { mbar_init(A1_READY(s), NEW); mbar_init(T1_FULL(s), 1); mbar_init(A2_READY(s), NEW); mbar_init(X_FULL(s), 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -180,12 +192,14 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
     const uint32_t tmem_T1 = tmem_X + (uint32_t)(kS * C);
     if (threadIdx.x == 0) RB_DBG(1);
 
-    if (warp < 4) {
+    if (warp < NEW) {
         // ======================================================================================= slab load + epilogues
-        const int rq = warp * 32 + lane;                       // row inside a sub-tile == TMEM lane
-        const uint32_t tm_lane = (uint32_t)(warp * 32) << 16;
+        const int quad = warp & 3;                             // TMEM lane quadrant this warp may touch
+        const int cbase = (warp >> 2) * (CHW * 32);            // first column of this warp's slice
+        const int rq = quad * 32 + lane;                       // row inside a sub-tile == TMEM lane
+        const uint32_t tm_lane = (uint32_t)(quad * 32) << 16;
         const uint32_t a1_u32 = smem_u32(sA1), a2_u32 = smem_u32(sA2);
-        const float *xrow = p.x + ((size_t)w * p.T + (t_base + rq)) * C;          // row rq of sub-tile 0 (may lie outside: guarded)
+        const float *xrow = p.x + ((size_t)w * p.T + (t_base + rq)) * C + cbase;  // row rq of sub-tile 0 (may lie outside: guarded)
         uint32_t inside_mask = 0, out_mask = 0;                 // bit s: this lane's row of sub-tile s is inside the window / is an output row
 #pragma unroll
         for (int s = 0; s < kS; s++) {
@@ -201,17 +215,17 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
             uint32_t bufA[32], bufB[32];
             ld_row32(xrow, inside(0), bufA);
 #pragma unroll
-            for (int q = 0; q < NCH; q++) {
-                const int s = q / CH, c0 = (q % CH) * 32;
+            for (int q = 0; q < NCHW; q++) {
+                const int s = q / CHW, c0 = cbase + (q % CHW) * 32;
                 uint32_t (&v)[32] = (q & 1) ? bufB : bufA;
                 uint32_t (&nx)[32] = (q & 1) ? bufA : bufB;
-                if (q + 1 < NCH) {
-                    const int s1 = (q + 1) / CH, c1 = ((q + 1) % CH) * 32;
+                if (q + 1 < NCHW) {
+                    const int s1 = (q + 1) / CHW, c1 = ((q + 1) % CHW) * 32;
                     ld_row32(xrow + (size_t)s1 * 128 * C + c1, inside(s1), nx);
                 }
                 tmem_st32(tmem_X + tm_lane + (uint32_t)(s * C + c0), v);
-                write_operand_row(a1_u32, s * 128 + rq, c0, v, nullptr, p.slope, true);
-                if (c0 + 32 == C) {
+                write_operand_row<kRtot>(a1_u32, s * 128 + rq, c0, v, nullptr, p.slope, true);
+                if ((q % CHW) == CHW - 1) {
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     publish_rows(A1_READY(s), lane);
                     if (threadIdx.x == 0) RB_DBG(44 + s);
@@ -230,10 +244,11 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (threadIdx.x == 0 && s == 0) RB_DBG(3 + 4 * i);
 #pragma unroll
-                for (int c0 = 0; c0 < C; c0 += 32) {
+                for (int cc = 0; cc < CHW; cc++) {
+                    const int c0 = cbase + cc * 32;
                     uint32_t acc[32];
                     tmem_ld32(tmem_T1 + tm_lane + (uint32_t)(s * C + c0), acc);
-                    write_operand_row(a2_u32, s * 128 + rq, c0, acc, p.bias1 + i * C + c0, p.slope, inside(s));
+                    write_operand_row<kRtot>(a2_u32, s * 128 + rq, c0, acc, p.bias1 + i * C + c0, p.slope, inside(s));
                 }
                 publish_rows(A2_READY(s), lane);
             }
@@ -246,10 +261,11 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (threadIdx.x == 0 && s == 0) RB_DBG(5 + 4 * i);
 #pragma unroll
-                    for (int c0 = 0; c0 < C; c0 += 32) {
+                    for (int cc = 0; cc < CHW; cc++) {
+                        const int c0 = cbase + cc * 32;
                         uint32_t acc[32];
                         tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C + c0), acc);
-                        write_operand_row(a1_u32, s * 128 + rq, c0, acc, p.cbias + i * C + c0, p.slope, inside(s));
+                        write_operand_row<kRtot>(a1_u32, s * 128 + rq, c0, acc, p.cbias + i * C + c0, p.slope, inside(s));
                     }
                     publish_rows(A1_READY(s), lane);
                 }
@@ -258,16 +274,16 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
                 // ---- while the last conv2 runs: T1 is idle from here on, so the MRF partial sum (acc_src) of this lane's output
                 // rows is parked there; the final epilogue then never waits on global memory
                 if (p.acc_src) {
-                    const float *arow = p.acc_src + ((size_t)w * p.T + (t_base + rq)) * C;
+                    const float *arow = p.acc_src + ((size_t)w * p.T + (t_base + rq)) * C + cbase;
                     uint32_t bufA[32], bufB[32];
                     ld_row32(arow, is_out(0), bufA);
 #pragma unroll
-                    for (int q = 0; q < NCH; q++) {
-                        const int s = q / CH, c0 = (q % CH) * 32;
+                    for (int q = 0; q < NCHW; q++) {
+                        const int s = q / CHW, c0 = cbase + (q % CHW) * 32;
                         uint32_t (&v)[32] = (q & 1) ? bufB : bufA;
                         uint32_t (&nx)[32] = (q & 1) ? bufA : bufB;
-                        if (q + 1 < NCH) {
-                            const int s1 = (q + 1) / CH, c1 = ((q + 1) % CH) * 32;
+                        if (q + 1 < NCHW) {
+                            const int s1 = (q + 1) / CHW, c1 = ((q + 1) % CHW) * 32;
                             ld_row32(arow + (size_t)s1 * 128 * C + c1, is_out(s1), nx);
                         }
                         tmem_st32(tmem_T1 + tm_lane + (uint32_t)(s * C + c0), v);
@@ -290,7 +306,8 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
 #pragma unroll
                     for (int j = 0; j < 8; j++) grow[j] = __shfl_sync(0xffffffffu, grow_own, j * 4 + sub_r);
 #pragma unroll 1
-                    for (int c0 = 0; c0 < C; c0 += 32) {
+                    for (int cc = 0; cc < CHW; cc++) {
+                        const int c0 = cbase + cc * 32;
                         {
                             uint32_t a32[32];
                             tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C + c0), a32);
@@ -340,17 +357,18 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
                 if (threadIdx.x == 0) RB_DBG(6 + 4 * i);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == NEW) {
         // ======================================================================================= weight ring (TMA)
         if (lane == 0) {
             int slot = 0; uint32_t phase = 0;
             for (int c = 0; c < 6; c++)
-                for (int g = 0; g < p.ngroups; g++) {
-                    mbar_wait(W_EMPTY(slot), phase ^ 1);
-                    mbar_expect_tx(W_FULL(slot), slot_bytes);
-                    tma_load_3d(smem_u32(sW + (size_t)slot * slot_bytes), &tmap_w, W_FULL(slot), 0, 0, c * p.taps + g * p.tps);
-                    if (++slot == p.nslots) { slot = 0; phase ^= 1; }
-                }
+                for (int g = 0; g < p.ngroups; g++)
+                    for (int kb = 0; kb < NKB; kb++) {
+                        mbar_wait(W_EMPTY(slot), phase ^ 1);
+                        mbar_expect_tx(W_FULL(slot), slot_bytes);
+                        tma_load_3d(smem_u32(sW + (size_t)slot * slot_bytes), &tmap_w, W_FULL(slot), kb * KB, 0, c * p.taps + g * p.tps);
+                        if (++slot == p.nslots) { slot = 0; phase ^= 1; }
+                    }
         }
         __syncwarp();
     } else {
@@ -358,18 +376,18 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
         // Everything that feeds tcgen05.mma has to live in UNIFORM registers.  The warp index and the TMEM base are therefore
         // taken through a lane-0 broadcast (which the compiler knows to be warp-uniform) and the whole issue loop runs inside
         // one elected thread: descriptors are then computed on the uniform datapath, with no per-MMA R2UR traffic.
-        const int mw = __shfl_sync(0xffffffffu, warp, 0) - 5;
+        const int mw = __shfl_sync(0xffffffffu, warp, 0) - (NEW + 1);
         const uint32_t tX = __shfl_sync(0xffffffffu, tmem_X, 0);
         if (elect_one()) {
             const int s_first = mw * SPW;
             // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = C, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t b_layout = (C == 64) ? 2u : 4u;                 // SWIZZLE_128B : SWIZZLE_64B (a weight row is C bf16)
+            const uint32_t b_layout = (KB == 64) ? 2u : 4u;                // SWIZZLE_128B : SWIZZLE_64B (a weight row is KB bf16)
             const uint64_t adesc_1 = smem_desc(smem_u32(sA1), (uint32_t)kRtot * 16, 128u, 0u);
             const uint64_t adesc_2 = smem_desc(smem_u32(sA2), (uint32_t)kRtot * 16, 128u, 0u);
-            const uint64_t bdesc0 = smem_desc(smem_u32(sW), 0u, 8u * (uint32_t)C * 2, b_layout);
-            const uint32_t slot_16 = slot_bytes >> 4, tap_16 = kTapBytes >> 4;
-            constexpr int ksteps = C / 16;
+            const uint64_t bdesc0 = smem_desc(smem_u32(sW), 0u, 8u * (uint32_t)KB * 2, b_layout);
+            const uint32_t slot_16 = slot_bytes >> 4, tap_16 = kTapKbBytes >> 4;
+            constexpr int ksteps = KB / 16;
             int slot = 0; uint32_t phase = 0;
 #pragma unroll 1
             for (int i = 0; i < 3; i++) {
@@ -384,39 +402,43 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
                     const uint32_t done0 = cv ? X_FULL(0) : T1_FULL(0);
 #pragma unroll 1
                     for (int g = 0; g < p.ngroups; g++) {
-                        mbar_wait(W_FULL(slot), phase);
-                        const uint64_t bdesc_g = bdesc0 + (uint64_t)((uint32_t)slot * slot_16);
                         const int j0 = g * p.tps;
                         const int ntap = min(p.tps, p.taps - j0);
 #pragma unroll 1
-                        for (int ss = 0; ss < SPW; ss++) {
-                            const int s = s_first + ss;
-                            if (g == 0) {
-                                // operand rows of sub-tiles s-1 .. s+1 (the taps reach at most 25 rows out)
-                                if (ss == 0) {
-                                    if (s > 0) mbar_wait(ready0 + 8u * (uint32_t)(s - 1), par);
-                                    mbar_wait(ready0 + 8u * (uint32_t)s, par);
-                                }
-                                if (s + 1 < kS) mbar_wait(ready0 + 8u * (uint32_t)(s + 1), par);
-                            }
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            if (mw == 0 && g == 0 && ss == 0) RB_DBG(16 + 2 * (2 * i + cv));
-                            const uint32_t tacc = acc_base + (uint32_t)(s * C);
-                            uint64_t ad = adesc_c + (uint64_t)(uint32_t)(s * 128 + j0 * dil);
-                            uint64_t bd = bdesc_g;
+                        for (int kb = 0; kb < NKB; kb++) {
+                            mbar_wait(W_FULL(slot), phase);
+                            const uint64_t bdesc_g = bdesc0 + (uint64_t)((uint32_t)slot * slot_16);
+                            const bool first = (g == 0) && (kb == 0), last = (g == p.ngroups - 1) && (kb == NKB - 1);
 #pragma unroll 1
-                            for (int tt = 0; tt < ntap; tt++) {
+                            for (int ss = 0; ss < SPW; ss++) {
+                                const int s = s_first + ss;
+                                if (first) {
+                                    // operand rows of sub-tiles s-1 .. s+1 (the taps reach at most 25 rows out)
+                                    if (ss == 0) {
+                                        if (s > 0) mbar_wait(ready0 + 8u * (uint32_t)(s - 1), par);
+                                        mbar_wait(ready0 + 8u * (uint32_t)s, par);
+                                    }
+                                    if (s + 1 < kS) mbar_wait(ready0 + 8u * (uint32_t)(s + 1), par);
+                                }
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                if (mw == 0 && first && ss == 0) RB_DBG(16 + 2 * (2 * i + cv));
+                                const uint32_t tacc = acc_base + (uint32_t)(s * C);
+                                uint64_t ad = adesc_c + (uint64_t)(uint32_t)(s * 128 + j0 * dil + kb * (KB / 8) * kRtot);
+                                uint64_t bd = bdesc_g;
+#pragma unroll 1
+                                for (int tt = 0; tt < ntap; tt++) {
 #pragma unroll
-                                for (int ks = 0; ks < ksteps; ks++)
-                                    umma_f16(tacc, ad + (uint64_t)(uint32_t)(ks * 2 * kRtot), bd + (uint64_t)(uint32_t)(ks * 2), idesc,
-                                             (ks || cv || g || tt) ? 1u : 0u);          // conv2 always adds to the residual stream
-                                ad += (uint64_t)(uint32_t)dil;
-                                bd += (uint64_t)tap_16;
+                                    for (int ks = 0; ks < ksteps; ks++)
+                                        umma_f16(tacc, ad + (uint64_t)(uint32_t)(ks * 2 * kRtot), bd + (uint64_t)(uint32_t)(ks * 2), idesc,
+                                                 (ks || cv || !first || tt) ? 1u : 0u);      // conv2 always adds to the residual stream
+                                    ad += (uint64_t)(uint32_t)dil;
+                                    bd += (uint64_t)tap_16;
+                                }
+                                if (last) umma_commit(done0 + 8u * (uint32_t)s);
                             }
-                            if (g == p.ngroups - 1) umma_commit(done0 + 8u * (uint32_t)s);
+                            umma_commit(W_EMPTY(slot));
+                            if (++slot == p.nslots) { slot = 0; phase ^= 1; }
                         }
-                        umma_commit(W_EMPTY(slot));
-                        if (++slot == p.nslots) { slot = 0; phase ^= 1; }
                     }
                     if (mw == 0) RB_DBG(17 + 2 * (2 * i + cv));
                 }
@@ -428,7 +450,7 @@ __global__ void __launch_bounds__((5 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) RB_DBG(28);
-    if (warp == 4) {
+    if (warp == NEW) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_X), "r"((uint32_t)(2 * kS * C)) : "memory");
     }
 }
@@ -448,10 +470,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int tps_for(int C) { return 4; }
-static int nslots_for(int C) { return C == 32 ? 4 : 2; }
+static int tps_for(int C) { return C <= 64 ? 4 : 1; }           // taps per weight slot
+static int nslots_for(int C) { return C == 64 ? 2 : 4; }          // slots of 8 KB (C=32), 32 KB (C=64), 16 KB (C=128: one tap, one K block)
+static int kb_for(int C) { return C >= 64 ? 64 : 32; }
+static int rows_for(int C) { return C <= 64 ? 512 : 256; }
 
-bool resblock_supported(int C, int taps) { return (C == 32 || C == 64) && (taps & 1) && taps >= 3 && taps <= 11; }
+bool resblock_supported(int C, int taps) { return (C == 32 || C == 64 || C == 128) && (taps & 1) && taps >= 3 && taps <= 11; }
 
 int resblock_pack(const Layer *const conv1[3], const Layer *const conv2[3], ResBlockPack &out, std::vector<void *> &allocs, size_t &bytes) {
     const int C = conv1[0]->Cin, k = conv1[0]->taps;
@@ -497,10 +521,10 @@ int resblock_pack(const Layer *const conv1[3], const Layer *const conv2[3], ResB
     CUtensorMap *tm = new CUtensorMap();
     cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)C, (cuuint64_t)(6 * k + tps)};
     cuuint64_t gstr[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * C * 2};
-    cuuint32_t box[3] = {(cuuint32_t)C, (cuuint32_t)C, (cuuint32_t)tps};
+    cuuint32_t box[3] = {(cuuint32_t)kb_for(C), (cuuint32_t)C, (cuuint32_t)tps};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)out.w, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                                     C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                     C >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete tm; return set_error("resblock: cuTensorMapEncodeTiled failed with CUresult %d (C %d k %d)", (int)r, C, k); }
     out.tmap = tm;
@@ -511,17 +535,17 @@ void resblock_free(ResBlockPack &p) {
     if (p.tmap) { delete reinterpret_cast<CUtensorMap *>(p.tmap); p.tmap = nullptr; }
 }
 
-static bool g_rb_attr[64][2] = {};
+static bool g_rb_attr[64][3] = {};
 
-template <int C, int NMW>
+template <int C, int NEW, int NMW>
 static int launch_rb(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int slot) {
     int dev = 0;
     B2_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 64 && !g_rb_attr[dev][slot]) {
-        B2_CUDA_OK(cudaFuncSetAttribute(k_resblock<C, NMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B2_CUDA_OK(cudaFuncSetAttribute(k_resblock<C, NEW, NMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         g_rb_attr[dev][slot] = true;
     }
-    k_resblock<C, NMW><<<grid, (5 + NMW) * 32, smem, st>>>(tm, p);
+    k_resblock<C, NEW, NMW><<<grid, (NEW + 1 + NMW) * 32, smem, st>>>(tm, p);
     B2_LAUNCH_OK("k_resblock");
     return 0;
 }
@@ -540,19 +564,25 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     int dsum = 0;
     for (int i = 0; i < 3; i++) dsum += pk.dil[i] + 1;
     p.dil0 = pk.dil[0]; p.dil1 = pk.dil[1]; p.dil2 = pk.dil[2];
-    p.H = ((pk.taps - 1) / 2) * dsum;
-    const int vmax = kRows - 2 * p.H;
-    if (vmax < 64) return set_error("resblock: halo %d leaves no room in a %d-row slab", p.H, kRows);
-    p.tiles_per_win = cdiv(a.T, vmax);
-    p.V = cdiv(a.T, p.tiles_per_win);
+    const int rows = rows_for(pk.C);
+    if (a.T <= rows) {
+        // the whole window fits in one slab: its edges are the reference's own zero padding, no halo is needed
+        p.H = 0; p.tiles_per_win = 1; p.V = a.T;
+    } else {
+        p.H = ((pk.taps - 1) / 2) * dsum;
+        const int vmax = rows - 2 * p.H;
+        if (vmax < 64) return set_error("resblock: halo %d leaves no room in a %d-row slab", p.H, rows);
+        p.tiles_per_win = cdiv(a.T, vmax);
+        p.V = cdiv(a.T, p.tiles_per_win);
+    }
     p.m_tpw = ((1ull << 40) + (unsigned long long)p.tiles_per_win - 1) / (unsigned long long)p.tiles_per_win;
     p.tps = tps_for(pk.C);
     p.ngroups = cdiv(pk.taps, p.tps);
     p.nslots = nslots_for(pk.C);
     const long long nct = (long long)a.W * p.tiles_per_win;
     if (nct >= (1ll << 24)) return set_error("resblock: too many tiles (%lld)", nct);
-    const size_t a_bytes = ((size_t)kRtot * pk.C * 2 + 1023) & ~(size_t)1023;
-    const size_t smem = (size_t)p.nslots * p.tps * pk.C * pk.C * 2 + 2 * a_bytes + 24 * 8 + 16;
+    const size_t a_bytes = ((size_t)(rows + 2 * kGuard + 1) * pk.C * 2 + 1023) & ~(size_t)1023;
+    const size_t smem = (size_t)p.nslots * p.tps * pk.C * kb_for(pk.C) * 2 + 2 * a_bytes + 24 * 8 + 16;
     if (smem > 227 * 1024) return set_error("resblock: needs %zu bytes of shared memory", smem);
     const CUtensorMap &tm = *reinterpret_cast<const CUtensorMap *>(pk.tmap);
     static const bool dbg_on = getenv("B2_RB_DBG") != nullptr;
@@ -561,7 +591,8 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     if (dbg_on && !dbg_buf) B2_CUDA_OK(cudaMalloc(&dbg_buf, dbg_n * 8));
     p.dbg = dbg_on ? dbg_buf : nullptr;
     if (dbg_on) B2_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, dbg_n * 8, st));
-    const int rc = (pk.C == 32) ? launch_rb<32, 2>(tm, p, (unsigned)nct, smem, st, 0) : launch_rb<64, 4>(tm, p, (unsigned)nct, smem, st, 1);
+    const int rc = (pk.C == 32) ? launch_rb<32, 4, 2>(tm, p, (unsigned)nct, smem, st, 0)
+                   : (pk.C == 64) ? launch_rb<64, 8, 2>(tm, p, (unsigned)nct, smem, st, 1) : launch_rb<128, 8, 2>(tm, p, (unsigned)nct, smem, st, 2);
     if (dbg_on && !rc) {
         // per-phase averages over the first CTAs of the launch (cycles of the SM clock)
         B2_CUDA_OK(cudaStreamSynchronize(st));

@@ -58,6 +58,7 @@ SHAPES = [
     (3, 3072, 32, 11), (2, 3072, 32, 7), (2, 3072, 32, 3),
     (2, 768, 64, 11), (3, 768, 64, 7), (2, 768, 64, 3),
     (3, 100, 32, 7), (2, 700, 64, 11), (1, 393, 32, 11), (5, 1, 32, 3), (2, 513, 64, 3),
+    (3, 192, 128, 3), (2, 192, 128, 7), (3, 192, 128, 11), (2, 600, 128, 7), (1, 257, 128, 3), (2, 40, 128, 11),
 ]
 
 
@@ -96,10 +97,10 @@ def test_fused_resblock_output_options():
 def test_fused_resblock_rejects_unsupported_width():
     from infernos_b200 import _lib
     lib = _lib.load()
-    x = torch.zeros(1, 8, 128, device="cuda")
-    w = torch.zeros(6, 128, 128, 3)
-    b = torch.zeros(6, 128)
-    o = torch.zeros(1, 8, 128, device="cuda")
-    rc = lib.b2_resblock_tc(x.data_ptr(), w.data_ptr(), b.data_ptr(), 1, 8, 128, 3, 1, 3, 5, None, o.data_ptr(), None, 0.1, 0.1, 1.0, None)
+    x = torch.zeros(1, 8, 256, device="cuda")
+    w = torch.zeros(6, 256, 256, 3)
+    b = torch.zeros(6, 256)
+    o = torch.zeros(1, 8, 256, device="cuda")
+    rc = lib.b2_resblock_tc(x.data_ptr(), w.data_ptr(), b.data_ptr(), 1, 8, 256, 3, 1, 3, 5, None, o.data_ptr(), None, 0.1, 0.1, 1.0, None)
     assert rc != 0
     assert b"unsupported" in lib.b2_last_error(None)
