@@ -126,7 +126,7 @@ static constexpr int kRbDbgEvents = 48, kRbDbgCtas = 4096;
 // TMA weight ring, then NMW MMA-issuing warps, each owning kS / NMW sub-tiles (a sub-tile's accumulator is only ever touched by
 // one issuing thread, so the summation order is fixed).
 template <int C, int NEW, int NMW>
-__global__ void __launch_bounds__((NEW + 1 + NMW) * 32, (C == 32) ? 2 : 1) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ RbParams p) {
+__global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 128 : 168) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ RbParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using G = RbGeom<C>;
     constexpr int kS = G::kS, kRows = G::kRows, kRtot = G::kRtot, KB = G::KB, NKB = G::NKB;
@@ -199,7 +199,6 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32, (C == 32) ? 2 : 1) k_res
         const int rq = quad * 32 + lane;                       // row inside a sub-tile == TMEM lane
         const uint32_t tm_lane = (uint32_t)(quad * 32) << 16;
         const uint32_t a1_u32 = smem_u32(sA1), a2_u32 = smem_u32(sA2);
-        const float *xrow = p.x + ((size_t)w * p.T + (t_base + rq)) * C + cbase;  // row rq of sub-tile 0 (may lie outside: guarded)
         uint32_t inside_mask = 0, out_mask = 0;                 // bit s: this lane's row of sub-tile s is inside the window / is an output row
 #pragma unroll
         for (int s = 0; s < kS; s++) {
@@ -210,19 +209,40 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32, (C == 32) ? 2 : 1) k_res
 #define inside(s) (((inside_mask >> (s)) & 1u) != 0u)
 #define is_out(s) (((out_mask >> (s)) & 1u) != 0u)
 
-        // ---- x -> X (TMEM) and lrelu(x) -> A1.  A lane owns a row and reads the row's 128-byte pieces itself, one piece ahead.
-        {
-            uint32_t bufA[32], bufB[32];
-            ld_row32(xrow, inside(0), bufA);
+        // ---- x -> X (TMEM) and lrelu(x) -> A1.  Global memory is read coalesced (8 lanes per 128 contiguous bytes of a row, one
+        // 32x32 piece ahead) and turned into the lane-owns-a-row order TMEM wants by a per-warp transpose through shared memory
+        // (A2 is free until the first epilogue).  Row-per-lane loads cost 8x the LSU wavefronts and made this phase ~10k cycles.
+        const int sub_r = lane >> 3, c4 = lane & 7;
+        uint32_t inside_t[8];                                  // inside_mask of the rows this lane touches in the transposed order
 #pragma unroll
-            for (int q = 0; q < NCHW; q++) {
+        for (int j = 0; j < 8; j++) inside_t[j] = __shfl_sync(0xffffffffu, inside_mask, j * 4 + sub_r);
+        {
+            float *stg = reinterpret_cast<float *>(sA2) + warp * 32 * kRbStageLd;
+            const float *xq = p.x + ((size_t)w * p.T + (t_base + quad * 32 + sub_r)) * C + cbase + c4 * 4;   // row sub_r of this warp's rows in sub-tile 0
+            auto ld_piece = [&](int q, uint4 (&b)[8]) {
+                const int s1 = q / CHW, c1 = (q % CHW) * 32;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    b[j] = ((inside_t[j] >> s1) & 1u) ? __ldg(reinterpret_cast<const uint4 *>(xq + ((size_t)s1 * 128 + j * 4) * C + c1)) : make_uint4(0u, 0u, 0u, 0u);
+            };
+            uint4 bufA[8], bufB[8];
+            ld_piece(0, bufA);
+            // one piece: prefetch the next, transpose this one through shared memory, hand it to TMEM and to A1.  The loop is
+            // kept ROLLED (two pieces per trip for the ping-pong buffers): the kernel's code has to stay inside the 32 KB
+            // instruction cache, fully unrolled phases made every CTA start run at L2 instruction-fetch speed.
+            auto piece = [&](int q, uint4 (&cur)[8], uint4 (&nx)[8]) {
                 const int s = q / CHW, c0 = cbase + (q % CHW) * 32;
-                uint32_t (&v)[32] = (q & 1) ? bufB : bufA;
-                uint32_t (&nx)[32] = (q & 1) ? bufA : bufB;
-                if (q + 1 < NCHW) {
-                    const int s1 = (q + 1) / CHW, c1 = ((q + 1) % CHW) * 32;
-                    ld_row32(xrow + (size_t)s1 * 128 * C + c1, inside(s1), nx);
+                if (q + 1 < NCHW) ld_piece(q + 1, nx);
+#pragma unroll
+                for (int j = 0; j < 8; j++) *reinterpret_cast<uint4 *>(stg + (j * 4 + sub_r) * kRbStageLd + c4 * 4) = cur[j];
+                __syncwarp();
+                uint32_t v[32];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint4 t4 = *reinterpret_cast<const uint4 *>(stg + lane * kRbStageLd + j * 4);
+                    v[4 * j] = t4.x; v[4 * j + 1] = t4.y; v[4 * j + 2] = t4.z; v[4 * j + 3] = t4.w;
                 }
+                __syncwarp();
                 tmem_st32(tmem_X + tm_lane + (uint32_t)(s * C + c0), v);
                 write_operand_row<kRtot>(a1_u32, s * 128 + rq, c0, v, nullptr, p.slope, true);
                 if ((q % CHW) == CHW - 1) {
@@ -230,15 +250,35 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32, (C == 32) ? 2 : 1) k_res
                     publish_rows(A1_READY(s), lane);
                     if (threadIdx.x == 0) RB_DBG(44 + s);
                 }
+            };
+            static_assert(NCHW % 2 == 0, "ping-pong needs an even number of pieces");
+#pragma unroll 1
+            for (int q = 0; q < NCHW; q += 2) {
+                piece(q, bufA, bufB);
+                piece(q + 1, bufB, bufA);
+            }
+            // the staging area lay over guard rows of A2: zero them again (only this warp wrote there; the first conv2 reads
+            // A2 after this warp's epilogue-1 publication, which comes later in program order)
+            {
+                constexpr int kGuardRows = kRtot - kRows;
+                const uint32_t lo = (uint32_t)(warp * 32 * kRbStageLd * 4), hi = lo + 32 * kRbStageLd * 4;
+                for (int q = lane; q < kGuardRows * (C / 8); q += 32) {
+                    const int ch = q / kGuardRows, g = q - ch * kGuardRows;
+                    const int row = (g < kGuard) ? g : (kRows + g);
+                    const uint32_t off = (uint32_t)((ch * kRtot + row) * 16);
+                    if (off + 16 > lo && off < hi) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a2_u32 + off), "r"(0u) : "memory");
+                }
             }
         }
+        // every warp's staging area lies in rows of A2 that OTHER warps write in epilogue 1: nobody starts it before all are done
+        asm volatile("bar.sync 1, %0;" ::"n"(NEW * 32) : "memory");
         if (threadIdx.x == 0) RB_DBG(2);
 
 #pragma unroll 1
         for (int i = 0; i < 3; i++) {
             const uint32_t par = (uint32_t)(i & 1);
             // ---- epilogue 1: T1 -> lrelu(. + b1) -> A2
-#pragma unroll
+#pragma unroll 1
             for (int s = 0; s < kS; s++) {
                 mbar_wait(T1_FULL(s), par);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -255,7 +295,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32, (C == 32) ? 2 : 1) k_res
             if (threadIdx.x == 0) RB_DBG(4 + 4 * i);
             if (i < 2) {
                 // ---- epilogue 2: X (+ running conv2 bias) -> lrelu -> A1 of the next pair
-#pragma unroll
+#pragma unroll 1
                 for (int s = 0; s < kS; s++) {
                     mbar_wait(X_FULL(s), par);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -271,88 +311,74 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32, (C == 32) ? 2 : 1) k_res
                 }
                 if (threadIdx.x == 0) RB_DBG(6 + 4 * i);
             } else {
-                // ---- while the last conv2 runs: T1 is idle from here on, so the MRF partial sum (acc_src) of this lane's output
-                // rows is parked there; the final epilogue then never waits on global memory
-                if (p.acc_src) {
-                    const float *arow = p.acc_src + ((size_t)w * p.T + (t_base + rq)) * C + cbase;
-                    uint32_t bufA[32], bufB[32];
-                    ld_row32(arow, is_out(0), bufA);
-#pragma unroll
-                    for (int q = 0; q < NCHW; q++) {
-                        const int s = q / CHW, c0 = cbase + (q % CHW) * 32;
-                        uint32_t (&v)[32] = (q & 1) ? bufB : bufA;
-                        uint32_t (&nx)[32] = (q & 1) ? bufA : bufB;
-                        if (q + 1 < NCHW) {
-                            const int s1 = (q + 1) / CHW, c1 = ((q + 1) % CHW) * 32;
-                            ld_row32(arow + (size_t)s1 * 128 * C + c1, is_out(s1), nx);
-                        }
-                        tmem_st32(tmem_T1 + tm_lane + (uint32_t)(s * C + c0), v);
-                    }
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                }
-                if (threadIdx.x == 0) RB_DBG(40);
                 // ---- final epilogue: rows [H, H+V) of the slab leave through a per-warp transpose (A1 is dead: every conv1
-                // has retired), 8 lanes per 128 contiguous bytes of an output row
+                // has retired), 8 lanes per 128 contiguous bytes of an output row.  The MRF partial sum (acc_src) is read in that
+                // same coalesced order, one 32x32 piece ahead, starting before the last conv2 has finished.
                 float *stg = reinterpret_cast<float *>(sA1) + warp * 32 * kRbStageLd;
-                const int sub_r = lane >> 3, c4 = lane & 7;
-#pragma unroll 1
-                for (int s = 0; s < kS; s++) {
-                    mbar_wait(X_FULL(s), par);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (threadIdx.x == 0 && s == 0) RB_DBG(5 + 4 * i);
-                    if (threadIdx.x == 0) RB_DBG(32 + s);
-                    const int grow_own = is_out(s) ? (w * p.T + t_base + s * 128 + rq) : -1;
-                    int grow[8];
+                uint32_t out_t[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) grow[j] = __shfl_sync(0xffffffffu, grow_own, j * 4 + sub_r);
-#pragma unroll 1
-                    for (int cc = 0; cc < CHW; cc++) {
-                        const int c0 = cbase + cc * 32;
-                        {
-                            uint32_t a32[32];
-                            tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C + c0), a32);
-                            const float *cb = p.cbias + 2 * C + c0;
+                for (int j = 0; j < 8; j++) out_t[j] = __shfl_sync(0xffffffffu, out_mask, j * 4 + sub_r);
+                const size_t row0 = (size_t)w * p.T + (t_base + quad * 32 + sub_r);        // global row of (sub-tile 0, j = 0)
+                const float *aq = p.acc_src ? p.acc_src + row0 * C + cbase + c4 * 4 : nullptr;
+                auto ld_acc = [&](int q, float4 (&b)[8]) {
+                    const int s1 = q / CHW, c1 = (q % CHW) * 32;
 #pragma unroll
-                            for (int j = 0; j < 32; j++) a32[j] = __float_as_uint(__uint_as_float(a32[j]) + cb[j]);
-                            if (p.acc_src) {
-                                uint32_t b32[32];
-                                tmem_ld32(tmem_T1 + tm_lane + (uint32_t)(s * C + c0), b32);
-#pragma unroll
-                                for (int j = 0; j < 32; j++) a32[j] = __float_as_uint(__uint_as_float(b32[j]) + __uint_as_float(a32[j]));
-                            }
-                            if (p.div != 1.0f) {
-                                // v / div as a reciprocal multiply plus one Newton correction (correctly rounded away from
-                                // denormals; __fdiv_rn was 9 % of this kernel's stall samples)
-                                const float rcp = p.rdiv, nd = -p.div;
-#pragma unroll
-                                for (int j = 0; j < 32; j++) {
-                                    const float v = __uint_as_float(a32[j]);
-                                    const float q = v * rcp;
-                                    a32[j] = __float_as_uint(fmaf(fmaf(nd, q, v), rcp, q));
-                                }
-                            }
-#pragma unroll
-                            for (int j = 0; j < 8; j++)
-                                *reinterpret_cast<uint4 *>(stg + lane * kRbStageLd + j * 4) = make_uint4(a32[4 * j], a32[4 * j + 1], a32[4 * j + 2], a32[4 * j + 3]);
-                        }
-                        __syncwarp();
-                        const int col = c0 + c4 * 4;
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const int g = grow[j];
-                            if (g < 0) continue;
-                            const float4 v = *reinterpret_cast<const float4 *>(stg + (j * 4 + sub_r) * kRbStageLd + c4 * 4);
-                            const size_t o = (size_t)g * C + col;
-                            if (p.out32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
-                            if (p.outb) {
-                                __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
-                                __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
-                                *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
-                            }
-                        }
-                        __syncwarp();
+                    for (int j = 0; j < 8; j++)
+                        b[j] = ((out_t[j] >> s1) & 1u) ? *reinterpret_cast<const float4 *>(aq + ((size_t)s1 * 128 + j * 4) * C + c1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                };
+                float4 accA[8], accB[8];
+                if (p.acc_src) ld_acc(0, accA);
+                if (threadIdx.x == 0) RB_DBG(40);
+                const float rcp = p.rdiv, nd = -p.div;
+                auto out_piece = [&](int q, float4 (&acur)[8], float4 (&anx)[8]) {
+                    const int s = q / CHW, c0 = cbase + (q % CHW) * 32;
+                    if ((q % CHW) == 0) {
+                        mbar_wait(X_FULL(s), par);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (threadIdx.x == 0 && s == 0) RB_DBG(5 + 4 * i);
+                        if (threadIdx.x == 0) RB_DBG(32 + s);
                     }
-                    if (threadIdx.x == 0) RB_DBG(36 + s);
+                    {
+                        uint32_t a32[32];
+                        tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C + c0), a32);
+                        const float *cb = p.cbias + 2 * C + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) a32[j] = __float_as_uint(__uint_as_float(a32[j]) + cb[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            *reinterpret_cast<uint4 *>(stg + lane * kRbStageLd + j * 4) = make_uint4(a32[4 * j], a32[4 * j + 1], a32[4 * j + 2], a32[4 * j + 3]);
+                    }
+                    __syncwarp();
+                    if (p.acc_src && q + 1 < NCHW) ld_acc(q + 1, anx);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (!((out_t[j] >> s) & 1u)) continue;
+                        float4 v = *reinterpret_cast<const float4 *>(stg + (j * 4 + sub_r) * kRbStageLd + c4 * 4);
+                        if (p.acc_src) { v.x = acur[j].x + v.x; v.y = acur[j].y + v.y; v.z = acur[j].z + v.z; v.w = acur[j].w + v.w; }
+                        if (p.div != 1.0f) {
+                            // v / div as a reciprocal multiply plus one Newton correction (correctly rounded away from denormals;
+                            // __fdiv_rn was 9 % of this kernel's stall samples)
+                            float q0;
+                            q0 = v.x * rcp; v.x = fmaf(fmaf(nd, q0, v.x), rcp, q0);
+                            q0 = v.y * rcp; v.y = fmaf(fmaf(nd, q0, v.y), rcp, q0);
+                            q0 = v.z * rcp; v.z = fmaf(fmaf(nd, q0, v.z), rcp, q0);
+                            q0 = v.w * rcp; v.w = fmaf(fmaf(nd, q0, v.w), rcp, q0);
+                        }
+                        const size_t o = (row0 + (size_t)s * 128 + j * 4) * C + (size_t)(c0 + c4 * 4);
+                        if (p.out32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
+                        if (p.outb) {
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
+                            __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
+                            *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                        }
+                    }
+                    __syncwarp();
+                    if ((q % CHW) == CHW - 1 && threadIdx.x == 0) RB_DBG(36 + s);
+                };
+#pragma unroll 1
+                for (int q = 0; q < NCHW; q += 2) {
+                    out_piece(q, accA, accB);
+                    out_piece(q + 1, accB, accA);
                 }
                 if (threadIdx.x == 0) RB_DBG(6 + 4 * i);
             }
@@ -535,7 +561,7 @@ void resblock_free(ResBlockPack &p) {
     if (p.tmap) { delete reinterpret_cast<CUtensorMap *>(p.tmap); p.tmap = nullptr; }
 }
 
-static bool g_rb_attr[64][3] = {};
+static bool g_rb_attr[64][4] = {};
 
 template <int C, int NEW, int NMW>
 static int launch_rb(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int slot) {
@@ -585,6 +611,7 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     const size_t smem = (size_t)p.nslots * p.tps * pk.C * kb_for(pk.C) * 2 + 2 * a_bytes + 24 * 8 + 16;
     if (smem > 227 * 1024) return set_error("resblock: needs %zu bytes of shared memory", smem);
     const CUtensorMap &tm = *reinterpret_cast<const CUtensorMap *>(pk.tmap);
+    static const int nmw128 = getenv("B2_RB_NMW128") ? atoi(getenv("B2_RB_NMW128")) : 2;
     static const bool dbg_on = getenv("B2_RB_DBG") != nullptr;
     static unsigned long long *dbg_buf = nullptr;
     const size_t dbg_n = (size_t)kRbDbgCtas * kRbDbgEvents;
@@ -592,7 +619,8 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     p.dbg = dbg_on ? dbg_buf : nullptr;
     if (dbg_on) B2_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, dbg_n * 8, st));
     const int rc = (pk.C == 32) ? launch_rb<32, 4, 2>(tm, p, (unsigned)nct, smem, st, 0)
-                   : (pk.C == 64) ? launch_rb<64, 8, 2>(tm, p, (unsigned)nct, smem, st, 1) : launch_rb<128, 8, 2>(tm, p, (unsigned)nct, smem, st, 2);
+                   : (pk.C == 64) ? launch_rb<64, 8, 2>(tm, p, (unsigned)nct, smem, st, 1)
+                   : (nmw128 == 2 ? launch_rb<128, 8, 2>(tm, p, (unsigned)nct, smem, st, 3) : launch_rb<128, 8, 1>(tm, p, (unsigned)nct, smem, st, 2));
     if (dbg_on && !rc) {
         // per-phase averages over the first CTAs of the launch (cycles of the SM clock)
         B2_CUDA_OK(cudaStreamSynchronize(st));

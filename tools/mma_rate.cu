@@ -21,16 +21,17 @@ struct Cfg {
     int iters;      // MMAs per timed run
     int distinct;   // how many different A start rows are cycled through (1 = same operand every time)
     int a_step;     // rows between consecutive A starts (tap shift)
+    int commit_every; // 0: one commit at the end; n: a tcgen05.commit (to a second barrier) after every n MMAs
 };
 
 __global__ void __launch_bounds__(128) k_rate(Cfg c, unsigned long long *out) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar2;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5;
     // zero operands (timing does not depend on the values)
     for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(128) k_rate(Cfg c, unsigned long long *out) {
                 const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)(d * c.a_step) * row_units);
                 if (leader) umma_f16(tmem, adesc, bdesc0, idesc, 1u);
                 if (++d == c.distinct) d = 0;
+                if (c.commit_every && ((i + 1) % c.commit_every) == 0 && leader) umma_commit(smem_u32(&bar2));
             }
             if (leader) umma_commit(smem_u32(&bar));
             __syncwarp();
@@ -87,6 +89,7 @@ int main() {
                 Cfg c;
                 c.N = Ns[ni]; c.a_mode = a_mode; c.iters = 2048;
                 c.b_mode = (variant == 2) ? 0 : ((c.N == 32) ? 4 : 2);
+                c.commit_every = 0;
                 c.distinct = (variant == 0) ? 1 : 11; c.a_step = (variant == 0) ? 0 : ((a_mode == 1) ? 8 : 5);
                 if (a_mode == 1 && variant == 2) continue;
                 for (int grid : {1, 148}) {
@@ -100,5 +103,18 @@ int main() {
                            (double)h[0] / c.iters, (double)h[grid / 2] / c.iters);
                 }
             }
+    printf("# effect of tcgen05.commit frequency (a_mode 0, 11 distinct A starts)\n");
+    for (int ni = 0; ni < 4; ni++)
+        for (int ce : {0, 32, 8, 4, 2, 1}) {
+            Cfg c;
+            c.N = Ns[ni]; c.a_mode = 0; c.iters = 2048; c.b_mode = (c.N == 32) ? 4 : 2; c.distinct = 11; c.a_step = 5; c.commit_every = ce;
+            k_rate<<<148, 128, 160 * 1024>>>(c, d_out);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+            std::vector<unsigned long long> h(148);
+            cudaMemcpy(h.data(), d_out, 148 * 8, cudaMemcpyDeviceToHost);
+            std::sort(h.begin(), h.end());
+            printf("N=%3d commit_every=%2d : %6.1f cycles/MMA\n", c.N, ce, (double)h[74] / c.iters);
+        }
     return 0;
 }
