@@ -120,12 +120,14 @@ __device__ __forceinline__ void publish_rows(uint32_t bar, int lane) {
 }
 
 static constexpr int kRbDbgEvents = 48, kRbDbgCtas = 4096;
-#define RB_DBG(k) do { if (p.dbg && blockIdx.x < kRbDbgCtas) p.dbg[(size_t)blockIdx.x * kRbDbgEvents + (k)] = clock64(); } while (0)
+#define RB_DBG(k) do { if (DBG && p.dbg && blockIdx.x < kRbDbgCtas) p.dbg[(size_t)blockIdx.x * kRbDbgEvents + (k)] = clock64(); } while (0)
 
 // Warp roles: [0, NEW) slab load + all epilogues (warp e: TMEM lane quadrant e % 4, column slice e / 4), warp NEW = TMEM alloc +
 // TMA weight ring, then NMW MMA-issuing warps, each owning kS / NMW sub-tiles (a sub-tile's accumulator is only ever touched by
 // one issuing thread, so the summation order is fixed).
-template <int C, int NEW, int NMW>
+// EPI selects the final epilogue at compile time (its code is a third of the kernel, and the kernel has to fit the instruction
+// cache): 0 out32 = r;  1 out32 = acc + r;  2 outb = bf16(lrelu((acc + r) / div));  3 out32 = (acc + r) / div;  4 everything decided at run time.
+template <int C, int NEW, int NMW, int EPI, bool DBG>
 __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 128 : 168) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ RbParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using G = RbGeom<C>;
@@ -217,32 +219,42 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
 #pragma unroll
         for (int j = 0; j < 8; j++) inside_t[j] = __shfl_sync(0xffffffffu, inside_mask, j * 4 + sub_r);
         {
-            float *stg = reinterpret_cast<float *>(sA2) + warp * 32 * kRbStageLd;
+            // two 4 KB staging buffers per warp, 128-byte rows with the 16-byte piece index XOR-ed with (row & 7): conflict-free
+            // for the 8-lanes-per-row writes of cp.async and for the row-per-lane reads
+            const uint32_t stg_u32 = a2_u32 + (uint32_t)(warp * 8192);
             const float *xq = p.x + ((size_t)w * p.T + (t_base + quad * 32 + sub_r)) * C + cbase + c4 * 4;   // row sub_r of this warp's rows in sub-tile 0
-            auto ld_piece = [&](int q, uint4 (&b)[8]) {
+            auto issue_piece = [&](int q) {
                 const int s1 = q / CHW, c1 = (q % CHW) * 32;
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    b[j] = ((inside_t[j] >> s1) & 1u) ? __ldg(reinterpret_cast<const uint4 *>(xq + ((size_t)s1 * 128 + j * 4) * C + c1)) : make_uint4(0u, 0u, 0u, 0u);
-            };
-            uint4 bufA[8], bufB[8];
-            ld_piece(0, bufA);
-            // one piece: prefetch the next, transpose this one through shared memory, hand it to TMEM and to A1.  The loop is
-            // kept ROLLED (two pieces per trip for the ping-pong buffers): the kernel's code has to stay inside the 32 KB
-            // instruction cache, fully unrolled phases made every CTA start run at L2 instruction-fetch speed.
-            auto piece = [&](int q, uint4 (&cur)[8], uint4 (&nx)[8]) {
-                const int s = q / CHW, c0 = cbase + (q % CHW) * 32;
-                if (q + 1 < NCHW) ld_piece(q + 1, nx);
-#pragma unroll
-                for (int j = 0; j < 8; j++) *reinterpret_cast<uint4 *>(stg + (j * 4 + sub_r) * kRbStageLd + c4 * 4) = cur[j];
-                __syncwarp();
-                uint32_t v[32];
+                const uint32_t dst0 = stg_u32 + (uint32_t)((q & 1) * 4096);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const uint4 t4 = *reinterpret_cast<const uint4 *>(stg + lane * kRbStageLd + j * 4);
-                    v[4 * j] = t4.x; v[4 * j + 1] = t4.y; v[4 * j + 2] = t4.z; v[4 * j + 3] = t4.w;
+                    const int row = j * 4 + sub_r;
+                    const bool ok = ((inside_t[j] >> s1) & 1u) != 0u;
+                    const float *src = ok ? xq + ((size_t)s1 * 128 + j * 4) * C + c1 : p.x;
+                    cp_async16(dst0 + (uint32_t)(row * 128 + ((c4 ^ (row & 7)) << 4)), src, ok ? 16u : 0u);     // zero-fill outside the window
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            issue_piece(0);
+#pragma unroll 1
+            for (int q = 0; q < NCHW; q++) {
+                const int s = q / CHW, c0 = cbase + (q % CHW) * 32;
+                if (q + 1 < NCHW) {
+                    issue_piece(q + 1);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                 }
                 __syncwarp();
+                uint32_t v[32];
+                {
+                    const uint32_t src0 = stg_u32 + (uint32_t)((q & 1) * 4096 + lane * 128);
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
+                                     : "r"(src0 + (uint32_t)((j ^ (lane & 7)) << 4)) : "memory");
+                }
+                __syncwarp();                  // the buffer is refilled two pieces later
                 tmem_st32(tmem_X + tm_lane + (uint32_t)(s * C + c0), v);
                 write_operand_row<kRtot>(a1_u32, s * 128 + rq, c0, v, nullptr, p.slope, true);
                 if ((q % CHW) == CHW - 1) {
@@ -250,18 +262,12 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                     publish_rows(A1_READY(s), lane);
                     if (threadIdx.x == 0) RB_DBG(44 + s);
                 }
-            };
-            static_assert(NCHW % 2 == 0, "ping-pong needs an even number of pieces");
-#pragma unroll 1
-            for (int q = 0; q < NCHW; q += 2) {
-                piece(q, bufA, bufB);
-                piece(q + 1, bufB, bufA);
             }
             // the staging area lay over guard rows of A2: zero them again (only this warp wrote there; the first conv2 reads
             // A2 after this warp's epilogue-1 publication, which comes later in program order)
             {
                 constexpr int kGuardRows = kRtot - kRows;
-                const uint32_t lo = (uint32_t)(warp * 32 * kRbStageLd * 4), hi = lo + 32 * kRbStageLd * 4;
+                const uint32_t lo = (uint32_t)(warp * 8192), hi = lo + 8192;
                 for (int q = lane; q < kGuardRows * (C / 8); q += 32) {
                     const int ch = q / kGuardRows, g = q - ch * kGuardRows;
                     const int row = (g < kGuard) ? g : (kRows + g);
@@ -277,40 +283,31 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
 #pragma unroll 1
         for (int i = 0; i < 3; i++) {
             const uint32_t par = (uint32_t)(i & 1);
-            // ---- epilogue 1: T1 -> lrelu(. + b1) -> A2
+            // ---- epilogue 1: T1 -> lrelu(. + b1) -> A2, then (pairs 0, 1) epilogue 2: X (+ running conv2 bias) -> lrelu -> A1 of the
+            // next pair.  ONE body serves both (source accumulator, bias row, destination buffer and barriers are run-time
+            // values): the epilogue code is most of the kernel and has to stay small (instruction cache).
 #pragma unroll 1
-            for (int s = 0; s < kS; s++) {
-                mbar_wait(T1_FULL(s), par);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (threadIdx.x == 0 && s == 0) RB_DBG(3 + 4 * i);
-#pragma unroll
-                for (int cc = 0; cc < CHW; cc++) {
-                    const int c0 = cbase + cc * 32;
-                    uint32_t acc[32];
-                    tmem_ld32(tmem_T1 + tm_lane + (uint32_t)(s * C + c0), acc);
-                    write_operand_row<kRtot>(a2_u32, s * 128 + rq, c0, acc, p.bias1 + i * C + c0, p.slope, inside(s));
-                }
-                publish_rows(A2_READY(s), lane);
-            }
-            if (threadIdx.x == 0) RB_DBG(4 + 4 * i);
-            if (i < 2) {
-                // ---- epilogue 2: X (+ running conv2 bias) -> lrelu -> A1 of the next pair
+            for (int e = 0; e < ((i < 2) ? 2 : 1); e++) {
+                const uint32_t src = (e ? tmem_X : tmem_T1) + tm_lane;
+                const uint32_t dst = e ? a1_u32 : a2_u32;
+                const float *bias = (e ? p.cbias : p.bias1) + i * C + cbase;
+                const uint32_t full0 = e ? X_FULL(0) : T1_FULL(0), ready0 = e ? A1_READY(0) : A2_READY(0);
 #pragma unroll 1
                 for (int s = 0; s < kS; s++) {
-                    mbar_wait(X_FULL(s), par);
+                    mbar_wait(full0 + 8u * (uint32_t)s, par);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (threadIdx.x == 0 && s == 0) RB_DBG(5 + 4 * i);
-#pragma unroll
+                    if (threadIdx.x == 0 && s == 0) RB_DBG(3 + 4 * i + 2 * e);
+#pragma unroll 1
                     for (int cc = 0; cc < CHW; cc++) {
-                        const int c0 = cbase + cc * 32;
                         uint32_t acc[32];
-                        tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C + c0), acc);
-                        write_operand_row<kRtot>(a1_u32, s * 128 + rq, c0, acc, p.cbias + i * C + c0, p.slope, inside(s));
+                        tmem_ld32(src + (uint32_t)(s * C + cbase + cc * 32), acc);
+                        write_operand_row<kRtot>(dst, s * 128 + rq, cbase + cc * 32, acc, bias + cc * 32, p.slope, inside(s));
                     }
-                    publish_rows(A1_READY(s), lane);
+                    publish_rows(ready0 + 8u * (uint32_t)s, lane);
                 }
-                if (threadIdx.x == 0) RB_DBG(6 + 4 * i);
-            } else {
+                if (threadIdx.x == 0) RB_DBG(4 + 4 * i + 2 * e);
+            }
+            if (i == 2) {
                 // ---- final epilogue: rows [H, H+V) of the slab leave through a per-warp transpose (A1 is dead: every conv1
                 // has retired), 8 lanes per 128 contiguous bytes of an output row.  The MRF partial sum (acc_src) is read in that
                 // same coalesced order, one 32x32 piece ahead, starting before the last conv2 has finished.
@@ -319,15 +316,19 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
 #pragma unroll
                 for (int j = 0; j < 8; j++) out_t[j] = __shfl_sync(0xffffffffu, out_mask, j * 4 + sub_r);
                 const size_t row0 = (size_t)w * p.T + (t_base + quad * 32 + sub_r);        // global row of (sub-tile 0, j = 0)
-                const float *aq = p.acc_src ? p.acc_src + row0 * C + cbase + c4 * 4 : nullptr;
+                const float *aq = p.acc_src + row0 * C + cbase + c4 * 4;            // only dereferenced when the epilogue has an acc_src
                 auto ld_acc = [&](int q, float4 (&b)[8]) {
                     const int s1 = q / CHW, c1 = (q % CHW) * 32;
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                         b[j] = ((out_t[j] >> s1) & 1u) ? *reinterpret_cast<const float4 *>(aq + ((size_t)s1 * 128 + j * 4) * C + c1) : make_float4(0.f, 0.f, 0.f, 0.f);
                 };
+                const bool has_acc = (EPI == 4) ? (p.acc_src != nullptr) : (EPI >= 1);
+                const bool has_div = (EPI == 4) ? (p.div != 1.0f) : (EPI >= 2);
+                const bool has_o32 = (EPI == 4) ? (p.out32 != nullptr) : (EPI != 2);
+                const bool has_ob = (EPI == 4) ? (p.outb != nullptr) : (EPI == 2);
                 float4 accA[8], accB[8];
-                if (p.acc_src) ld_acc(0, accA);
+                if (has_acc) ld_acc(0, accA);
                 if (threadIdx.x == 0) RB_DBG(40);
                 const float rcp = p.rdiv, nd = -p.div;
                 auto out_piece = [&](int q, float4 (&acur)[8], float4 (&anx)[8]) {
@@ -349,13 +350,13 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                             *reinterpret_cast<uint4 *>(stg + lane * kRbStageLd + j * 4) = make_uint4(a32[4 * j], a32[4 * j + 1], a32[4 * j + 2], a32[4 * j + 3]);
                     }
                     __syncwarp();
-                    if (p.acc_src && q + 1 < NCHW) ld_acc(q + 1, anx);
+                    if (has_acc && q + 1 < NCHW) ld_acc(q + 1, anx);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         if (!((out_t[j] >> s) & 1u)) continue;
                         float4 v = *reinterpret_cast<const float4 *>(stg + (j * 4 + sub_r) * kRbStageLd + c4 * 4);
-                        if (p.acc_src) { v.x = acur[j].x + v.x; v.y = acur[j].y + v.y; v.z = acur[j].z + v.z; v.w = acur[j].w + v.w; }
-                        if (p.div != 1.0f) {
+                        if (has_acc) { v.x = acur[j].x + v.x; v.y = acur[j].y + v.y; v.z = acur[j].z + v.z; v.w = acur[j].w + v.w; }
+                        if (has_div) {
                             // v / div as a reciprocal multiply plus one Newton correction (correctly rounded away from denormals;
                             // __fdiv_rn was 9 % of this kernel's stall samples)
                             float q0;
@@ -365,8 +366,8 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                             q0 = v.w * rcp; v.w = fmaf(fmaf(nd, q0, v.w), rcp, q0);
                         }
                         const size_t o = (row0 + (size_t)s * 128 + j * 4) * C + (size_t)(c0 + c4 * 4);
-                        if (p.out32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
-                        if (p.outb) {
+                        if (has_o32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
+                        if (has_ob) {
                             __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
                             __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
                             *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
@@ -561,19 +562,34 @@ void resblock_free(ResBlockPack &p) {
     if (p.tmap) { delete reinterpret_cast<CUtensorMap *>(p.tmap); p.tmap = nullptr; }
 }
 
-static bool g_rb_attr[64][4] = {};
 
-template <int C, int NEW, int NMW>
-static int launch_rb(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int slot) {
+static bool g_rb_attr[64][3][6] = {};
+
+template <int C, int NEW, int NMW, int EPI, bool DBG>
+static int launch_rb_(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int wslot) {
     int dev = 0;
     B2_CUDA_OK(cudaGetDevice(&dev));
-    if (dev < 64 && !g_rb_attr[dev][slot]) {
-        B2_CUDA_OK(cudaFuncSetAttribute(k_resblock<C, NEW, NMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        g_rb_attr[dev][slot] = true;
+    const int eslot = DBG ? 5 : EPI;
+    if (dev < 64 && !g_rb_attr[dev][wslot][eslot]) {
+        B2_CUDA_OK(cudaFuncSetAttribute(k_resblock<C, NEW, NMW, EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        g_rb_attr[dev][wslot][eslot] = true;
     }
-    k_resblock<C, NEW, NMW><<<grid, (NEW + 1 + NMW) * 32, smem, st>>>(tm, p);
+    k_resblock<C, NEW, NMW, EPI, DBG><<<grid, (NEW + 1 + NMW) * 32, smem, st>>>(tm, p);
     B2_LAUNCH_OK("k_resblock");
     return 0;
+}
+
+// picks the compile-time epilogue that matches the request (the vocoder's three launches per stage are EPI 0, 1 and 2 or 3);
+// anything else, and the timestamped analysis build, runs the generic kernel
+template <int C, int NEW, int NMW>
+static int launch_rb(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int wslot) {
+    if (p.dbg) return launch_rb_<C, NEW, NMW, 4, true>(tm, p, grid, smem, st, wslot);
+    const bool acc = p.acc_src != nullptr, dv = p.div != 1.0f, o32 = p.out32 != nullptr, ob = p.outb != nullptr;
+    if (!acc && !dv && o32 && !ob) return launch_rb_<C, NEW, NMW, 0, false>(tm, p, grid, smem, st, wslot);
+    if (acc && !dv && o32 && !ob) return launch_rb_<C, NEW, NMW, 1, false>(tm, p, grid, smem, st, wslot);
+    if (acc && dv && !o32 && ob) return launch_rb_<C, NEW, NMW, 2, false>(tm, p, grid, smem, st, wslot);
+    if (acc && dv && o32 && !ob) return launch_rb_<C, NEW, NMW, 3, false>(tm, p, grid, smem, st, wslot);
+    return launch_rb_<C, NEW, NMW, 4, false>(tm, p, grid, smem, st, wslot);
 }
 
 int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
@@ -611,7 +627,6 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     const size_t smem = (size_t)p.nslots * p.tps * pk.C * kb_for(pk.C) * 2 + 2 * a_bytes + 24 * 8 + 16;
     if (smem > 227 * 1024) return set_error("resblock: needs %zu bytes of shared memory", smem);
     const CUtensorMap &tm = *reinterpret_cast<const CUtensorMap *>(pk.tmap);
-    static const int nmw128 = getenv("B2_RB_NMW128") ? atoi(getenv("B2_RB_NMW128")) : 2;
     static const bool dbg_on = getenv("B2_RB_DBG") != nullptr;
     static unsigned long long *dbg_buf = nullptr;
     const size_t dbg_n = (size_t)kRbDbgCtas * kRbDbgEvents;
@@ -620,7 +635,7 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     if (dbg_on) B2_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, dbg_n * 8, st));
     const int rc = (pk.C == 32) ? launch_rb<32, 4, 2>(tm, p, (unsigned)nct, smem, st, 0)
                    : (pk.C == 64) ? launch_rb<64, 8, 2>(tm, p, (unsigned)nct, smem, st, 1)
-                   : (nmw128 == 2 ? launch_rb<128, 8, 2>(tm, p, (unsigned)nct, smem, st, 3) : launch_rb<128, 8, 1>(tm, p, (unsigned)nct, smem, st, 2));
+                   : launch_rb<128, 8, 2>(tm, p, (unsigned)nct, smem, st, 2);
     if (dbg_on && !rc) {
         // per-phase averages over the first CTAs of the launch (cycles of the SM clock)
         B2_CUDA_OK(cudaStreamSynchronize(st));
