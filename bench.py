@@ -30,6 +30,8 @@ AUDIO_S_PER_FRAME = 256 / 16000.0
 FLOP_PER_WINDOW_TC = 12 * 2 * (4 * 33.030144e6 + 4 * 1.048576e6 + 0.28672e6) + 2 * 10.22e6   # tcgen05 kernels: upsamplers, ResBlocks,
                                                                                             # conv_pre, chunker upsamplers + ResBlock
 FLOP_PER_WINDOW_ALL = 12 * 273.318e6 + 25.68e6 + 0.057e6 * 4
+# the three stages the fused ResBlock kernel covers (C = 128, 64, 32): 33.03 MMAC per frame per stage, algorithmic (no halo rows)
+FLOP_PER_WINDOW_RESBLOCK_STAGE = 12 * 2 * 33.030144e6
 CODEC_BYTES_PER_OUT = 9.0                                            # 2 fp32 in + 1 byte out per 8 kHz sample
 
 
@@ -40,6 +42,17 @@ def load_peaks():
             d = json.load(f)
         return dict(hbm_gbs=d["hbm_gbs"], tf_sustained=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], source="measured")
     return dict(hbm_gbs=6650.0, tf_sustained=1400.0, tf_burst=1590.0, source="fallback")
+
+
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/): measured under the
+    profiler at a smaller session count, scaled per window; {} when the summary is absent."""
+    p = os.path.join(ROOT, "profiles", "r1_resblock_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -220,15 +233,36 @@ def main_b200(args, rank, local_rank, world):
     ms_cls, n_cls = tail.profile_end()
     peaks = load_peaks()
     W_step = S * nwin
-    tc_ms = ms_cls["conv_tc"] if args.mode == "bf16" else ms_cls["conv_f32"]
-    tc_n = n_cls["conv_tc"] if args.mode == "bf16" else n_cls["conv_f32"]
-    roofline = codec_roof = None
+    bf = args.mode == "bf16"
+    tc_ms = (ms_cls["conv_tc"] + ms_cls["resblock_tc"]) if bf else ms_cls["conv_f32"]
+    tc_n = (n_cls["conv_tc"] + n_cls["resblock_tc"]) if bf else n_cls["conv_f32"]
+    step_ms = max(sum(ms_cls.values()), 1e-9)
+    roofline = codec_roof = family_roof = None
+    traffic = load_traffic()
+    if bf and ms_cls["resblock_tc"] > 0:
+        # the dominant kernel: one fused launch per ResBlock for the C = 128 / 64 / 32 stages (9 launches per sub-batch)
+        rb_ms, rb_n = ms_cls["resblock_tc"], n_cls["resblock_tc"]
+        tf = 3 * FLOP_PER_WINDOW_RESBLOCK_STAGE * W_step * psteps / (rb_ms / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "k_resblock<C> (fused tcgen05 ResBlock: six convolutions per launch, residual stream in TMEM; "
+                                                 "stages C=128/64/32, 9 launches per sub-batch)",
+                    "achieved": round(tf, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(tf / peaks["tf_sustained"], 4),
+                    "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
+                    "traffic": traffic.get("k_resblock_bytes_per_launch"), "traffic_note": traffic.get("note"),
+                    "flop_per_launch": round(3 * FLOP_PER_WINDOW_RESBLOCK_STAGE * W_step * psteps / rb_n),
+                    "launches": rb_n, "avg_launch_ms": round(rb_ms / max(rb_n, 1), 4), "share_of_step": round(rb_ms / step_ms, 4),
+                    "note": "M128xN32/N64 MMAs cap at 40 % / 67 % of the tensor peak (operand fetch from shared memory: 32 + N/4 cycles "
+                            "per K=16 step, tools/mma_rate.cu); halo rows recomputed by the fused kernel are not counted as work"}
     if tc_ms > 0:
         tf = FLOP_PER_WINDOW_TC * W_step * psteps / (tc_ms / 1e3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels k_conv_umma / k_conv_umma_p (81 launches per sub-batch: conv_pre, 4 upsamplers, 72 ResBlock convs, 4 chunker convs)" if args.mode == "bf16" else "k_conv_simt",
-                    "achieved": round(tf, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(tf / peaks["tf_sustained"], 4),
-                    "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)", "traffic": None,
-                    "launches": tc_n, "avg_launch_ms": round(tc_ms / max(tc_n, 1), 4), "share_of_step": round(tc_ms / max(sum(ms_cls.values()), 1e-9), 4)}
+        fam = {"bound": "tensor", "kernel": "all tcgen05 kernels (k_resblock + per-layer k_conv_umma / k_conv_umma_p: conv_pre, upsamplers, stage-0 ResBlock "
+                                            "convs, chunker convs)" if bf else "k_conv_simt",
+               "achieved": round(tf, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(tf / peaks["tf_sustained"], 4),
+               "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)", "traffic": None,
+               "launches": tc_n, "avg_launch_ms": round(tc_ms / max(tc_n, 1), 4), "share_of_step": round(tc_ms / step_ms, 4)}
+        if roofline is None:
+            roofline = fam
+        else:
+            family_roof = fam
     if ms_cls["resample_g711"] > 0:
         gbs = CODEC_BYTES_PER_OUT * S * F * 128 * psteps / (ms_cls["resample_g711"] / 1e3) / 1e9
         codec_roof = {"bound": "hbm", "kernel": "k_resample_2to1_shfl (fused 16k->8k + G.711, warp-shuffle taps)", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"],
@@ -258,7 +292,7 @@ def main_b200(args, rank, local_rank, world):
             "e2e": {"value": round(e2e_value, 1), "unit": "streams", "h2d_bytes_per_step": int(mel_h.numel() * 4 + slots_h.numel() * 4) * world,
                     "d2h_bytes_per_step": int(g_h.numel()) * world, "ms_per_step": round(e2e_ms / args.steps, 3)},
             "gpu_launches": int(sum(s["kernel_launches"] for s in allstats)),
-            "roofline": roofline, "roofline_codec": codec_roof,
+            "roofline": roofline, "roofline_conv_family": family_roof, "roofline_codec": codec_roof,
             "kernel_ms_per_step": {k: round(v / psteps, 3) for k, v in ms_cls.items()},
             "cpu_baseline": cpu,
             "per_gpu_stats": [{"sessions": int(s["sessions"]), "steps": int(s["steps"]), "g711_bytes": int(s["g711_bytes"]),

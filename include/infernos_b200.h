@@ -131,7 +131,7 @@ B2_API int b2_resblock_tc(const float *d_x, const float *h_weights, const float 
 B2_API uint64_t b2_kernel_launch_count(void);
 /* Per-kernel-class device timing (CUDA events on the launching stream around every launch of this context)
  * between b2_profile_begin and b2_profile_end.  Classes: 0 tcgen05 convs, 1 CUDA-core convs, 2 conv_post+tanh,
- * 3 resample+G.711, 4 other (window builder, chunker prologue/epilogue).  Arrays of 8. */
+ * 3 resample+G.711, 4 other (window builder, chunker prologue/epilogue), 5 fused tcgen05 ResBlock kernel.  Arrays of 8. */
 B2_API int b2_profile_begin(b2_ctx *ctx);
 B2_API int b2_profile_end(b2_ctx *ctx, double *ms_by_class, uint64_t *launches_by_class);
 

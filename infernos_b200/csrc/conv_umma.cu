@@ -575,7 +575,19 @@ static EncodeTiledFn g_encode = nullptr;
 static std::mutex g_init_mu;
 static bool g_attr_set[64][4] = {};
 
+// Stage 0 (C = 256, T = 48) is bound by re-streaming the weights from L2 for every 128-row tile (k x 128 KB per two windows).
+// Experiment (B2_UMMA_TALL256=1): its ResBlock convs as 256-row tiles (two M sub-tiles per weight tile, up to five windows packed
+// per tile) of 128 output channels in the one-tile-per-CTA kernel, i.e. half the weight bytes per FLOP.  Measured on B200: correct,
+// but 5 % SLOWER end to end (26.3 vs 25.0 ms per step) -- at one CTA per SM its load / MMA / epilogue phases do not overlap, which
+// costs more than the weight traffic saves -- so the persistent pipelined kernel stays the default for these layers.
+static bool tall256() {
+    static const bool on = getenv("B2_UMMA_TALL256") && atoi(getenv("B2_UMMA_TALL256")) != 0;
+    return on;
+}
+static bool is_tall256(const Layer &l) { return tall256() && l.Cin == 256 && l.Cout == 256; }
+
 static int n_tile_for(const Layer &l) {
+    if (is_tall256(l)) return 128;
     if (l.Cout >= 256) return (l.Cin >= 512) ? 128 : 256;
     return l.Cout;     // 32, 64, 128
 }
@@ -667,11 +679,13 @@ static int launch_conv_umma_v1(const UmmaConvArgs &a, cudaStream_t st) {
         while (want > 1 && 128 * want > ((a.T + 127) / 128) * 128) want >>= 1;
         p.mt = want;
     }
+    if (is_tall256(l)) p.mt = 2;
     p.R = (128 * p.mt + (l.taps - 1) * l.dil) | 1;
     unsigned mtiles;
-    if (a.T < 128) {
+    if (a.T < 128 * p.mt) {
+        // short windows: several per tile, `pad` zero rows apart (the thin layers never get here with mt > 1)
         const int G = l.pad;
-        p.nseg = std::max(1, (128 + G) / (a.T + G));
+        p.nseg = std::max(1, (128 * p.mt + G) / (a.T + G));
         p.period = a.T + G;
         p.tiles_per_win = 1;
         mtiles = (unsigned)cdiv(a.W, p.nseg);
@@ -762,7 +776,7 @@ int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
     static const bool force_v1 = getenv("B2_UMMA_V1") != nullptr, force_v2 = getenv("B2_UMMA_V2") != nullptr;
     const Layer &l = *a.layer;
     const bool wide = l.Cin >= 256 || l.Cout > l.Cin;
-    if (force_v1 || (!force_v2 && !wide)) return launch_conv_umma_v1(a, st);
+    if (force_v1 || (!force_v2 && (!wide || is_tall256(l)))) return launch_conv_umma_v1(a, st);
     if (!l.tmap || !l.wbf) return set_error("conv_umma: layer has no tensor-core weights (context not in B2_MODE_BF16?)");
     if (a.W <= 0 || a.T <= 0) return 0;
     if ((l.taps - 1) * l.dil != 2 * l.pad) return set_error("conv_umma: only 'same' convolutions are supported");

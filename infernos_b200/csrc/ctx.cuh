@@ -50,7 +50,7 @@ struct Workspace {
 };
 
 // optional per-kernel-class timing with CUDA events on the launching stream (used by bench.py's roofline leg)
-enum ProfClass { PC_CONV_TC = 0, PC_CONV_F32 = 1, PC_CONV_POST = 2, PC_RESAMPLE_G711 = 3, PC_OTHER = 4, PC_COUNT = 8 };
+enum ProfClass { PC_CONV_TC = 0, PC_CONV_F32 = 1, PC_CONV_POST = 2, PC_RESAMPLE_G711 = 3, PC_OTHER = 4, PC_RESBLOCK = 5, PC_COUNT = 8 };
 struct ProfSpan { int cls; cudaEvent_t a, b; };
 struct Prof {
     bool on = false;

@@ -338,7 +338,7 @@ static int vocoder_bf16(b2_ctx *c, const float *xn, int W, int T, float *audio, 
                     if (i < 3) ra.outb = ws.sb;
                     else ra.out32 = ws.s0;
                 }
-                PROF(PC_CONV_TC, launch_resblock(ra, st));
+                PROF(PC_RESBLOCK, launch_resblock(ra, st));
             }
             stage_in = ws.sb;
             continue;

@@ -161,11 +161,12 @@ class TTSTail:
         _lib.check(self.lib.b2_profile_begin(self.ctx), "profile_begin")
 
     def profile_end(self):
-        """-> ({class: ms}, {class: launches}) for classes conv_tc, conv_f32, conv_post, resample_g711, other."""
+        """-> ({class: ms}, {class: launches}) for classes conv_tc (per-layer tcgen05 convs), conv_f32, conv_post, resample_g711,
+        other, resblock_tc (the fused tcgen05 ResBlock kernel)."""
         ms = (ctypes.c_double * 8)()
         n = (ctypes.c_uint64 * 8)()
         _lib.check(self.lib.b2_profile_end(self.ctx, ms, n), "profile_end")
-        names = ["conv_tc", "conv_f32", "conv_post", "resample_g711", "other"]
+        names = ["conv_tc", "conv_f32", "conv_post", "resample_g711", "other", "resblock_tc"]
         return {k: ms[i] for i, k in enumerate(names)}, {k: int(n[i]) for i, k in enumerate(names)}
 
     def reset_sessions(self, slots: Sequence[int]) -> None:

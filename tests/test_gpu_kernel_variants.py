@@ -1,4 +1,4 @@
-"""GPU: the alternative tcgen05 code paths stay correct.  The library picks a kernel per layer (conv_umma.cu:launch_conv_umma);
+"""GPU: the alternative tcgen05 code paths stay correct (the default runs the fused ResBlock kernel for the C <= 128 stages).  The library picks a kernel per layer (conv_umma.cu:launch_conv_umma);
 environment switches force the others.  They are read once per process, so each variant runs in a subprocess and must
 reproduce the default path's audio to fp32-summation-order noise (same bf16 operand rounding everywhere)."""
 import os
@@ -35,15 +35,19 @@ def _run(tmp_path, name, env):
 @pytest.mark.parametrize("name,env", [
     ("one_tile_kernel_everywhere", {"B2_UMMA_V1": "1"}),
     ("persistent_kernel_everywhere", {"B2_UMMA_V2": "1"}),
-    ("fused_resblock_pairs", {"B2_PAIR_FUSION": "1"}),
-    ("single_subtile", {"B2_UMMA_MT": "1"}),
+    ("fused_resblock_pairs", {"B2_PAIR_FUSION": "1", "B2_RESBLOCK_FUSION": "0"}),
+    ("single_subtile", {"B2_UMMA_MT": "1", "B2_RESBLOCK_FUSION": "0"}),
+    ("conv_by_conv_resblocks", {"B2_RESBLOCK_FUSION": "0"}),
+    ("tall_stage0_tiles", {"B2_UMMA_TALL256": "1"}),
 ])
 def test_variant_matches_default(tmp_path, name, env):
     ref = _run(tmp_path, "default", {})
     got = _run(tmp_path, name, env)
     err = np.abs(got["audio"] - ref["audio"]).max()
     snr = 10 * np.log10((ref["audio"] ** 2).sum() / max(((ref["audio"] - got["audio"]) ** 2).sum(), 1e-30))
-    # identical operand rounding; only the fp32 accumulation order (tile shapes) differs, which can flip a bf16 rounding
-    # of an intermediate now and then
-    assert snr > 50.0, (name, snr, err)
-    assert (got["g711"] != ref["g711"]).mean() < 0.05
+    # identical operand rounding points; what differs is the fp32 accumulation order (tile shapes; the fused ResBlock kernel also
+    # carries the conv2 biases as a running offset), which flips the bf16 rounding of an intermediate now and then.  Each path is
+    # ~44.5 dB from the fp32 module on its own (test_gpu_tail.py); against each other they must be well inside that.
+    print(f"{name}: snr {snr:.1f} dB, max abs {err:.2e}, g711 mismatch {(got['g711'] != ref['g711']).mean():.4f}")
+    assert snr > 46.0, (name, snr, err)
+    assert (got["g711"] != ref["g711"]).mean() < 0.08
