@@ -19,11 +19,13 @@ class InfernBatchedWorker(InfernWrkThread, ABC):
     def infer(self, wi: object):
         self.inf_queue.put(wi)
 
-    def next_batch(self) -> Optional[List[object]]:
+    def next_batch(self, block: bool = True, limit: Optional[int] = None) -> Optional[List[object]]:
+        """block=False never waits (continuous batching polls while work is in flight); limit caps the batch below max_batch_size."""
         batch: List[object] = []
-        while len(batch) < self.max_batch_size:
+        cap = self.max_batch_size if limit is None else min(limit, self.max_batch_size)
+        while len(batch) < cap:
             try:
-                wi = self.inf_queue.get() if not batch else self.inf_queue.get_nowait()
+                wi = self.inf_queue.get() if (block and not batch) else self.inf_queue.get_nowait()
             except Empty:
                 break
             if wi is None:

@@ -4,6 +4,11 @@ InfernTTSWorker(lang, output_sr, device=None), .infer(wi) / .start() / .stop() /
 
 The reference caps a batch at 8 because its eager tail is launch-bound; the B200 tail wants thousands of
 windows in flight, so max_batch_size defaults to the engine's slot pool.
+
+continuous=True replaces the reference's run-a-batch-to-completion loop (:83-92) by continuous batching:
+between two engine calls the worker admits whatever has been queued as a new cohort, every cohort advances by one call, and
+the tail runs once over all live sessions (HelloSippyRTPipe.infer_many).  A request therefore waits at most one call
+(16 decoder steps, 0.512 s of audio) instead of the rest of the longest sentence in flight.
 """
 from __future__ import annotations
 
@@ -12,6 +17,7 @@ from typing import List
 import torch
 
 from infernos_b200.Cluster.InfernBatchedWorker import InfernBatchedWorker
+from infernos_b200.Core.InfernWrkThread import RTPWrkTRun
 from infernos_b200.HelloSippyTTSRT.HelloSippyRTPipe import HelloSippyPipeState, HelloSippyPipeStateBatched, HelloSippyPlayRequest, HelloSippyRTPipe
 
 # language -> HF model table of the reference (InfernTTSWorker.py:37-45); resolving these needs the hub
@@ -39,8 +45,11 @@ class InfernTTSWorker(InfernBatchedWorker):
     tts_engine: HelloSippyRTPipe
     output_sr: int
 
-    def __init__(self, lang, output_sr, device=None, **engine_kwa):
+    continuous: bool = False
+
+    def __init__(self, lang, output_sr, device=None, continuous: bool = False, **engine_kwa):
         super().__init__()
+        self.continuous = continuous
         if device is None:
             device = get_torch_hw()
         kwa = dict(lang2model[lang])
@@ -60,6 +69,39 @@ class InfernTTSWorker(InfernBatchedWorker):
                 raise
             if not self.tts_engine.unbatch_and_dispatch(state):
                 break
+
+    def run(self):
+        if not self.continuous:
+            return super().run()
+        self.thread_started()
+        cohorts: List[HelloSippyPipeStateBatched] = []
+        while self.get_state() == RTPWrkTRun:
+            in_flight = sum(len(c.dispatch) for c in cohorts)
+            room = self.max_batch_size - in_flight
+            wis = self.next_batch(block=not cohorts, limit=room) if room > 0 else []
+            if wis is None:
+                break
+            if wis:
+                for wi in wis:
+                    cb = getattr(wi, "_proc_start_cb", None)
+                    if cb is not None:
+                        cb()
+                cohorts.append(HelloSippyPipeStateBatched([HelloSippyPipeState(self.tts_engine, r) for r in wis], self.tts_engine))
+            if not cohorts:
+                continue
+            try:
+                self.tts_engine.infer_many(cohorts)
+            except RuntimeError as e:
+                for c in cohorts:
+                    self.handle_runtime_error(e, c, [])
+                raise
+            alive = []
+            for c in cohorts:
+                if self.tts_engine.unbatch_and_dispatch(c):
+                    alive.append(c)
+                else:
+                    c.release()                       # its pre_frames slots go back to the pool at once
+            cohorts = alive
 
     def handle_runtime_error(self, e, state, wis: List[HelloSippyPlayRequest]):
         print(f"InfernTTSWorker.handle_runtime_error: {e}")

@@ -14,6 +14,10 @@ What differs, by design:
   * the G.711 payload of every call is produced on the GPU in the same pass (state.g711); the reference encodes
     later, per call, on the CPU of another process (RTP/RTPOutputWorker.py:118).
   * unbatch_and_dispatch does one device->host copy per call instead of two .item() syncs and one .cpu() per session.
+  * continuous batching (the reference's `mergein` is disabled, HelloSippyRTPipeTest.py:145): infer_many()
+    takes any number of independently started batch states ("cohorts", each with its own front-half state and step counter)
+    and runs ONE tail call over the union of their live sessions, so requests admitted while others are mid-sentence share
+    the GPU pass.  InfernTTSWorker(continuous=True) drives it.
   * the autoregressive front half (SpeechT5 encoder/decoder/postnet, :111-118, :195-230) is out of this project's
     scope: it is reached through a small `frontend` object.  SpeechT5Frontend wraps a transformers model and
     issues the same calls the reference does; tests and benchmarks script it.
@@ -97,7 +101,7 @@ class HelloSippyPipeStateBatched:
         self.ends_at = torch.cat([s.ends_at for s in states])
         self.slots_host = pp._alloc_slots(len(states))
         self.slots = torch.tensor(self.slots_host, dtype=torch.int32, device=pp.device)
-        self._release = weakref.finalize(self, pp._free_slots, list(self.slots_host))
+        self._release = weakref.finalize(self, pp._free_slots, list(self.slots_host))     # also callable: state.release()
         self.audio = None
         self.g711 = None
         self.idx = 0
@@ -105,31 +109,50 @@ class HelloSippyPipeStateBatched:
         self.minlen, self.maxlen = pp.frontend.length_bounds(self, pp.minlenratio, pp.maxlenratio)
 
 
+def _release_state(state) -> None:
+    state._release()
+
+
+HelloSippyPipeStateBatched.release = _release_state      # returns the state's pre_frames slots to the pool (idempotent)
+
+
 class ScriptedFrontend:
-    """A front half that replays a fixed mel plan (B, N, 80), two frames per decoder step, and scripted stop steps.
-    Stands in for SpeechT5 in tests/benchmarks (the AR decoder is out of scope)."""
+    """A front half that replays a fixed mel plan, two frames per decoder step, and scripted stop steps.  Stands in for
+    SpeechT5 in tests/benchmarks (the AR decoder is out of scope).  `plan` is either one (B, N, 80) tensor for a single batch
+    (rows in request order) or a dict text -> ((N, 80) tensor, stop_step) from which every started batch state picks its rows,
+    which is what continuous batching needs.  The replay position lives on the batch state, so several states can be in flight."""
 
     reduction_factor = 2
     num_mel_bins = 80
 
-    def __init__(self, plan: torch.Tensor, stop_step: Optional[List[int]] = None, maxlen: int = 1 << 30):
-        self.plan, self.stop_step, self.maxlen = plan, stop_step or [1 << 30] * plan.size(0), maxlen
-        self.step_no = 0
+    def __init__(self, plan, stop_step: Optional[List[int]] = None, maxlen: int = 1 << 30):
+        self.plan, self.maxlen = plan, maxlen
+        self.stop_step = stop_step if (stop_step or isinstance(plan, dict)) else [1 << 30] * plan.size(0)
 
     def tokenize(self, text):
         return torch.zeros(1, 1, dtype=torch.long)
 
     def start(self, state, states):
-        self.step_no = 0
+        state._fe_step = 0
+        if isinstance(self.plan, dict):
+            rows = [self.plan[s.text] for s in states]
+            n = max(r[0].size(0) for r in rows)
+            state._fe_plan = torch.stack([torch.nn.functional.pad(r[0], (0, 0, 0, n - r[0].size(0))) for r in rows])
+            state._fe_stop = [int(r[1]) for r in rows]
+        else:
+            state._fe_plan, state._fe_stop = self.plan, self.stop_step
 
     def length_bounds(self, state, minlenratio, maxlenratio):
         return 0, self.maxlen
 
     def step(self, state):
-        s = self.step_no
-        self.step_no += 1
-        spectrum = self.plan[:, 2 * s:2 * s + 2, :]
-        prob = torch.tensor([[1.0, 1.0] if s >= st else [0.0, 0.0] for st in self.stop_step])
+        s = state._fe_step
+        state._fe_step += 1
+        plan = state._fe_plan
+        spectrum = plan[:, 2 * s:2 * s + 2, :]
+        if spectrum.size(1) < 2:                      # past the end of the script: silence-level frames
+            spectrum = torch.nn.functional.pad(spectrum, (0, 0, 0, 2 - spectrum.size(1)), value=-4.0)
+        prob = torch.tensor([[1.0, 1.0] if s >= st else [0.0, 0.0] for st in state._fe_stop])
         return spectrum, prob
 
     def postnet(self, spectrogram):
@@ -270,25 +293,63 @@ class HelloSippyRTPipe:
             self._free.extend(slots)
 
     # ---- the engine ----------------------------------------------------------------------------------------
+    def _front_half(self, state: HelloSippyPipeStateBatched) -> torch.Tensor:
+        """Reference :195-230 for one batch state: 16 decoder steps (32 frames), stop bookkeeping, postnet.  -> mel (B, 32, 80)."""
+        frames = []
+        nframes = 0
+        eframes = self.pre_nframes + self.post_nframes
+        while nframes < self.chunk_size * 4:
+            spectrum, prob = self.frontend.step(state)
+            frames.append(spectrum)
+            nframes += spectrum.size(1)
+            stop = (prob >= self.threshold).sum(dim=1).cpu() > 0
+            fire = (state.ends_at < 0) & (state.minlen <= state.idx) & (stop | (state.maxlen <= state.idx))
+            state.ends_at = torch.where(fire, state.idx + eframes // self.reduction_factor, state.ends_at)
+            state.idx += 1
+        spectrogram = self.frontend.postnet(torch.cat(frames, dim=1))
+        return spectrogram.to(device=self.device, dtype=torch.float32).contiguous()
+
     def infer(self, state: HelloSippyPipeStateBatched) -> None:
         with self.cuda_lock:
-            frames = []
-            nframes = 0
-            eframes = self.pre_nframes + self.post_nframes
-            while nframes < self.chunk_size * 4:
-                spectrum, prob = self.frontend.step(state)
-                frames.append(spectrum)
-                nframes += spectrum.size(1)
-                stop = (prob >= self.threshold).sum(dim=1).cpu() > 0
-                fire = (state.ends_at < 0) & (state.minlen <= state.idx) & (stop | (state.maxlen <= state.idx))
-                state.ends_at = torch.where(fire, state.idx + eframes // self.reduction_factor, state.ends_at)
-                state.idx += 1
-            spectrogram = self.frontend.postnet(torch.cat(frames, dim=1))
-            mel = spectrogram.to(device=self.device, dtype=torch.float32).contiguous()
+            mel = self._front_half(state)
             if self.fused:
                 state.g711, state.audio = self.tail.tail(state.slots, mel, law=self.law)
             else:
                 self._infer_three_callables(state, mel)
+
+    def infer_many(self, states: List[HelloSippyPipeStateBatched]) -> None:
+        """Continuous batching: every state advances by one call (its own front half, its own step counter), and the tail runs
+        ONCE over the union of the sessions that still have a listener.  Sessions are independent in the tail (state = one
+        pre_frames slot each), so a session's audio does not depend on which other sessions share the pass."""
+        if not states:
+            return
+        if not self.fused:
+            for st in states:
+                self.infer(st)
+            return
+        with self.cuda_lock:
+            mels, slots, parts = [], [], []
+            for st in states:
+                mel = self._front_half(st)
+                live = [i for i, d in enumerate(st.dispatch) if d is not None]
+                parts.append((st, live, mel.size(0), mel.size(1)))
+                if live:
+                    idx = torch.tensor(live, dtype=torch.long, device=self.device)
+                    mels.append(mel.index_select(0, idx))
+                    slots.append(st.slots.index_select(0, idx))
+            if not mels:
+                return
+            g711, audio = self.tail.tail(torch.cat(slots), torch.cat(mels), law=self.law)
+            row = 0
+            for st, live, B, nfr in parts:
+                # rows of sessions that already ended stay zero: unbatch_and_dispatch never reads them
+                st.audio = audio.new_zeros(B, audio.size(1))
+                st.g711 = g711.new_zeros(B, g711.size(1))
+                if live:
+                    idx = torch.tensor(live, dtype=torch.long, device=self.device)
+                    st.audio.index_copy_(0, idx, audio[row:row + len(live)])
+                    st.g711.index_copy_(0, idx, g711[row:row + len(live)])
+                    row += len(live)
 
     def _infer_three_callables(self, state, mel):
         """Lines 231-240 of the reference, through self.vocoder / self.chunker / self.resampler."""
