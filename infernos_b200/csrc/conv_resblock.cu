@@ -54,6 +54,9 @@ struct RbParams {
     const float *acc_src;    // optional fp32 [W][T][C] added to the result (MRF sum); may alias out32
     float *out32;            // optional
     __nv_bfloat16 *outb;     // optional: bf16(lrelu(result, outb_slope))
+    const float *post_w;     // EPI 5: conv_post weights [7][32] fp32 and bias [1] (device), output audio [W][T] fp32
+    const float *post_b;
+    float *audio;
     float slope, outb_slope, div, rdiv;
     int W, T, taps, H, V, tiles_per_win, tps, ngroups, nslots;
     int dil0, dil1, dil2;
@@ -126,7 +129,8 @@ static constexpr int kRbDbgEvents = 48, kRbDbgCtas = 4096;
 // TMA weight ring, then NMW MMA-issuing warps, each owning kS / NMW sub-tiles (a sub-tile's accumulator is only ever touched by
 // one issuing thread, so the summation order is fixed).
 // EPI selects the final epilogue at compile time (its code is a third of the kernel, and the kernel has to fit the instruction
-// cache): 0 out32 = r;  1 out32 = acc + r;  2 outb = bf16(lrelu((acc + r) / div));  3 out32 = (acc + r) / div;  4 everything decided at run time.
+// cache): 0 out32 = r;  1 out32 = acc + r;  2 outb = bf16(lrelu((acc + r) / div));  3 out32 = (acc + r) / div;  4 everything decided at run time;
+// 5 (C = 32 only) the vocoder's last step fused in: audio = tanh(conv_post(lrelu((acc + r) / div, 0.01))), nothing else written.
 template <int C, int NEW, int NMW, int EPI, bool DBG>
 __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 128 : 168) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ RbParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -308,6 +312,91 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                 if (threadIdx.x == 0) RB_DBG(4 + 4 * i + 2 * e);
             }
             if (i == 2) {
+                if constexpr (EPI == 5) {
+                    // ---- last ResBlock of the vocoder: MRF mean -> lrelu(0.01) -> conv_post (32 -> 1, 7 taps) -> tanh, in place of
+                    // writing the fp32 mean and reading it back in k_conv_post (modeling_speecht5.py:3074-3078).  Every MMA of the
+                    // CTA has to be complete first, because the whole 512 x 32 fp32 slab V is laid over the weight ring and A1
+                    // (rows of 128 bytes, 16-byte pieces XOR-ed with row & 7) and the conv_post weights over A2.
+                    static_assert(EPI != 5 || (C == 32 && NEW == 4), "conv_post is fused into the C = 32 stage only");
+#pragma unroll 1
+                    for (int s = 0; s < kS; s++) mbar_wait(X_FULL(s), par);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (threadIdx.x == 0) RB_DBG(5 + 4 * i);
+                    const uint32_t v_u32 = smem_u32(smem);
+                    float *wp = reinterpret_cast<float *>(sA2);
+                    for (int q = threadIdx.x; q < 7 * 32; q += NEW * 32) wp[q] = __ldg(p.post_w + q);
+                    // pass A (lane owns a row): X + running bias -> V
+#pragma unroll 1
+                    for (int s = 0; s < kS; s++) {
+                        uint32_t a32[32];
+                        tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C), a32);
+                        const float *cb = p.cbias + 2 * C;
+                        const int r = s * 128 + rq;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const uint32_t dst = v_u32 + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(__uint_as_float(a32[4 * j]) + cb[4 * j]),
+                                         "f"(__uint_as_float(a32[4 * j + 1]) + cb[4 * j + 1]), "f"(__uint_as_float(a32[4 * j + 2]) + cb[4 * j + 2]),
+                                         "f"(__uint_as_float(a32[4 * j + 3]) + cb[4 * j + 3]) : "memory");
+                        }
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(NEW * 32) : "memory");
+                    // pass B (8 lanes per row, coalesced): + MRF partial sum, mean, lrelu(0.01), zero outside the window
+                    {
+                        const float rcp = p.rdiv, nd = -p.div;
+                        const float *aq = p.acc_src + ((size_t)w * p.T + (t_base + quad * 32 + sub_r)) * C + c4 * 4;
+#pragma unroll 1
+                        for (int s = 0; s < kS; s++) {
+                            float4 acc4[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++)
+                                acc4[j] = ((inside_t[j] >> s) & 1u) ? *reinterpret_cast<const float4 *>(aq + ((size_t)s * 128 + j * 4) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int r = s * 128 + quad * 32 + j * 4 + sub_r;
+                                const uint32_t a = v_u32 + (uint32_t)(r * 128 + ((c4 ^ (r & 7)) << 4));
+                                float4 v;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+                                const bool in = ((inside_t[j] >> s) & 1u) != 0u;
+                                float o[4] = {acc4[j].x + v.x, acc4[j].y + v.y, acc4[j].z + v.z, acc4[j].w + v.w};
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    const float q0 = o[e] * rcp;
+                                    const float m = fmaf(fmaf(nd, q0, o[e]), rcp, q0);       // (acc + r) / 3, see the generic epilogue
+                                    o[e] = in ? fmaxf(m, 0.01f * m) : 0.0f;
+                                }
+                                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+                            }
+                        }
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(NEW * 32) : "memory");
+                    // pass C (one output sample per thread and trip): 7 taps x 32 channels, weights broadcast from shared memory
+                    {
+                        const float pb = __ldg(p.post_b);
+                        const int tid = threadIdx.x;             // 0 .. 127 (epilogue warps are warps 0 .. 3)
+#pragma unroll 1
+                        for (int r = p.H + tid; r < p.H + p.V; r += NEW * 32) {
+                            const int t = t_base + r;
+                            if (t >= p.T) break;
+                            float acc = pb;
+#pragma unroll
+                            for (int j = 0; j < 7; j++) {
+                                const int rr = r - 3 + j;
+                                if ((unsigned)rr >= (unsigned)kRows) continue;          // outside the slab == outside the window here
+#pragma unroll
+                                for (int ch = 0; ch < 8; ch++) {
+                                    float4 x, wv;
+                                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                                                 : "r"(v_u32 + (uint32_t)(rr * 128 + ((ch ^ (rr & 7)) << 4))) : "memory");
+                                    wv = *reinterpret_cast<const float4 *>(wp + j * 32 + ch * 4);
+                                    acc = fmaf(wv.x, x.x, acc); acc = fmaf(wv.y, x.y, acc); acc = fmaf(wv.z, x.z, acc); acc = fmaf(wv.w, x.w, acc);
+                                }
+                            }
+                            p.audio[(size_t)w * p.T + t] = tanhf(acc);
+                        }
+                    }
+                    if (threadIdx.x == 0) RB_DBG(6 + 4 * i);
+                } else {
                 // ---- final epilogue: rows [H, H+V) of the slab leave through a per-warp transpose (A1 is dead: every conv1
                 // has retired), 8 lanes per 128 contiguous bytes of an output row.  The MRF partial sum (acc_src) is read in that
                 // same coalesced order, one 32x32 piece ahead, starting before the last conv2 has finished.
@@ -380,6 +469,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                 for (int q = 0; q < NCHW; q += 2) {
                     out_piece(q, accA, accB);
                     out_piece(q + 1, accB, accA);
+                }
                 }
                 if (threadIdx.x == 0) RB_DBG(6 + 4 * i);
             }
@@ -563,13 +653,13 @@ void resblock_free(ResBlockPack &p) {
 }
 
 
-static bool g_rb_attr[64][3][6] = {};
+static bool g_rb_attr[64][3][7] = {};
 
 template <int C, int NEW, int NMW, int EPI, bool DBG>
 static int launch_rb_(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int wslot) {
     int dev = 0;
     B2_CUDA_OK(cudaGetDevice(&dev));
-    const int eslot = DBG ? 5 : EPI;
+    const int eslot = DBG ? 6 : EPI;
     if (dev < 64 && !g_rb_attr[dev][wslot][eslot]) {
         B2_CUDA_OK(cudaFuncSetAttribute(k_resblock<C, NEW, NMW, EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         g_rb_attr[dev][wslot][eslot] = true;
@@ -584,6 +674,9 @@ static int launch_rb_(const CUtensorMap &tm, const RbParams &p, unsigned grid, s
 template <int C, int NEW, int NMW>
 static int launch_rb(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int wslot) {
     if (p.dbg) return launch_rb_<C, NEW, NMW, 4, true>(tm, p, grid, smem, st, wslot);
+    if constexpr (C == 32) {
+        if (p.audio) return launch_rb_<C, NEW, NMW, 5, false>(tm, p, grid, smem, st, wslot);
+    }
     const bool acc = p.acc_src != nullptr, dv = p.div != 1.0f, o32 = p.out32 != nullptr, ob = p.outb != nullptr;
     if (!acc && !dv && o32 && !ob) return launch_rb_<C, NEW, NMW, 0, false>(tm, p, grid, smem, st, wslot);
     if (acc && !dv && o32 && !ob) return launch_rb_<C, NEW, NMW, 1, false>(tm, p, grid, smem, st, wslot);
@@ -595,10 +688,13 @@ static int launch_rb(const CUtensorMap &tm, const RbParams &p, unsigned grid, si
 int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     const ResBlockPack &pk = *a.pack;
     if (!pk.tmap || !pk.w) return set_error("resblock: weights were not packed");
-    if (!a.x || (!a.out32 && !a.outb)) return set_error("resblock: null input or no output");
+    const bool post = a.audio != nullptr;
+    if (post && (pk.C != 32 || !a.post_w || !a.post_b || !a.acc_src)) return set_error("resblock: the conv_post epilogue needs C = 32, weights and the MRF partial sum");
+    if (!a.x || (!a.out32 && !a.outb && !post)) return set_error("resblock: null input or no output");
     if (a.W <= 0 || a.T <= 0) return 0;
     RbParams p;
     p.x = a.x; p.acc_src = a.acc_src; p.out32 = a.out32; p.outb = a.outb;
+    p.post_w = a.post_w; p.post_b = a.post_b; p.audio = a.audio;
     p.slope = a.slope; p.outb_slope = a.outb_slope; p.div = a.div; p.rdiv = 1.0f / a.div;
     p.W = a.W; p.T = a.T; p.taps = pk.taps;
     for (int i = 0; i < 3 * kRbMaxC; i++) { p.bias1[i] = 0.0f; p.cbias[i] = 0.0f; }
@@ -611,7 +707,7 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
         // the whole window fits in one slab: its edges are the reference's own zero padding, no halo is needed
         p.H = 0; p.tiles_per_win = 1; p.V = a.T;
     } else {
-        p.H = ((pk.taps - 1) / 2) * dsum;
+        p.H = ((pk.taps - 1) / 2) * dsum + (post ? 3 : 0);      // conv_post reaches three more rows either side
         const int vmax = rows - 2 * p.H;
         if (vmax < 64) return set_error("resblock: halo %d leaves no room in a %d-row slab", p.H, rows);
         p.tiles_per_win = cdiv(a.T, vmax);

@@ -48,6 +48,9 @@ struct ResBlockArgs {
     __nv_bfloat16 *outb = nullptr;
     float slope = 0.1f, outb_slope = 1.0f, div = 1.0f;
     int W = 0, T = 0;
+    // C = 32 only: fuse the vocoder's last step, audio[W][T] = tanh(conv_post(lrelu((acc_src + x3) / div, 0.01))); nothing else is written
+    const float *post_w = nullptr, *post_b = nullptr;     // device: [7][32], [1]
+    float *audio = nullptr;
 };
 bool resblock_supported(int C, int taps);
 // gathers the six convolutions' bf16 weights into one TMA-addressable buffer (device allocations are appended to `allocs`)

@@ -317,10 +317,12 @@ static int vocoder_bf16(b2_ctx *c, const float *xn, int W, int T, float *audio, 
     }
     const __nv_bfloat16 *stage_in = ws.c0b;
     int Tc = T;
+    bool post_done = false;
     for (int i = 0; i < 4; i++) {
         // One launch per ResBlock where the fused kernel covers the stage (conv_resblock.cu); B2_RESBLOCK_FUSION=0 keeps the
         // conv-by-conv path everywhere.
         static const bool fusion_on = !(getenv("B2_RESBLOCK_FUSION") && atoi(getenv("B2_RESBLOCK_FUSION")) == 0);
+        static const bool post_fusion = !(getenv("B2_POST_FUSION") && atoi(getenv("B2_POST_FUSION")) == 0);
         const bool fused = fusion_on && c->rb[i][0].tmap && c->rb[i][1].tmap && c->rb[i][2].tmap;
         UmmaConvArgs u;
         u.in = stage_in; u.layer = &c->up[i]; u.out32 = ws.h; u.outb = fused ? nullptr : ws.hb; u.outb_slope = 0.1f; u.W = W; u.T = Tc;
@@ -336,6 +338,7 @@ static int vocoder_bf16(b2_ctx *c, const float *xn, int W, int T, float *audio, 
                 else {
                     ra.div = 3.0f;
                     if (i < 3) ra.outb = ws.sb;
+                    else if (post_fusion) { ra.post_w = c->post_w; ra.post_b = c->post_b; ra.audio = audio; post_done = true; }   // conv_post + tanh in the same launch
                     else ra.out32 = ws.s0;
                 }
                 PROF(PC_RESBLOCK, launch_resblock(ra, st));
@@ -383,7 +386,7 @@ static int vocoder_bf16(b2_ctx *c, const float *xn, int W, int T, float *audio, 
         }
         stage_in = ws.sb;
     }
-    PROF(PC_CONV_POST, launch_conv_post(ws.s0, c->post_w, c->post_b, audio, W, Tc, st));
+    if (!post_done) PROF(PC_CONV_POST, launch_conv_post(ws.s0, c->post_w, c->post_b, audio, W, Tc, st));
     return 0;
 }
 
