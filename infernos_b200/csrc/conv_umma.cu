@@ -323,12 +323,15 @@ struct UmmaParams2 {
     int nA;            // A buffers: 2, or 1 when two do not fit (per-K-block recycling still overlaps the refill)
     int resident;      // all (K-block, tap) weight tiles stay in shared memory
     int rows_per_thr;  // A rows handled by one producer thread per K block
+    int iters;         // tiles per CTA, ceil(total_tiles / grid)
+    int mc;            // 2-CTA cluster: each CTA fetches half of every weight tile and multicasts it to both (needs ntiles == 1)
 };
 
 static constexpr int kThreads2 = 320;
 
 template <int N_TILE, int MINB>
-__global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_constant__ CUtensorMap tmap_w, const UmmaParams2 pp) {
+__global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
+                                                                  const UmmaParams2 pp) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const UmmaParams &p = pp.b;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
-        for (int s = 0; s < 4; s++) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
+        for (int s = 0; s < 4; s++) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), pp.mc ? 2 : 1); }     // multicast: both CTAs' MMAs release a slot
         for (int b = 0; b < 2; b++)
             for (int k = 0; k < 8; k++) { mbar_init(A_FULL(b, k), 128); mbar_init(A_EMPTY(b, k), 1); }
         for (int a = 0; a < 2; a++) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
@@ -362,11 +365,13 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * N_TILE)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(pp.mc ? &tmap_h : &tmap_w) : "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (pp.mc) cluster_sync_all();           // the peer's barriers exist before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = pp.mc ? cluster_ctarank() : 0u;
 
     auto tile_coords = [&](int tile, int &w0, int &t0, int &n0) {
         const int mt = (pp.ntiles > 1) ? fdiv(tile, p.m_ntiles) : tile;
@@ -379,8 +384,11 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
         // =========================== epilogue ===========================
         float *stg = sStage + warp * 32 * kStageLd;
         const int sub_r = lane >> 3, c4 = lane & 7;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x, ++it) {
+        // in multicast mode both CTAs of a cluster run the same number of tiles (the weight ring is shared): tiles past the end are
+        // dummies whose rows are all masked (w >= W)
+        for (int it = 0; it < pp.iters; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            if (!pp.mc && tile >= pp.total_tiles) break;
             int w0, t0, n0;
             tile_coords(tile, w0, t0, n0);
             const int acc = it & 1, use = it >> 1;
@@ -459,14 +467,20 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                         tma_load_3d(smem_u32(sB + (size_t)(kb * p.taps + j) * b_tile_bytes), &tmap_w, B_FULL(0), kb * KB, 0, j);
             } else {
                 int stage = 0; uint32_t phase = 0;
-                for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x) {
+                for (int it = 0; it < pp.iters; ++it) {
+                    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                    if (!pp.mc && tile >= pp.total_tiles) break;
                     int w0, t0, n0;
                     tile_coords(tile, w0, t0, n0);
                     for (int kb = 0; kb < p.nkb; kb++)
                         for (int j = 0; j < p.taps; j++) {
                             mbar_wait(B_EMPTY(stage), phase ^ 1);
                             mbar_expect_tx(B_FULL(stage), b_tile_bytes);
-                            tma_load_3d(smem_u32(sB + (size_t)stage * b_tile_bytes), &tmap_w, B_FULL(stage), kb * KB, n0, j);
+                            if (pp.mc)       // my half of the tile, into both CTAs: L2 serves every weight byte once per cluster
+                                tma_load_3d_mc(smem_u32(sB + (size_t)stage * b_tile_bytes) + crank * (b_tile_bytes / 2), &tmap_h, B_FULL(stage),
+                                               kb * KB, n0 + (int)crank * (N_TILE / 2), j, (uint16_t)3);
+                            else
+                                tma_load_3d(smem_u32(sB + (size_t)stage * b_tile_bytes), &tmap_w, B_FULL(stage), kb * KB, n0, j);
                             if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         }
                 }
@@ -485,8 +499,9 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
             const int ksteps = KB / 16;
             int stage = 0; uint32_t phase = 0;
             if (pp.resident) { mbar_wait(B_FULL(0), 0); }
-            int it = 0;
-            for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x, ++it) {
+            for (int it = 0; it < pp.iters; ++it) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                if (!pp.mc && tile >= pp.total_tiles) break;
                 const int acc = it & 1, use = it >> 1;
                 const int abuf = (pp.nA == 2) ? (it & 1) : 0, ause = (pp.nA == 2) ? (it >> 1) : it;
                 mbar_wait(ACC_EMPTY(acc), (uint32_t)((use & 1) ^ 1));
@@ -511,7 +526,8 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                             accum = 1;
                         }
                         if (!pp.resident) {
-                            umma_commit(B_EMPTY(stage));
+                            if (pp.mc) umma_commit_mc(B_EMPTY(stage), (uint16_t)3);
+                            else umma_commit(B_EMPTY(stage));
                             if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -528,8 +544,9 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
         const int cpr = 1 << cshift;
         const int rstep = 128 >> cshift;
         const int r_first = ptid >> cshift, c = ptid & (cpr - 1);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x, ++it) {
+        for (int it = 0; it < pp.iters; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            if (!pp.mc && tile >= pp.total_tiles) break;
             int w0, t0, n0;
             tile_coords(tile, w0, t0, n0);
             const int abuf = (pp.nA == 2) ? (it & 1) : 0, ause = (pp.nA == 2) ? (it >> 1) : it;
@@ -562,6 +579,7 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (pp.mc) cluster_sync_all();           // nobody leaves while the peer may still arrive on this CTA's barriers
     if (warp == 5) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * N_TILE)) : "memory");
     }
@@ -628,11 +646,21 @@ int umma_prepare_layer(Layer &l) {
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete tm; return set_error("cuTensorMapEncodeTiled failed with CUresult %d (Cin %d Cout %d taps %d)", (int)r, l.Cin, l.Cout, l.taps); }
     l.tmap = tm;
+    if (nt == 256 && l.Cout == 256) {
+        // the persistent kernel's 2-CTA multicast mode: the same tensor with a box of half the tile's rows
+        CUtensorMap *th = new CUtensorMap();
+        cuuint32_t boxh[3] = {(cuuint32_t)KB, (cuuint32_t)(nt / 2), 1};
+        r = g_encode(th, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)l.wbf, gdim, gstr, boxh, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { delete th; return set_error("cuTensorMapEncodeTiled (half box) failed with CUresult %d", (int)r); }
+        l.tmap_half = th;
+    }
     return 0;
 }
 
 void umma_free_layer(Layer &l) {
     if (l.tmap) { delete reinterpret_cast<CUtensorMap *>(l.tmap); l.tmap = nullptr; }
+    if (l.tmap_half) { delete reinterpret_cast<CUtensorMap *>(l.tmap_half); l.tmap_half = nullptr; }
 }
 
 template <int NT>
@@ -752,7 +780,7 @@ static int launch_conv_umma_v1(const UmmaConvArgs &a, cudaStream_t st) {
 static int g_occ2[64][4] = {};
 
 template <int NT, int MINB>
-static int launch_nt2(const CUtensorMap &tm, const UmmaParams2 &p, size_t smem, cudaStream_t st, int slot) {
+static int launch_nt2(const CUtensorMap &tm, const CUtensorMap *tm_half, UmmaParams2 &p, size_t smem, cudaStream_t st, int slot) {
     int dev = 0;
     B2_CUDA_OK(cudaGetDevice(&dev));
     if (dev >= 64) return set_error("conv_umma: device index too large");
@@ -763,9 +791,28 @@ static int launch_nt2(const CUtensorMap &tm, const UmmaParams2 &p, size_t smem, 
     int occ = 0;
     B2_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_conv_umma_p<NT, MINB>, kThreads2, smem));
     occ = std::max(1, std::min(occ, std::min(MINB, 512 / (2 * NT))));
-    const int grid = std::min(p.total_tiles, sm_count() * occ);
-    k_conv_umma_p<NT, MINB><<<grid, kThreads2, smem, st>>>(tm, p);
-    B2_LAUNCH_OK("k_conv_umma_p");
+    int grid = std::min(p.total_tiles, sm_count() * occ);
+    // Experiment (B2_UMMA_MULTICAST=1): weight multicast in 2-CTA clusters for the C=256 ResBlock convs (one N tile, weights streamed:
+    // 0.8-2.9 GB of L2 reads per launch otherwise) -- each CTA fetches half of every weight tile and TMA-multicasts it to both.
+    // Measured on B200: correct, and NO faster (23.92 vs 23.93 ms per step); a 2-deep instead of 3-deep weight ring costs only 2.6 %
+    // as well, so these launches are bound neither by L2 reads nor by weight-fetch latency.  Off by default.
+    static const bool mc_on = getenv("B2_UMMA_MULTICAST") && atoi(getenv("B2_UMMA_MULTICAST")) != 0;
+    p.mc = (mc_on && tm_half && p.ntiles == 1 && !p.resident && grid >= 2 && occ == 1) ? 1 : 0;
+    if (p.mc) grid &= ~1;
+    p.iters = cdiv(p.total_tiles, grid);
+    if (!p.mc) {
+        k_conv_umma_p<NT, MINB><<<grid, kThreads2, smem, st>>>(tm, tm, p);
+        B2_LAUNCH_OK("k_conv_umma_p");
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    B2_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma_p<NT, MINB>, tm, *tm_half, (const UmmaParams2)p));
+    B2_LAUNCH_OK("k_conv_umma_p (2-CTA multicast)");
     return 0;
 }
 
@@ -825,17 +872,20 @@ int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
         while (stages > 2 && stages * b_tile + pp.nA * a_bytes + fixed > budget) stages--;
         if (stages * b_tile + pp.nA * a_bytes + fixed > budget) { pp.nA = 1; stages = 4; }
         while (stages > 2 && stages * b_tile + pp.nA * a_bytes + fixed > budget) stages--;
+        static const int st_cap = getenv("B2_UMMA_P_STAGES") ? atoi(getenv("B2_UMMA_P_STAGES")) : 4;     // analysis: fewer weight tiles in flight
+        stages = std::max(1, std::min(stages, st_cap));
         p.stages = std::min(stages, std::max(1, p.nkb * l.taps));
         b_bytes = p.stages * b_tile;
     }
     const size_t smem = b_bytes + pp.nA * a_bytes + fixed;
     if (smem > 227 * 1024) return set_error("conv_umma: tile needs %zu bytes of shared memory", smem);
     const CUtensorMap &tm = *reinterpret_cast<const CUtensorMap *>(l.tmap);
+    const CUtensorMap *th = reinterpret_cast<const CUtensorMap *>(l.tmap_half);
     switch (nt) {
-        case 32: return launch_nt2<32, 3>(tm, pp, smem, st, 0);
-        case 64: return launch_nt2<64, 2>(tm, pp, smem, st, 1);
-        case 128: return launch_nt2<128, 1>(tm, pp, smem, st, 2);
-        default: return launch_nt2<256, 1>(tm, pp, smem, st, 3);
+        case 32: return launch_nt2<32, 3>(tm, nullptr, pp, smem, st, 0);
+        case 64: return launch_nt2<64, 2>(tm, nullptr, pp, smem, st, 1);
+        case 128: return launch_nt2<128, 1>(tm, nullptr, pp, smem, st, 2);
+        default: return launch_nt2<256, 1>(tm, th, pp, smem, st, 3);
     }
 }
 

@@ -19,6 +19,7 @@ struct Layer {
     float *bias = nullptr;           // [Cout] fp32
     __nv_bfloat16 *wbf = nullptr;    // [taps][Cout][Cin] bf16, K-major (tensor-core path); nullptr if unused
     void *tmap = nullptr;            // host copy of the CUtensorMap for wbf (tensor-core path)
+    void *tmap_half = nullptr;       // same weights, box of half the N tile: each CTA of a 2-CTA cluster fetches one half and multicasts it
 };
 
 // the six convolutions of one ResBlock packed for the fused kernel (conv_resblock.cu)

@@ -40,6 +40,7 @@ def _run(tmp_path, name, env):
     ("conv_by_conv_resblocks", {"B2_RESBLOCK_FUSION": "0"}),
     ("tall_stage0_tiles", {"B2_UMMA_TALL256": "1"}),
     ("separate_conv_post", {"B2_POST_FUSION": "0"}),
+    ("cluster_multicast_weights", {"B2_UMMA_MULTICAST": "1"}),
 ])
 def test_variant_matches_default(tmp_path, name, env):
     ref = _run(tmp_path, "default", {})
