@@ -396,15 +396,33 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
             const int s = (p.nseg > 1) ? fdiv(m, p.m_period) : 0;
             const int t = t0 + (m - s * p.period);
             const int w = w0 + s;
-            const int grow_own = ((t < p.T) && (s < p.nseg) && (w < p.W)) ? (w * p.T + t) : -1;
+            const int grow_own = ((t < p.T) && (s < p.nseg) && (w < p.W) && !(p.flags & 4)) ? (w * p.T + t) : -1;
             int grow[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) grow[i] = __shfl_sync(0xffffffffu, grow_own, i * 4 + sub_r);
             const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * N_TILE) + ((uint32_t)(warp * 32) << 16);
+            // The fp32 residual (and the MRF running sum) of a 32-column piece are fetched ONE PIECE AHEAD, the first one before the
+            // accumulator barrier is even waited on: loaded right before use they cost a full memory latency per half piece, which made
+            // the conv2 launches of stage 0 epilogue-bound (what-if runs: epilogue memory = 2.9 of the 8.1 ms of this kernel family).
+            // (the MRF sum, present in one conv out of six, is fetched at the top of its own piece instead: registers)
+            float4 res_n[8];
+            auto fetch = [&](int c0n) {
+                const int coln = n0 + c0n + c4 * 4;
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    res_n[i] = (grow[i] >= 0) ? *reinterpret_cast<const float4 *>(p.residual + (size_t)grow[i] * p.N + coln) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            if (p.residual) fetch(0);
 #pragma unroll 1
             for (int c0 = 0; c0 < N_TILE; c0 += 32) {
                 const int col = n0 + c0 + c4 * 4;
                 const float4 bias = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
+                float4 accs[8];
+                if (p.acc_src) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        accs[i] = (grow[i] >= 0) ? *reinterpret_cast<const float4 *>(p.acc_src + (size_t)grow[i] * p.N + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 if (c0 == 0) {
                     mbar_wait(ACC_FULL(acc), (uint32_t)(use & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -423,35 +441,25 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                         *reinterpret_cast<uint4 *>(stg + lane * kStageLd + i * 4) = make_uint4(a32[4 * i], a32[4 * i + 1], a32[4 * i + 2], a32[4 * i + 3]);
                 }
                 __syncwarp();
+                float4 res[8];
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    float4 res[4], accs[4];
-                    if (p.residual) {
+                for (int i = 0; i < 8; i++) res[i] = res_n[i];
+                if (p.residual && c0 + 32 < N_TILE) fetch(c0 + 32);
 #pragma unroll
-                        for (int i = 0; i < 4; i++)
-                            res[i] = grow[h * 4 + i] >= 0 ? *reinterpret_cast<const float4 *>(p.residual + (size_t)grow[h * 4 + i] * p.N + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    if (p.acc_src) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-                            accs[i] = grow[h * 4 + i] >= 0 ? *reinterpret_cast<const float4 *>(p.acc_src + (size_t)grow[h * 4 + i] * p.N + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int g = grow[h * 4 + i];
-                        if (g < 0) continue;
-                        float4 v = *reinterpret_cast<const float4 *>(stg + ((h * 4 + i) * 4 + sub_r) * kStageLd + c4 * 4);
-                        v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
-                        if (p.residual) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
-                        if (p.acc_src) { v.x = accs[i].x + v.x; v.y = accs[i].y + v.y; v.z = accs[i].z + v.z; v.w = accs[i].w + v.w; }
-                        if (p.div != 1.0f) { v.x = __fdiv_rn(v.x, p.div); v.y = __fdiv_rn(v.y, p.div); v.z = __fdiv_rn(v.z, p.div); v.w = __fdiv_rn(v.w, p.div); }
-                        const size_t o = (size_t)g * p.N + col;
-                        if (p.out32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
-                        if (p.outb) {
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
-                            __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
-                            *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
-                        }
+                for (int i = 0; i < 8; i++) {
+                    const int g = grow[i];
+                    if (g < 0) continue;
+                    float4 v = *reinterpret_cast<const float4 *>(stg + (i * 4 + sub_r) * kStageLd + c4 * 4);
+                    v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+                    if (p.residual) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+                    if (p.acc_src) { v.x = accs[i].x + v.x; v.y = accs[i].y + v.y; v.z = accs[i].z + v.z; v.w = accs[i].w + v.w; }
+                    if (p.div != 1.0f) { v.x = __fdiv_rn(v.x, p.div); v.y = __fdiv_rn(v.y, p.div); v.z = __fdiv_rn(v.z, p.div); v.w = __fdiv_rn(v.w, p.div); }
+                    const size_t o = (size_t)g * p.N + col;
+                    if (p.out32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
+                    if (p.outb) {
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
+                        __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
+                        *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
                     }
                 }
                 __syncwarp();
@@ -569,7 +577,7 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                     const int r = r_first + i * rstep;
                     if (r < p.R) {
                         const __nv_bfloat16 *src = grow[i] >= 0 ? p.in + (size_t)grow[i] * p.Cin + kb * KB + c * 8 : p.in;
-                        cp_async16(sA_u32 + (uint32_t)(((kb * cpr + c) * p.R + r) * 16), src, grow[i] >= 0 ? 16u : 0u);
+                        cp_async16(sA_u32 + (uint32_t)(((kb * cpr + c) * p.R + r) * 16), src, (grow[i] >= 0 && !(p.flags & 8)) ? 16u : 0u);
                     }
                 }
                 cp_async_arrive_noinc(A_FULL(abuf, kb));
