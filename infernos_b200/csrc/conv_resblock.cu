@@ -420,7 +420,12 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                 if (has_acc) ld_acc(0, accA);
                 if (threadIdx.x == 0) RB_DBG(40);
                 const float rcp = p.rdiv, nd = -p.div;
-                auto out_piece = [&](int q, float4 (&acur)[8], float4 (&anx)[8]) {
+                // (one copy of this body: the next piece's partial sums are fetched into accB and moved over, which is cheaper
+                // than a second, ping-pong copy of the code -- the kernel has to stay small)
+#pragma unroll 1
+                for (int q = 0; q < NCHW; q++) {
+                    float4 (&acur)[8] = accA;
+                    float4 (&anx)[8] = accB;
                     const int s = q / CHW, c0 = cbase + (q % CHW) * 32;
                     if ((q % CHW) == 0) {
                         mbar_wait(X_FULL(s), par);
@@ -463,12 +468,11 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                         }
                     }
                     __syncwarp();
+                    if (has_acc) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) accA[j] = accB[j];
+                    }
                     if ((q % CHW) == CHW - 1 && threadIdx.x == 0) RB_DBG(36 + s);
-                };
-#pragma unroll 1
-                for (int q = 0; q < NCHW; q += 2) {
-                    out_piece(q, accA, accB);
-                    out_piece(q + 1, accB, accA);
                 }
                 }
                 if (threadIdx.x == 0) RB_DBG(6 + 4 * i);
