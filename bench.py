@@ -171,8 +171,13 @@ def main_b200(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE JSON line: until it is printed, file descriptor 1 points at stderr, so that anything a native library
+    # writes there (NCCL prints its version banner to stdout whatever NCCL_DEBUG_FILE says) cannot land next to it
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner must not land on stdout next to the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     F = args.frames
     first, S = sharding.shard_range(args.sessions * world, world, rank)      # weak scaling: a fixed block of sessions per GPU
@@ -299,7 +304,10 @@ def main_b200(args, rank, local_rank, world):
                                "device_ms": round(s["device_ms"], 3)} for s in allstats],
             "hbm_bytes_ctx": tail.device_bytes,
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     tail.close()
     if world > 1:
         dist.destroy_process_group()
