@@ -285,47 +285,65 @@ int launch_normalise(const float *mel, const float *mean, const float *scale, fl
 // warp 0 = the 32 mel channels (Cin 80), warps 1..5 = the 160 audio channels (Cin 256).
 // mel_view[ci][t] = mel_window_flat[ci*12 + t]; audio_view[ci][t] = audio[ci*12 + t]  (raw .view, not a transpose)
 // ---------------------------------------------------------------------------------------------------
+// NW windows per trip: every weight is fetched once per NW windows (the 491 KB of conv_pre_a weights do not fit L1, so at one
+// window per trip the kernel was bound by re-reading them from L2: 2 GB per call at 4,096 windows)
+template <int NW>
 __global__ void __launch_bounds__(192) k_chunker_pre(const float *__restrict__ mel, const float *__restrict__ audio,
                                                     const float *__restrict__ wm, const float *__restrict__ bm,
                                                     const float *__restrict__ wa, const float *__restrict__ ba,
                                                     float *__restrict__ z0, __nv_bfloat16 *__restrict__ z0b, int W) {
-    __shared__ __align__(16) float sm[80 * 12];
-    __shared__ __align__(16) float sa[256 * 12];
+    extern __shared__ __align__(16) float smem_f[];
+    float *sm = smem_f;                       // [NW][80 * 12]
+    float *sa = smem_f + NW * 960;            // [NW][256 * 12]
     const int tid = threadIdx.x;
-    for (int w = blockIdx.x; w < W; w += gridDim.x) {
-        for (int e = tid; e < 960; e += 192) sm[e] = mel[(long long)w * 960 + e];
-        for (int e = tid; e < 3072; e += 192) sa[e] = audio[(long long)w * 3072 + e];
+    const int ngroups = (W + NW - 1) / NW;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int w0 = g * NW;
+        for (int e = tid; e < NW * 960; e += 192) { const int q = e / 960; sm[e] = (w0 + q < W) ? mel[(long long)w0 * 960 + e] : 0.0f; }
+        for (int e = tid; e < NW * 3072; e += 192) { const int q = e / 3072; sa[e] = (w0 + q < W) ? audio[(long long)w0 * 3072 + e] : 0.0f; }
         __syncthreads();
-        float acc[12];
+        float acc[NW][12];
         const bool is_mel = tid < 32;
         const int co = is_mel ? tid : tid - 32;
         const int Cin = is_mel ? 80 : 256, Cout = is_mel ? 32 : 160;
         const float *src = is_mel ? sm : sa;
+        const int wstride = is_mel ? 960 : 3072;
         const float *wt = is_mel ? wm : wa;
         const float b = is_mel ? bm[co] : ba[co];
 #pragma unroll
-        for (int t = 0; t < 12; t++) acc[t] = b;
+        for (int q = 0; q < NW; q++)
+#pragma unroll
+            for (int t = 0; t < 12; t++) acc[q][t] = b;
         for (int ci = 0; ci < Cin; ci++) {
-            const float4 x0 = *reinterpret_cast<const float4 *>(src + ci * 12);
-            const float4 x1 = *reinterpret_cast<const float4 *>(src + ci * 12 + 4);
-            const float4 x2 = *reinterpret_cast<const float4 *>(src + ci * 12 + 8);
-            const float x[14] = {0.f, x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, 0.f};
+            float wv[3];
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const float wv = __ldg(wt + ((long long)k * Cin + ci) * Cout + co);
+            for (int k = 0; k < 3; k++) wv[k] = __ldg(wt + ((long long)k * Cin + ci) * Cout + co);
 #pragma unroll
-                for (int t = 0; t < 12; t++) acc[t] = fmaf(wv, x[t + k], acc[t]);
+            for (int q = 0; q < NW; q++) {
+                const float *row = src + q * wstride + ci * 12;
+                const float4 x0 = *reinterpret_cast<const float4 *>(row);
+                const float4 x1 = *reinterpret_cast<const float4 *>(row + 4);
+                const float4 x2 = *reinterpret_cast<const float4 *>(row + 8);
+                const float x[14] = {0.f, x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, 0.f};
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+#pragma unroll
+                    for (int t = 0; t < 12; t++) acc[q][t] = fmaf(wv[k], x[t + k], acc[q][t]);
             }
         }
-        if (z0) {
-            float *o = z0 + (long long)w * 12 * 192 + tid;
 #pragma unroll
-            for (int t = 0; t < 12; t++) o[t * 192] = acc[t];
-        }
-        if (z0b) {
-            __nv_bfloat16 *o = z0b + (long long)w * 12 * 192 + tid;
+        for (int q = 0; q < NW; q++) {
+            if (w0 + q >= W) break;
+            if (z0) {
+                float *o = z0 + (long long)(w0 + q) * 12 * 192 + tid;
 #pragma unroll
-            for (int t = 0; t < 12; t++) o[t * 192] = __float2bfloat16_rn(lrelu(acc[t], 0.01f));
+                for (int t = 0; t < 12; t++) o[t * 192] = acc[q][t];
+            }
+            if (z0b) {
+                __nv_bfloat16 *o = z0b + (long long)(w0 + q) * 12 * 192 + tid;
+#pragma unroll
+                for (int t = 0; t < 12; t++) o[t * 192] = __float2bfloat16_rn(lrelu(acc[q][t], 0.01f));
+            }
         }
         __syncthreads();
     }
@@ -334,8 +352,18 @@ __global__ void __launch_bounds__(192) k_chunker_pre(const float *__restrict__ m
 int launch_chunker_pre(const float *mel, const float *audio, const float *wm, const float *bm, const float *wa, const float *ba,
                        float *z0, __nv_bfloat16 *z0b, int W, cudaStream_t st) {
     if (W <= 0) return 0;
-    int cap = sm_count() * 8;
-    k_chunker_pre<<<W < cap ? W : cap, 192, 0, st>>>(mel, audio, wm, bm, wa, ba, z0, z0b, W);
+    constexpr int NW = 4;
+    static bool attr_set[64] = {};
+    const size_t smem = (size_t)NW * (960 + 3072) * sizeof(float);
+    int dev = 0;
+    B2_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        B2_CUDA_OK(cudaFuncSetAttribute(k_chunker_pre<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev] = true;
+    }
+    const int groups = (W + NW - 1) / NW;
+    const int cap = sm_count() * 3;
+    k_chunker_pre<NW><<<groups < cap ? groups : cap, 192, smem, st>>>(mel, audio, wm, bm, wa, ba, z0, z0b, W);
     B2_LAUNCH_OK("k_chunker_pre");
     return 0;
 }
