@@ -20,7 +20,7 @@
  *   - 16k->8k resample          torchaudio/functional/functional.py:1416-1428 applied at
  *                               /root/reference/HelloSippyTTSRT/HelloSippyRTPipe.py:240:
  *                               y[j] = sum_i h[i] * xpad[2j+i], xpad = 13 zeros | x | 15 zeros, per call.
- *                               Here the sum is a defined fmaf chain over taps i = 0..27 ascending so the CUDA
+ *                               Here the sum is a defined pair of fmaf chains (o_down_dot below) so the CUDA
  *                               kernel can be bit-exact against it; torch's own summation order differs, and
  *                               tests bound that difference (|dPCM| <= 1).
  *   - 8k->16k resample          same module, orig 1 / new 2: 2 phases x 15 taps, pad (7, 8), stride 1,
@@ -119,6 +119,21 @@ void o_decode_f32(const uint8_t *in, size_t n, int law, float *out)
     for (size_t i = 0; i < n; i++) out[i] = o_pcm16_to_float(law ? o_alaw_dec(in[i]) : o_ulaw_dec(in[i]));
 }
 
+/* One output of the 16k->8k filter.  torchaudio's taps 0 and 27 are -0 by construction (the Hann window's zero) and are
+ * skipped; the sum is DEFINED as two ascending fmaf chains from +0 -- e over the odd taps 1,3,..,25 and o over the even taps
+ * 2,4,..,26 -- and one rounded add y = e + o.  (This is the order a packed two-lane fused multiply-add per tap pair produces;
+ * the CUDA kernels are bit-exact against it.) */
+static float o_down_dot(const float *xr, size_t L, size_t j, const float *h)
+{
+    float e = 0.0f, o = 0.0f;
+    for (int i = 1; i < 27; i++) {
+        long p = (long)(2 * j) + i - 13;
+        float v = (p >= 0 && p < (long)L) ? xr[p] : 0.0f;
+        if (i & 1) e = fmaf(h[i], v, e); else o = fmaf(h[i], v, o);
+    }
+    return e + o;
+}
+
 /* ---- 16k -> 8k: 28 taps, stride 2, zero pad (13, 15) per row ------------------------------
  * h: the 28 fp32 taps of torchaudio.transforms.Resample(16000, 8000).kernel (passed in; the tests
  * pass the values frozen in tests/golden/resample_taps.npz).  Rows are independent (per session
@@ -130,13 +145,7 @@ void o_resample_2to1(const float *x, size_t rows, size_t L, const float *h, floa
         const float *xr = x + r * L;
         float *yr = y + r * Lo;
         for (size_t j = 0; j < Lo; j++) {
-            float acc = 0.0f;
-            for (int i = 0; i < 28; i++) {
-                long p = (long)(2 * j) + i - 13;
-                float v = (p >= 0 && p < (long)L) ? xr[p] : 0.0f;
-                acc = fmaf(h[i], v, acc);
-            }
-            yr[j] = acc;
+            yr[j] = o_down_dot(xr, L, j, h);
         }
     }
 }
@@ -148,13 +157,7 @@ void o_resample_2to1_encode(const float *x, size_t rows, size_t L, const float *
     for (size_t r = 0; r < rows; r++) {
         const float *xr = x + r * L;
         for (size_t j = 0; j < Lo; j++) {
-            float acc = 0.0f;
-            for (int i = 0; i < 28; i++) {
-                long p = (long)(2 * j) + i - 13;
-                float v = (p >= 0 && p < (long)L) ? xr[p] : 0.0f;
-                acc = fmaf(h[i], v, acc);
-            }
-            int16_t s = o_float_to_pcm16(acc);
+            int16_t s = o_float_to_pcm16(o_down_dot(xr, L, j, h));
             out[r * Lo + j] = law ? o_alaw_enc(s) : o_ulaw_enc(s);
         }
     }

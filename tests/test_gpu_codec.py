@@ -77,7 +77,9 @@ def test_float_to_pcm_bit_exact(eng, oc):
 
 
 @pytest.mark.parametrize("law", [0, 1])
-@pytest.mark.parametrize("rows,L", [(3, 8192), (5, 2048), (2, 512), (1, 16), (7, 320), (3, 1600), (2, 333), (1, 1), (4, 4096 + 16)])
+@pytest.mark.parametrize("rows,L", [(3, 8192), (5, 2048), (2, 512), (1, 16), (7, 320), (3, 1600), (2, 333), (1, 1), (4, 4096 + 16),
+                                     # row ends on every lane of the flat kernel, one-chunk rows, and several grid-stride trips
+                                     (70, 16), (40, 48), (33, 16 * 31), (300, 32), (9, 16 * 33), (3000, 1600), (40, 8192 * 2)])
 def test_fused_resample_encode_bit_exact_vs_oracle(eng, oc, taps, law, rows, L):
     x = synth.synth_audio(rows, L, seed=L + rows)
     ref_u8 = oc.resample_2to1_encode(x.numpy(), taps["down"], law)
