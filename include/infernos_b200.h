@@ -59,6 +59,11 @@ B2_API size_t b2_ctx_device_bytes(const b2_ctx *ctx);
  * replacing SpeechT5HifiGan.from_pretrained / AmendmentNetwork1.from_pretrained (HelloSippyRTPipe.py:171-179). */
 B2_API int b2_load_vocoder_tensor(b2_ctx *ctx, const char *key, const float *h_data, const int64_t *shape, int ndim);
 B2_API int b2_load_chunker_tensor(b2_ctx *ctx, const char *key, const float *h_data, const int64_t *shape, int ndim);
+/* optional: the `layers.*` keys of transformers SpeechT5SpeechDecoderPostnet (layers.{0..4}.conv.weight and
+ * layers.{0..4}.batch_norm.{weight,bias,running_mean,running_var}; modeling_speecht5.py:700-750), i.e. the weights behind
+ * self.model.speech_decoder_postnet.postnet (HelloSippyRTPipe.py:230).  Other keys (feat_out, prob_out, num_batches_tracked)
+ * are not used by this library and must not be passed. */
+B2_API int b2_load_postnet_tensor(b2_ctx *ctx, const char *key, const float *h_data, const int64_t *shape, int ndim);
 /* packs the loaded weights for the kernels; must be called once after all tensors are loaded */
 B2_API int b2_weights_finalize(b2_ctx *ctx);
 /* 28 taps of torchaudio Resample(16000,8000).kernel and 2x15 taps of Resample(8000,16000).kernel; the library
@@ -85,6 +90,18 @@ B2_API int b2_tts_tail(b2_ctx *ctx, const int32_t *d_slots, const float *d_mel, 
  * stream synchronise before returning.  This is the end-to-end entry the e2e benchmark times. */
 B2_API int b2_tts_tail_host(b2_ctx *ctx, const int32_t *h_slots, const float *h_mel, int B, int nframes, int law,
                      uint8_t *h_g711, float *h_audio, void *stream);
+/* The step before the path: self.model.speech_decoder_postnet.postnet(spectrogram), HelloSippyRTPipe.py:230 =
+ * transformers SpeechT5SpeechDecoderPostnet.postnet (modeling_speecht5.py:758-762): out = x + BNConv5(tanh(BNConv4(...tanh(BNConv1(x))))),
+ * eval-mode batch norm, k5 "same" convolutions zero-padded per (session, call).  d_in, d_out (B, T, 80) fp32, not aliased.
+ * B2_MODE_FP32: CUDA-core fp32; B2_MODE_BF16: tcgen05 convolutions with bf16 operands, fp32 accumulate, fp32 tanh. */
+B2_API int b2_postnet_forward(b2_ctx *ctx, const float *d_in, int B, int T, float *d_out, void *stream);
+/* b2_tts_tail with flags: B2_TAIL_APPLY_POSTNET = d_mel holds the PRE-post-net frames (the feat_out outputs,
+ * HelloSippyRTPipe.py:213-216) and the post-net runs on the GPU inside the same call. */
+#define B2_TAIL_APPLY_POSTNET 1
+B2_API int b2_tts_tail2(b2_ctx *ctx, const int32_t *d_slots, const float *d_mel, int B, int nframes, int law, int flags,
+                 uint8_t *d_g711, float *d_audio, void *stream);
+B2_API int b2_tts_tail_host2(b2_ctx *ctx, const int32_t *h_slots, const float *h_mel, int B, int nframes, int law, int flags,
+                      uint8_t *h_g711, float *h_audio, void *stream);
 /* zero the pre_frames of the given slots (HelloSippyPipeState.__init__, HelloSippyRTPipe.py:77); h_slots host */
 B2_API int b2_session_reset(b2_ctx *ctx, const int32_t *h_slots, int n, void *stream);
 /* read / write one session's pre_frames (4x80 fp32, host) — used to migrate or checkpoint a session */

@@ -18,7 +18,9 @@ What differs, by design:
     takes any number of independently started batch states ("cohorts", each with its own front-half state and step counter)
     and runs ONE tail call over the union of their live sessions, so requests admitted while others are mid-sentence share
     the GPU pass.  InfernTTSWorker(continuous=True) drives it.
-  * the autoregressive front half (SpeechT5 encoder/decoder/postnet, :111-118, :195-230) is out of this project's
+  * the decoder post-net (:230) runs on the GPU inside the same tail call when its weights are given
+    (`postnet_state_dict`, or automatically when the engine loads a SpeechT5 model itself); `frontend.postnet` is then not called.
+  * the autoregressive front half (SpeechT5 encoder/decoder, :111-118, :195-229) is out of this project's
     scope: it is reached through a small `frontend` object.  SpeechT5Frontend wraps a transformers model and
     issues the same calls the reference does; tests and benchmarks script it.
 """
@@ -225,6 +227,8 @@ class HelloSippyRTPipe:
           frontend            object with tokenize/start/length_bounds/step/postnet (default: SpeechT5Frontend on `model`)
           vocoder_state_dict  SpeechT5HifiGan weights (default: `microsoft/speecht5_hifigan` via transformers, needs the hub)
           chunker_state_dict  AmendmentNetwork1 weights (default: synthetic when vocoder weights are synthetic)
+          postnet_state_dict  SpeechT5SpeechDecoderPostnet weights (`layers.*`): the post-net (:230) then runs inside the tail call
+                              on the GPU instead of through frontend.postnet (default: taken from `model` when the engine loads it)
           mode                'bf16' (tensor cores, default — the reference runs bf16, :57) or 'fp32'
           law                 'ulaw' (default) or 'alaw' for state.g711
           max_sessions        size of the pre_frames slot pool; max_windows: workspace in 12-frame windows
@@ -242,6 +246,7 @@ class HelloSippyRTPipe:
         frontend = kwa.pop("frontend", None)
         voc_sd = kwa.pop("vocoder_state_dict", None)
         chk_sd = kwa.pop("chunker_state_dict", None)
+        pn_sd = kwa.pop("postnet_state_dict", None)
         mode = kwa.pop("mode", "bf16")
         self.law = {"ulaw": LAW_ULAW, "alaw": LAW_ALAW}[kwa.pop("law", "ulaw")]
         max_sessions = kwa.pop("max_sessions", 64)
@@ -250,13 +255,16 @@ class HelloSippyRTPipe:
         self.speaker_embeddings = kwa.pop("speaker_embeddings", None) or [torch.zeros(1, 512)]
         if frontend is None:
             frontend = self._load_speecht5(model, get_processor, kwa)
+            if pn_sd is None:
+                pn_sd = frontend.model.speech_decoder_postnet.state_dict()
         self.frontend = frontend
         self.reduction_factor = frontend.reduction_factor
         if voc_sd is None:
             voc_sd = self._load_hub_vocoder()
         if chk_sd is None:
             raise RuntimeError("chunker_state_dict is required (sobomax/speecht5-rt.post_vocoder.v2 cannot be fetched offline)")
-        self.tail = TTSTail(self.device, voc_sd, chk_sd, mode=mode, max_sessions=max_sessions, max_windows=max_windows)
+        self.tail = TTSTail(self.device, voc_sd, chk_sd, mode=mode, max_sessions=max_sessions, max_windows=max_windows, postnet_sd=pn_sd)
+        self.gpu_postnet = pn_sd is not None
         self.device = self.tail.device
         # the reference's three plug points (:236, :237, :240)
         self.vocoder = self.tail.vocoder
@@ -294,7 +302,8 @@ class HelloSippyRTPipe:
 
     # ---- the engine ----------------------------------------------------------------------------------------
     def _front_half(self, state: HelloSippyPipeStateBatched) -> torch.Tensor:
-        """Reference :195-230 for one batch state: 16 decoder steps (32 frames), stop bookkeeping, postnet.  -> mel (B, 32, 80)."""
+        """Reference :195-230 for one batch state: 16 decoder steps (32 frames), stop bookkeeping, postnet.  -> mel (B, 32, 80);
+        with gpu_postnet the frames are returned as feat_out produced them and the post-net is left to the tail call."""
         frames = []
         nframes = 0
         eframes = self.pre_nframes + self.post_nframes
@@ -306,16 +315,18 @@ class HelloSippyRTPipe:
             fire = (state.ends_at < 0) & (state.minlen <= state.idx) & (stop | (state.maxlen <= state.idx))
             state.ends_at = torch.where(fire, state.idx + eframes // self.reduction_factor, state.ends_at)
             state.idx += 1
-        spectrogram = self.frontend.postnet(torch.cat(frames, dim=1))
+        spectrogram = torch.cat(frames, dim=1)
+        if not self.gpu_postnet:
+            spectrogram = self.frontend.postnet(spectrogram)
         return spectrogram.to(device=self.device, dtype=torch.float32).contiguous()
 
     def infer(self, state: HelloSippyPipeStateBatched) -> None:
         with self.cuda_lock:
             mel = self._front_half(state)
             if self.fused:
-                state.g711, state.audio = self.tail.tail(state.slots, mel, law=self.law)
+                state.g711, state.audio = self.tail.tail(state.slots, mel, law=self.law, apply_postnet=self.gpu_postnet)
             else:
-                self._infer_three_callables(state, mel)
+                self._infer_three_callables(state, self.tail.postnet(mel) if self.gpu_postnet else mel)
 
     def infer_many(self, states: List[HelloSippyPipeStateBatched]) -> None:
         """Continuous batching: every state advances by one call (its own front half, its own step counter), and the tail runs
@@ -339,7 +350,7 @@ class HelloSippyRTPipe:
                     slots.append(st.slots.index_select(0, idx))
             if not mels:
                 return
-            g711, audio = self.tail.tail(torch.cat(slots), torch.cat(mels), law=self.law)
+            g711, audio = self.tail.tail(torch.cat(slots), torch.cat(mels), law=self.law, apply_postnet=self.gpu_postnet)
             row = 0
             for st, live, B, nfr in parts:
                 # rows of sessions that already ended stay zero: unbatch_and_dispatch never reads them

@@ -14,6 +14,7 @@ SO_PATH = os.path.join(HERE, "libinfernos_b200.so")
 
 MODE_FP32, MODE_BF16 = 0, 1
 LAW_ULAW, LAW_ALAW, LAW_NONE = 0, 1, -1
+TAIL_APPLY_POSTNET = 1
 
 # name -> (restype, argtypes); must list every symbol of include/infernos_b200.h (tests check that)
 SIGNATURES = {
@@ -25,6 +26,7 @@ SIGNATURES = {
     "b2_ctx_device_bytes": (c_size_t, [c_void_p]),
     "b2_load_vocoder_tensor": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int]),
     "b2_load_chunker_tensor": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int]),
+    "b2_load_postnet_tensor": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int]),
     "b2_weights_finalize": (c_int, [c_void_p]),
     "b2_set_resample_taps": (c_int, [c_void_p, c_void_p]),
     "b2_vocoder_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
@@ -32,6 +34,9 @@ SIGNATURES = {
     "b2_resample_2to1": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "b2_tts_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2_tts_tail_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b2_postnet_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b2_tts_tail2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b2_tts_tail_host2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2_session_reset": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "b2_session_get_pre_frames": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "b2_session_set_pre_frames": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),

@@ -405,4 +405,77 @@ int launch_trim(const float *audio, float *out, int W, int Lin, int lo, int Lout
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// post-net element-wise steps (see conv_simt.cuh).  All HBM-bound, 128-bit accesses, grid-stride.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pn_prep(const float *__restrict__ mel, __nv_bfloat16 *__restrict__ outb, size_t rows) {
+    // one thread = 8 output bins (one 16-byte store); 16 threads per row
+    const size_t total = rows * 16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i >> 4;
+        const int q = (int)(i & 15);
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (q < 10) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(mel + r * 80 + q * 8));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(mel + r * 80 + q * 8 + 4));
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+            o = make_uint4(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1), *reinterpret_cast<uint32_t *>(&h2), *reinterpret_cast<uint32_t *>(&h3));
+        }
+        reinterpret_cast<uint4 *>(outb)[i] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pn_tanh(const float *__restrict__ in, float *__restrict__ out32, __nv_bfloat16 *__restrict__ outb, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4 *>(in)[i];
+        v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
+        if (out32) reinterpret_cast<float4 *>(out32)[i] = v;
+        if (outb) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+            reinterpret_cast<uint2 *>(outb)[i] = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pn_out(const float *__restrict__ mel, const float *__restrict__ y, int ystride, float *__restrict__ out, size_t rows) {
+    const size_t total = rows * 20;                 // 20 float4 per row of 80 bins
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / 20;
+        const int q = (int)(i - r * 20);
+        const float4 m = __ldg(reinterpret_cast<const float4 *>(mel) + i);
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(y + r * ystride) + q);
+        reinterpret_cast<float4 *>(out)[i] = make_float4(m.x + v.x, m.y + v.y, m.z + v.z, m.w + v.w);
+    }
+}
+
+static inline int ew_grid(size_t items) {
+    long long b = (long long)((items + 255) / 256);
+    const long long cap = (long long)sm_count() * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int launch_pn_prep(const float *mel, __nv_bfloat16 *outb, size_t rows, cudaStream_t st) {
+    if (!rows) return 0;
+    k_pn_prep<<<ew_grid(rows * 16), 256, 0, st>>>(mel, outb, rows);
+    B2_LAUNCH_OK("k_pn_prep");
+    return 0;
+}
+
+int launch_pn_tanh(const float *in, float *out32, __nv_bfloat16 *outb, size_t n, cudaStream_t st) {
+    if (!n) return 0;
+    if (n % 4) return set_error("pn_tanh: element count must be a multiple of 4");
+    k_pn_tanh<<<ew_grid(n / 4), 256, 0, st>>>(in, out32, outb, n / 4);
+    B2_LAUNCH_OK("k_pn_tanh");
+    return 0;
+}
+
+int launch_pn_out(const float *mel, const float *y, int ystride, float *out, size_t rows, cudaStream_t st) {
+    if (!rows) return 0;
+    if (ystride % 4) return set_error("pn_out: row stride must be a multiple of 4");
+    k_pn_out<<<ew_grid(rows * 20), 256, 0, st>>>(mel, y, ystride, out, rows);
+    B2_LAUNCH_OK("k_pn_out");
+    return 0;
+}
+
 }  // namespace b2

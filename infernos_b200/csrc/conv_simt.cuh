@@ -51,4 +51,14 @@ int launch_chunker_final(const float *audio, const float *post, float *out, int 
 // vocoder-only trim for calls that bypass the chunker: out[w][i] = audio[w][512+i]
 int launch_trim(const float *audio, float *out, int W, int Lin, int lo, int Lout, cudaStream_t st);
 
+// SpeechT5 decoder post-net helpers (transformers modeling_speecht5.py:700-762; call site HelloSippyRTPipe.py:230).  The five
+// Conv1d(k5, "same") + BatchNorm1d(eval) layers run through the conv kernels above with the batch norm folded into weight and
+// bias; these are the element-wise steps between them.
+//   prep : mel fp32 [rows][80] -> bf16 [rows][128], bins 80..127 zero (tensor-core operand of the first layer)
+//   tanh : v = tanh(in[i]) -> out32[i] (may alias in) and/or outb[i] (bf16 operand of the next layer)
+//   out  : out[r][b] = mel[r][b] + y[r*ystride + b], b < 80   (the post-net is residual: :762)
+int launch_pn_prep(const float *mel, __nv_bfloat16 *outb, size_t rows, cudaStream_t st);
+int launch_pn_tanh(const float *in, float *out32, __nv_bfloat16 *outb, size_t n, cudaStream_t st);
+int launch_pn_out(const float *mel, const float *y, int ystride, float *out, size_t rows, cudaStream_t st);
+
 }  // namespace b2

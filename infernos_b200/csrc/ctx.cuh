@@ -44,6 +44,9 @@ struct Workspace {
     __nv_bfloat16 *win_norm_b = nullptr;               // [F][128] bf16, bins 80..127 zero (BF16 mode)
     __nv_bfloat16 *z0b = nullptr, *z1b = nullptr, *z2b = nullptr, *zyb = nullptr;   // chunker operands (BF16 mode)
     float *audio16k = nullptr;                         // [W][2048]
+    // post-net, sized for 12 frames per window like the rest: conv output, ping-pong operands, the post-net's mel
+    float *pn_a32 = nullptr, *pn_f0 = nullptr, *pn_f1 = nullptr, *pn_mel = nullptr;    // [F][256] x3, [F][80]
+    __nv_bfloat16 *pn_inb = nullptr, *pn_b0 = nullptr, *pn_b1 = nullptr;               // [F][128], [F][256] x2
     int32_t *slots = nullptr;                          // device copy for the host entry point
     float *mel_in = nullptr;                           // device staging for the host entry point
     uint8_t *g711_out = nullptr;
@@ -71,7 +74,7 @@ struct Prof {
 struct b2_ctx {
     int device = 0, mode = 0, max_sessions = 0, max_windows = 0;
     bool finalized = false;
-    std::map<std::string, b2::HostTensor> voc_raw, chk_raw;
+    std::map<std::string, b2::HostTensor> voc_raw, chk_raw, pn_raw;
     std::vector<void *> allocs;
     size_t device_bytes = 0;
     std::string err;
@@ -84,6 +87,10 @@ struct b2_ctx {
     // chunker
     float *cwm = nullptr, *cbm = nullptr, *cwa = nullptr, *cba = nullptr;
     b2::Layer c_up[2], c_res1, c_res2, c_post;
+
+    // SpeechT5 decoder post-net (optional): five k5 convs, batch norm folded in
+    bool has_postnet = false;
+    b2::Layer pn[5];
 
     float *pre_pool = nullptr;                         // [max_sessions][4][80]
     b2::Workspace ws;

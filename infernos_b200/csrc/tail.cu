@@ -227,6 +227,40 @@ static int finalize(b2_ctx *c) {
         if (!(w = find(c->chk_raw, "post_conv.weight", {256, 64, 8})) || !(b = find(c->chk_raw, "post_conv.bias", {256}))) return 1;
         if (pack_conv(c, c->c_post, *w, *b, 1, 0, 24, false)) return 1;
     }
+    // SpeechT5 decoder post-net (optional): Conv1d(k5, pad 2, no bias) -> BatchNorm1d(eval) [-> tanh], x5
+    // (modeling_speecht5.py:700-737).  y = (conv(x) - mean) / sqrt(var + eps) * gamma + beta is folded into the conv:
+    // w' = w * s, b' = beta - mean * s with s = gamma / sqrt(var + 1e-5).  On the tensor-core path the 80-bin ends are
+    // padded to 128 (zero weights) like conv_pre.
+    if (!c->pn_raw.empty()) {
+        for (int i = 0; i < 5; i++) {
+            const int cin = i == 0 ? 80 : 256, cout = i == 4 ? 80 : 256;
+            const HostTensor *g, *be, *mu, *var;
+            snprintf(k1, sizeof k1, "layers.%d.conv.weight", i);
+            if (!(w = find(c->pn_raw, k1, {cout, cin, 5}))) return 1;
+            snprintf(k1, sizeof k1, "layers.%d.batch_norm.weight", i);
+            if (!(g = find(c->pn_raw, k1, {cout}))) return 1;
+            snprintf(k1, sizeof k1, "layers.%d.batch_norm.bias", i);
+            if (!(be = find(c->pn_raw, k1, {cout}))) return 1;
+            snprintf(k1, sizeof k1, "layers.%d.batch_norm.running_mean", i);
+            if (!(mu = find(c->pn_raw, k1, {cout}))) return 1;
+            snprintf(k1, sizeof k1, "layers.%d.batch_norm.running_var", i);
+            if (!(var = find(c->pn_raw, k1, {cout}))) return 1;
+            const int cin_p = (bf && cin == 80) ? 128 : cin, cout_p = (bf && cout == 80) ? 128 : cout;
+            HostTensor wf, bfold;
+            wf.shape = {cout_p, cin_p, 5};
+            wf.data.assign((size_t)cout_p * cin_p * 5, 0.0f);
+            bfold.shape = {cout_p};
+            bfold.data.assign((size_t)cout_p, 0.0f);
+            for (int co = 0; co < cout; co++) {
+                const float sc = g->data[co] / sqrtf(var->data[co] + 1e-5f);
+                bfold.data[co] = be->data[co] - mu->data[co] * sc;
+                for (int ci = 0; ci < cin; ci++)
+                    for (int j = 0; j < 5; j++) wf.data[((size_t)co * cin_p + ci) * 5 + j] = w->data[((size_t)co * cin + ci) * 5 + j] * sc;
+            }
+            if (pack_conv(c, c->pn[i], wf, bfold, 1, 2, 1, bf)) return 1;
+        }
+        c->has_postnet = true;
+    }
     // workspaces
     Workspace &ws = c->ws;
     const size_t F = (size_t)c->max_windows * 12, Wn = (size_t)c->max_windows;
@@ -247,10 +281,16 @@ static int finalize(b2_ctx *c) {
             dev_alloc(c, &ws.zy, Wn * 192 * 64) || dev_alloc(c, &ws.z3, Wn * 192 * 64) || dev_alloc(c, &ws.post, Wn * 2048)) return 1;
     }
     if (dev_alloc(c, &ws.audio16k, Wn * 2048)) return 1;
+    if (c->has_postnet) {
+        if (dev_alloc(c, &ws.pn_a32, F * 256) || dev_alloc(c, &ws.pn_mel, F * 80)) return 1;
+        if (bf) { if (dev_alloc(c, &ws.pn_inb, F * 128) || dev_alloc(c, &ws.pn_b0, F * 256) || dev_alloc(c, &ws.pn_b1, F * 256)) return 1; }
+        else { if (dev_alloc(c, &ws.pn_f0, F * 256) || dev_alloc(c, &ws.pn_f1, F * 256)) return 1; }
+    }
     if (dev_alloc(c, &c->pre_pool, (size_t)c->max_sessions * 320)) return 1;
     B2_CUDA_OK(cudaMemset(c->pre_pool, 0, (size_t)c->max_sessions * 320 * sizeof(float)));
     c->voc_raw.clear();
     c->chk_raw.clear();
+    c->pn_raw.clear();
     c->finalized = true;
     return 0;
 }
@@ -432,7 +472,41 @@ static int chunker_fwd(b2_ctx *c, const float *win_raw, const float *audio, int 
     return 0;
 }
 
-static int tail_device(b2_ctx *c, const int32_t *d_slots, const float *d_mel, int B, int nframes, int law,
+// speech_decoder_postnet.postnet (modeling_speecht5.py:758-762; HelloSippyRTPipe.py:230): (B, T, 80) -> (B, T, 80), every
+// (session, call) zero-padded on its own like the reference's conv over a (B, 80, T) tensor.  B*T <= 12*max_windows.
+static int postnet_fwd(b2_ctx *c, const float *d_in, int B, int T, float *d_out, cudaStream_t st) {
+    Workspace &ws = c->ws;
+    const size_t rows = (size_t)B * T;
+    if (c->mode == B2_MODE_BF16) {
+        PROF(PC_OTHER, launch_pn_prep(d_in, ws.pn_inb, rows, st));
+        const __nv_bfloat16 *x = ws.pn_inb;
+        __nv_bfloat16 *pp[2] = {ws.pn_b0, ws.pn_b1};
+        for (int i = 0; i < 5; i++) {
+            UmmaConvArgs u;
+            u.in = x; u.layer = &c->pn[i]; u.out32 = ws.pn_a32; u.W = B; u.T = T;
+            PROF(PC_CONV_TC, launch_conv_umma(u, st));
+            if (i < 4) {
+                PROF(PC_OTHER, launch_pn_tanh(ws.pn_a32, nullptr, pp[i & 1], rows * 256, st));
+                x = pp[i & 1];
+            }
+        }
+        PROF(PC_OTHER, launch_pn_out(d_in, ws.pn_a32, 128, d_out, rows, st));
+    } else {
+        const float *x = d_in;
+        float *pp[2] = {ws.pn_f0, ws.pn_f1};
+        for (int i = 0; i < 5; i++) {
+            float *o = i < 4 ? pp[i & 1] : ws.pn_a32;
+            ConvArgs a = conv_args(c->pn[i], x, o, B, T, T, 1.0f);
+            PROF(PC_CONV_F32, launch_conv_simt(a, st));
+            if (i < 4) PROF(PC_OTHER, launch_pn_tanh(o, o, nullptr, rows * 256, st));
+            x = o;
+        }
+        PROF(PC_OTHER, launch_pn_out(d_in, ws.pn_a32, 80, d_out, rows, st));
+    }
+    return 0;
+}
+
+static int tail_device(b2_ctx *c, const int32_t *d_slots, const float *d_mel, int B, int nframes, int law, bool apply_postnet,
                        uint8_t *d_g711, float *d_audio, cudaStream_t st) {
     const int nwin = nframes / 8;
     const int sess_per_pass = std::max(1, c->max_windows / nwin);
@@ -441,7 +515,12 @@ static int tail_device(b2_ctx *c, const int32_t *d_slots, const float *d_mel, in
         const int nb = std::min(sess_per_pass, B - b0);
         const int W = nb * nwin;
         Workspace &ws = c->ws;
-        PROF(PC_OTHER, launch_build_windows(d_slots + b0, d_mel + (size_t)b0 * nframes * 80, c->pre_pool, c->mean, c->scale,
+        const float *mel = d_mel + (size_t)b0 * nframes * 80;
+        if (apply_postnet) {
+            if (postnet_fwd(c, mel, nb, nframes, ws.pn_mel, st)) return 1;
+            mel = ws.pn_mel;
+        }
+        PROF(PC_OTHER, launch_build_windows(d_slots + b0, mel, c->pre_pool, c->mean, c->scale,
                                             ws.win_raw, ws.win_norm, ws.win_norm_b, nb, nframes, st));
         if (vocoder_any(c, ws.win_norm, W, 12, ws.audio, st)) return 1;
         if (c->cwm) { if (chunker_fwd(c, ws.win_raw, ws.audio, W, ws.audio16k, st)) return 1; }
@@ -504,6 +583,7 @@ void b2_ctx_destroy(b2_ctx *c) {
     }
     umma_free_layer(c->conv_pre);
     umma_free_layer(c->c_up[0]); umma_free_layer(c->c_up[1]); umma_free_layer(c->c_res1); umma_free_layer(c->c_res2);
+    for (int i = 0; i < 5; i++) umma_free_layer(c->pn[i]);
     delete c;
 }
 
@@ -584,9 +664,40 @@ int b2_chunker_forward(b2_ctx *c, const float *d_mel, const float *d_audio, int 
     return 0;
 }
 
+int b2_load_postnet_tensor(b2_ctx *c, const char *key, const float *h, const int64_t *shape, int ndim) {
+    if (!c) return set_error("null context");
+    if (c->finalized) return set_error("weights are already finalized");
+    return load_tensor(c->pn_raw, key, h, shape, ndim);
+}
+
+int b2_postnet_forward(b2_ctx *c, const float *d_in, int B, int T, float *d_out, void *stream) {
+    CTX_GUARD(c);
+    if (!c->finalized) return set_error("b2_weights_finalize has not been called");
+    if (!c->has_postnet) return set_error("b2_postnet_forward: no post-net weights were loaded into this context");
+    if (B < 0 || T < 1) return set_error("b2_postnet_forward: bad shape B=%d T=%d", B, T);
+    if (B == 0) return 0;
+    if (!d_in || !d_out) return set_error("b2_postnet_forward: null pointer");
+    if (d_in == d_out) return set_error("b2_postnet_forward: in-place operation is not supported");
+    const long long cap = (long long)c->max_windows * 12;
+    if (T > cap) return set_error("b2_postnet_forward: T=%d exceeds the context's workspace (%lld frames)", T, cap);
+    const int b_per_pass = (int)std::max<long long>(1, cap / T);
+    for (int b0 = 0; b0 < B; b0 += b_per_pass) {
+        const int nb = std::min(b_per_pass, B - b0);
+        if (postnet_fwd(c, d_in + (size_t)b0 * T * 80, nb, T, d_out + (size_t)b0 * T * 80, (cudaStream_t)stream)) return 1;
+    }
+    return 0;
+}
+
 int b2_tts_tail(b2_ctx *c, const int32_t *d_slots, const float *d_mel, int B, int nframes, int law,
                 uint8_t *d_g711, float *d_audio, void *stream) {
+    return b2_tts_tail2(c, d_slots, d_mel, B, nframes, law, 0, d_g711, d_audio, stream);
+}
+
+int b2_tts_tail2(b2_ctx *c, const int32_t *d_slots, const float *d_mel, int B, int nframes, int law, int flags,
+                 uint8_t *d_g711, float *d_audio, void *stream) {
     CTX_GUARD(c);
+    if (flags & ~B2_TAIL_APPLY_POSTNET) return set_error("b2_tts_tail2: unknown flags 0x%x", flags);
+    if ((flags & B2_TAIL_APPLY_POSTNET) && !c->has_postnet) return set_error("b2_tts_tail2: B2_TAIL_APPLY_POSTNET without post-net weights in this context");
     if (!c->finalized) return set_error("b2_weights_finalize has not been called");
     if (B < 0 || nframes < 8 || nframes % 8) return set_error("b2_tts_tail: nframes must be a positive multiple of 8 (got %d), B >= 0", nframes);
     if (nframes / 8 > c->max_windows) return set_error("b2_tts_tail: nframes=%d needs more windows than the context's workspace", nframes);
@@ -594,11 +705,16 @@ int b2_tts_tail(b2_ctx *c, const int32_t *d_slots, const float *d_mel, int B, in
     if (!d_slots || !d_mel) return set_error("b2_tts_tail: null input");
     if (d_g711 && law != B2_LAW_ULAW && law != B2_LAW_ALAW) return set_error("b2_tts_tail: bad law %d", law);
     if (!d_g711 && !d_audio) return set_error("b2_tts_tail: no output requested");
-    return tail_device(c, d_slots, d_mel, B, nframes, law, d_g711, d_audio, (cudaStream_t)stream);
+    return tail_device(c, d_slots, d_mel, B, nframes, law, (flags & B2_TAIL_APPLY_POSTNET) != 0, d_g711, d_audio, (cudaStream_t)stream);
 }
 
 int b2_tts_tail_host(b2_ctx *c, const int32_t *h_slots, const float *h_mel, int B, int nframes, int law,
                      uint8_t *h_g711, float *h_audio, void *stream) {
+    return b2_tts_tail_host2(c, h_slots, h_mel, B, nframes, law, 0, h_g711, h_audio, stream);
+}
+
+int b2_tts_tail_host2(b2_ctx *c, const int32_t *h_slots, const float *h_mel, int B, int nframes, int law, int flags,
+                      uint8_t *h_g711, float *h_audio, void *stream) {
     CTX_GUARD(c);
     if (!c->finalized) return set_error("b2_weights_finalize has not been called");
     if (B < 0 || nframes < 8 || nframes % 8) return set_error("b2_tts_tail_host: nframes must be a positive multiple of 8 (got %d)", nframes);
@@ -617,7 +733,7 @@ int b2_tts_tail_host(b2_ctx *c, const int32_t *h_slots, const float *h_mel, int 
     }
     B2_CUDA_OK(cudaMemcpyAsync(ws.slots, h_slots, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     B2_CUDA_OK(cudaMemcpyAsync(ws.mel_in, h_mel, (size_t)B * nframes * 80 * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (b2_tts_tail(c, ws.slots, ws.mel_in, B, nframes, law, h_g711 ? ws.g711_out : nullptr, h_audio ? ws.audio8k_out : nullptr, stream)) return 1;
+    if (b2_tts_tail2(c, ws.slots, ws.mel_in, B, nframes, law, flags, h_g711 ? ws.g711_out : nullptr, h_audio ? ws.audio8k_out : nullptr, stream)) return 1;
     if (h_g711) B2_CUDA_OK(cudaMemcpyAsync(h_g711, ws.g711_out, nout, cudaMemcpyDeviceToHost, st));
     if (h_audio) B2_CUDA_OK(cudaMemcpyAsync(h_audio, ws.audio8k_out, nout * sizeof(float), cudaMemcpyDeviceToHost, st));
     B2_CUDA_OK(cudaStreamSynchronize(st));

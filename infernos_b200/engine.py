@@ -9,7 +9,7 @@ from typing import Dict, Optional, Sequence, Tuple
 import torch
 
 from . import _lib, resample_taps
-from ._lib import LAW_ALAW, LAW_NONE, LAW_ULAW, MODE_BF16, MODE_FP32
+from ._lib import LAW_ALAW, LAW_NONE, LAW_ULAW, MODE_BF16, MODE_FP32, TAIL_APPLY_POSTNET
 
 _MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, MODE_FP32: MODE_FP32, MODE_BF16: MODE_BF16}
 _taps_set = set()
@@ -44,7 +44,10 @@ class TTSTail:
     """One context = packed weights + workspaces + the pre_frames pool of the sessions on one GPU."""
 
     def __init__(self, device, vocoder_sd: Dict[str, torch.Tensor], chunker_sd: Optional[Dict[str, torch.Tensor]] = None,
-                 mode="bf16", max_sessions: int = 1024, max_windows: int = 1024):
+                 mode="bf16", max_sessions: int = 1024, max_windows: int = 1024,
+                 postnet_sd: Optional[Dict[str, torch.Tensor]] = None):
+        """postnet_sd (optional): state_dict of transformers SpeechT5SpeechDecoderPostnet (or of the whole
+        SpeechT5ForTextToSpeech / its `speech_decoder_postnet`): only the `layers.*` conv / batch-norm tensors are taken."""
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -62,12 +65,15 @@ class TTSTail:
             self._load(vocoder_sd, self.lib.b2_load_vocoder_tensor)
             if chunker_sd is not None:
                 self._load(chunker_sd, self.lib.b2_load_chunker_tensor)
+            if postnet_sd is not None:
+                self._load(postnet_layers(postnet_sd), self.lib.b2_load_postnet_tensor)
             _lib.check(self.lib.b2_weights_finalize(self.ctx), "weights_finalize")
             ensure_taps(self.device)
         except Exception:
             self.close()
             raise
         self.has_chunker = chunker_sd is not None
+        self.has_postnet = postnet_sd is not None
 
     def _load(self, sd, fn):
         for k, v in sd.items():
@@ -123,10 +129,25 @@ class TTSTail:
         """torchaudio Resample(16000, 8000): (..., L) -> (..., ceil(L/2))."""
         return resample_2to1(audio)
 
+    def postnet(self, spectrogram: torch.Tensor) -> torch.Tensor:
+        """SpeechT5SpeechDecoderPostnet.postnet (the call at HelloSippyRTPipe.py:230): (B,T,80) -> (B,T,80)."""
+        if not self.has_postnet:
+            raise RuntimeError("this TTSTail was built without post-net weights (postnet_sd)")
+        in_dtype = spectrogram.dtype
+        x = _require_cuda(spectrogram.to(torch.float32), torch.float32, "spectrogram")
+        B, T, nm = x.shape
+        if nm != 80:
+            raise RuntimeError(f"spectrogram must have 80 mel bins, got {nm}")
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_postnet_forward(self.ctx, x.data_ptr(), B, T, out.data_ptr(), _stream_ptr(x.device)), "postnet_forward")
+        return out.to(in_dtype) if in_dtype != torch.float32 else out
+
     # ---- fused tail ----------------------------------------------------------------------------------
     def tail(self, slots: torch.Tensor, mel: torch.Tensor, law: int = LAW_ULAW, want_g711: bool = True,
-             want_audio: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
-        """slots (B,) int32 cuda, mel (B,n,80) fp32 cuda -> (g711 (B,n*128) uint8 | None, audio8k (B,n*128) fp32 | None)."""
+             want_audio: bool = True, apply_postnet: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """slots (B,) int32 cuda, mel (B,n,80) fp32 cuda -> (g711 (B,n*128) uint8 | None, audio8k (B,n*128) fp32 | None).
+        apply_postnet: mel holds the frames BEFORE the post-net (feat_out's output); the post-net runs in the same call."""
         s = _require_cuda(slots, torch.int32, "slots")
         m = _require_cuda(mel, torch.float32, "mel")
         B, n, nm = m.shape
@@ -135,13 +156,14 @@ class TTSTail:
         g = torch.empty(B, n * 128, device=m.device, dtype=torch.uint8) if want_g711 else None
         a = torch.empty(B, n * 128, device=m.device, dtype=torch.float32) if want_audio else None
         with torch.cuda.device(self.index):
-            _lib.check(self.lib.b2_tts_tail(self.ctx, s.data_ptr(), m.data_ptr(), B, n, law if want_g711 else LAW_NONE,
-                                            g.data_ptr() if g is not None else None, a.data_ptr() if a is not None else None,
-                                            _stream_ptr(m.device)), "tts_tail")
+            _lib.check(self.lib.b2_tts_tail2(self.ctx, s.data_ptr(), m.data_ptr(), B, n, law if want_g711 else LAW_NONE,
+                                             TAIL_APPLY_POSTNET if apply_postnet else 0,
+                                             g.data_ptr() if g is not None else None, a.data_ptr() if a is not None else None,
+                                             _stream_ptr(m.device)), "tts_tail")
         return g, a
 
     def tail_host(self, slots: torch.Tensor, mel: torch.Tensor, out_g711: Optional[torch.Tensor], out_audio: Optional[torch.Tensor] = None,
-                  law: int = LAW_ULAW) -> None:
+                  law: int = LAW_ULAW, apply_postnet: bool = False) -> None:
         """End-to-end entry with HOST (ideally pinned) tensors; returns after the outputs are in host memory."""
         if slots.is_cuda or mel.is_cuda:
             raise RuntimeError("tail_host takes host tensors")
@@ -152,7 +174,8 @@ class TTSTail:
         if out_audio is not None:
             assert out_audio.dtype == torch.float32 and out_audio.numel() == B * n * 128 and out_audio.is_contiguous()
         with torch.cuda.device(self.index):
-            _lib.check(self.lib.b2_tts_tail_host(self.ctx, slots.data_ptr(), mel.data_ptr(), B, n, law,
+            _lib.check(self.lib.b2_tts_tail_host2(self.ctx, slots.data_ptr(), mel.data_ptr(), B, n, law,
+                                                 TAIL_APPLY_POSTNET if apply_postnet else 0,
                                                  out_g711.data_ptr() if out_g711 is not None else None,
                                                  out_audio.data_ptr() if out_audio is not None else None,
                                                  _stream_ptr(self.device)), "tts_tail_host")
@@ -185,6 +208,24 @@ class TTSTail:
         assert tuple(f.shape) == (4, 80)
         with torch.cuda.device(self.index):
             _lib.check(self.lib.b2_session_set_pre_frames(self.ctx, int(slot), f.data_ptr(), _stream_ptr(self.device)), "set_pre_frames")
+
+
+def postnet_layers(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Picks the post-net's conv / batch-norm tensors out of a SpeechT5 state_dict, whatever prefix they carry
+    (`layers.0.conv.weight`, `speech_decoder_postnet.layers.0.conv.weight`, ...)."""
+    out = {}
+    for k, v in sd.items():
+        i = k.find("layers.")
+        if i < 0 or k.endswith("num_batches_tracked"):
+            continue
+        if i > 0 and not k[:i].endswith("speech_decoder_postnet.") and k[:i] != "":
+            continue
+        tail = k[i:]
+        if ".conv.weight" in tail or ".batch_norm." in tail:
+            out[tail] = v
+    if len(out) != 25:
+        raise RuntimeError(f"post-net state_dict: expected 25 tensors (5 layers x conv.weight + 4 batch-norm tensors), found {len(out)}")
+    return out
 
 
 # ---- ctx-less codec / resampler calls --------------------------------------------------------------------

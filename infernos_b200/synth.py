@@ -10,6 +10,7 @@ drawn at ~1/sqrt(fan_in) instead, which yields O(1) audio
 State-dict layouts follow the reference modules exactly:
   * HiFiGAN : transformers SpeechT5HifiGan (modeling_speecht5.py:2974-3010)
   * chunker : AmendmentNetwork1 (/root/reference/HelloSippyTTSRT/HelloSippyRT.py:202-217)
+  * post-net: transformers SpeechT5SpeechDecoderPostnet.layers (modeling_speecht5.py:700-750)
 """
 from __future__ import annotations
 
@@ -21,6 +22,7 @@ import torch
 HIFIGAN_SEED = 1234
 CHUNKER_SEED = 4321
 MEL_SEED = 7
+POSTNET_SEED = 2468
 
 UPSAMPLE_INITIAL_CHANNEL = 512
 UPSAMPLE_RATES = (4, 4, 4, 4)
@@ -86,6 +88,24 @@ def chunker_state_dict(seed: int = CHUNKER_SEED) -> Dict[str, torch.Tensor]:
     sd["resblock.conv2.bias"] = _bias(g, 64)
     sd["post_conv.weight"] = _conv_w(g, 256, 64, 8)
     sd["post_conv.bias"] = _bias(g, 256) + 1.0  # gains centred near 1 like a trained seam-smoother
+    return sd
+
+
+def postnet_state_dict(seed: int = POSTNET_SEED) -> Dict[str, torch.Tensor]:
+    """Random weights with the `layers.*` keys of transformers SpeechT5SpeechDecoderPostnet (default SpeechT5Config: 5 layers,
+    256 units, kernel 5; modeling_speecht5.py:700-750), fp32, CPU.  Scaled so that the tanh layers work in their curved range
+    on synth_mel-like inputs (pre-activations ~ N(0, 1)), with non-trivial batch-norm statistics."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for i in range(5):
+        cin = NUM_MELS if i == 0 else 256
+        cout = NUM_MELS if i == 4 else 256
+        gain = 1.0 / 4.5 if i == 0 else 1.6          # layer 0 sees mel ~ N(-4, 2^2); the others see tanh outputs (rms ~0.6)
+        sd[f"layers.{i}.conv.weight"] = _conv_w(g, cout, cin, 5) * gain
+        sd[f"layers.{i}.batch_norm.weight"] = torch.rand(cout, generator=g) * 0.6 + 0.7
+        sd[f"layers.{i}.batch_norm.bias"] = torch.randn(cout, generator=g) * 0.1
+        sd[f"layers.{i}.batch_norm.running_mean"] = torch.randn(cout, generator=g) * 0.2
+        sd[f"layers.{i}.batch_norm.running_var"] = torch.rand(cout, generator=g) * 1.0 + 0.5
     return sd
 
 

@@ -12,6 +12,8 @@ What is frozen, and which reference code produced it:
   resample_taps.npz    torchaudio.transforms.Resample(16000,8000).kernel and (8000,16000).kernel
   hifigan_golden.npz   real transformers SpeechT5HifiGan on the seeded synthetic weights/mel
   chunker_golden.npz   real AmendmentNetwork1 (HelloSippyRT.py:200-237) on seeded weights
+  postnet_golden.npz   real transformers SpeechT5SpeechDecoderPostnet.postnet (modeling_speecht5.py:758-762, the call at
+                       HelloSippyRTPipe.py:230) on seeded weights: one 32-frame call of 3 sessions and a 10-frame one
   infer_golden.npz     the real HelloSippyRTPipe.infer() + unbatch_and_dispatch() (HelloSippyRTPipe.py:191-259)
                        driven end to end in fp32 with a scripted front half (the AR decoder is out of scope,
                        so feat_out/prob_out/postnet are scripted to emit a fixed mel plan), and the real
@@ -106,6 +108,19 @@ def hifigan_and_chunker():
                         weights_sha=np.frombuffer(sha(torch.cat([v.flatten() for v in vsd.values()])).encode(), dtype=np.uint8))
     np.savez_compressed(os.path.join(OUT, "chunker_golden.npz"), mel=mel.numpy(), audio=a.numpy(), out=c.numpy(),
                         weights_sha=np.frombuffer(sha(torch.cat([v.flatten() for v in csd.values()])).encode(), dtype=np.uint8))
+
+
+def postnet():
+    psd = synth.postnet_state_dict()
+    pn = ref_shim.real_postnet(psd)
+    mel = synth.synth_mel(3, 32, seed=21)
+    mel_short = synth.synth_mel(2, 10, seed=22)
+    with torch.no_grad():
+        out, out_short = pn.postnet(mel), pn.postnet(mel_short)
+    np.savez_compressed(os.path.join(OUT, "postnet_golden.npz"), mel=mel.numpy(), out=out.numpy(), mel_short=mel_short.numpy(),
+                        out_short=out_short.numpy(),
+                        weights_sha=np.frombuffer(sha(torch.cat([v.flatten() for v in psd.values()])).encode(), dtype=np.uint8))
+    print("postnet golden: |out - mel| rms", float((out - mel).pow(2).mean().sqrt()), "max", float((out - mel).abs().max()))
 
 
 class _ScriptedFront:
@@ -207,10 +222,15 @@ def infer_e2e(P, G711Codec):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    import sys
+    if "--postnet-only" in sys.argv:          # adds postnet_golden.npz without regenerating the other fixtures
+        postnet()
+        return
     RT, P, G711Codec = ref_shim.load()
     g711(G711Codec)
     taps()
     hifigan_and_chunker()
+    postnet()
     infer_e2e(P, G711Codec)
     print("golden vectors written to", OUT)
 

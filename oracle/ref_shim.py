@@ -70,3 +70,16 @@ def real_chunker(sd):
     m.load_state_dict(sd, strict=True)
     m.eval()
     return m
+
+
+def real_postnet(sd):
+    """The real transformers SpeechT5SpeechDecoderPostnet (default SpeechT5Config) carrying the given `layers.*` tensors;
+    feat_out / prob_out keep their default init (they are not on the post-net path)."""
+    from transformers import SpeechT5Config
+    from transformers.models.speecht5.modeling_speecht5 import SpeechT5SpeechDecoderPostnet
+    m = SpeechT5SpeechDecoderPostnet(SpeechT5Config())
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith(("feat_out", "prob_out")) or k.endswith("num_batches_tracked") for k in missing), missing
+    m.eval()
+    return m

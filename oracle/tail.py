@@ -13,6 +13,8 @@ What it follows (reference file:line):
   * resampler                       torchaudio/functional/functional.py:1340-1402 (kernel), :1416-1428 (apply)
                                     [third-party, torchaudio 2.11.0; requirements.txt:7]
   * unbatch slicing                 /root/reference/HelloSippyTTSRT/HelloSippyRTPipe.py:242-259
+  * decoder post-net                transformers/models/speecht5/modeling_speecht5.py:700-737 (BatchNormConvLayer), :758-762
+                                    (SpeechT5SpeechDecoderPostnet.postnet), called at HelloSippyRTPipe.py:230
 
 Pinned by tests/golden/*.npz, which were produced by the REAL reference modules in the
 build container (oracle/make_golden.py); tests/test_oracle_golden.py checks this file against
@@ -63,6 +65,20 @@ def hifigan_forward(sd: Dict[str, torch.Tensor], mel: torch.Tensor, taps: Option
     h = F.leaky_relu(h)                                                     # :3074 (default slope 0.01)
     h = F.conv1d(h, sd["conv_post.weight"], sd["conv_post.bias"], padding=3)
     return torch.tanh(h).squeeze(1)                                         # :3076-3083
+
+
+# --------------------------------------------------------------------------- decoder post-net
+def postnet_forward(sd: Dict[str, torch.Tensor], mel: torch.Tensor) -> torch.Tensor:
+    """mel (B, T, 80) -> (B, T, 80).  modeling_speecht5.py:758-762 over five layers of :731-737 in eval mode
+    (dropout is the identity; BatchNorm1d uses its running statistics, eps 1e-5)."""
+    h = mel.transpose(1, 2)                                                 # :759
+    for i in range(5):
+        h = F.conv1d(h, sd[f"layers.{i}.conv.weight"], None, padding=2)     # :714-721, :732  (kernel 5, no bias)
+        h = F.batch_norm(h, sd[f"layers.{i}.batch_norm.running_mean"], sd[f"layers.{i}.batch_norm.running_var"],
+                         sd[f"layers.{i}.batch_norm.weight"], sd[f"layers.{i}.batch_norm.bias"], training=False, eps=1e-5)   # :733
+        if i < 4:
+            h = torch.tanh(h)                                               # :724-727, :734-735
+    return mel + h.transpose(1, 2)                                          # :762
 
 
 # --------------------------------------------------------------------------- chunker

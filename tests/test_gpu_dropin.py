@@ -115,3 +115,46 @@ def test_worker_thread_end_to_end_and_codec():
     a = G711ACodec().to("cuda:0")
     x = synth.synth_audio(1, 4000)[0]
     assert a.encode(x) == ocodec.encode_f32(x.numpy(), 1).tobytes()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_engine_with_gpu_postnet_equals_frontend_postnet(fused):
+    """postnet_state_dict moves HelloSippyRTPipe.py:230 onto the GPU (inside the tail call when fused).  Same run twice: once with
+    the post-net done by the front end on the CPU (the oracle's restatement of the transformers module), once by the engine."""
+    from infernos_b200.HelloSippyTTSRT.HelloSippyRTPipe import (HelloSippyPipeState, HelloSippyPipeStateBatched, HelloSippyPlayRequest,
+                                                                 HelloSippyRTPipe, ScriptedFrontend)
+    from oracle import tail as otail
+    d = np.load(os.path.join(G, "infer_golden.npz"))
+    B = d["plan"].shape[0]
+    psd = synth.postnet_state_dict()
+    called = []
+
+    class CpuPostnetFrontend(ScriptedFrontend):
+        def postnet(self, spectrogram):
+            called.append(1)
+            return otail.postnet_forward(psd, spectrogram.float().cpu())
+
+    def run(**kw):
+        pp = HelloSippyRTPipe("cuda:0", output_sr=8000, fused=fused, **_engine_kwargs(d, **kw))
+        got, ended, cbs = _collect(B)
+        reqs = [HelloSippyPlayRequest(uuid.uuid4(), "hello", pp.get_voice(0), cbs[i]) for i in range(B)]
+        state = HelloSippyPipeStateBatched([HelloSippyPipeState(pp, r) for r in reqs], pp)
+        audios = []
+        while True:
+            pp.infer(state)
+            audios.append(state.audio.cpu())
+            if not pp.unbatch_and_dispatch(state):
+                break
+        return pp, audios, got, ended
+
+    plan = torch.from_numpy(d["plan"])
+    _, ref_audio, ref_got, ref_ended = run(frontend=CpuPostnetFrontend(plan, d["stop_step"].tolist(), maxlen=60))
+    assert len(called) == len(ref_audio)
+    n = len(called)
+    pp, audio, got, ended = run(frontend=CpuPostnetFrontend(plan, d["stop_step"].tolist(), maxlen=60), postnet_state_dict=psd)
+    assert pp.gpu_postnet and len(called) == n            # the front end's post-net was not called again
+    assert ended == ref_ended and len(audio) == len(ref_audio)
+    for a, r in zip(audio, ref_audio):
+        assert (a - r).abs().max() < 1e-3
+    for i in range(B):
+        assert torch.cat(got[i]).shape == torch.cat(ref_got[i]).shape

@@ -163,3 +163,21 @@ def test_bf16_emulation_snr_margin():
         ref = tail.hifigan_forward(sd, mel)
         emu = tail.hifigan_forward_bf16emu(sd, mel)
     assert tail.snr_db(ref, emu) > 42.0
+
+
+def test_postnet_oracle_matches_real_module_golden():
+    """oracle.tail.postnet_forward against the real transformers SpeechT5SpeechDecoderPostnet.postnet (the call at
+    HelloSippyRTPipe.py:230), frozen by oracle/make_golden.py: a 32-frame call of 3 sessions and a 10-frame one."""
+    d = np.load(os.path.join(G, "postnet_golden.npz"))
+    sd = synth.postnet_state_dict()
+    wsha = hashlib.sha256(torch.cat([v.flatten() for v in sd.values()]).numpy().tobytes()).hexdigest()
+    assert wsha == bytes(d["weights_sha"]).decode()
+    for k_in, k_out in (("mel", "out"), ("mel_short", "out_short")):
+        y = tail.postnet_forward(sd, torch.from_numpy(d[k_in])).numpy()
+        assert y.shape == d[k_out].shape
+        assert np.abs(y - d[k_out]).max() < 1e-5
+    # the post-net changes the mel by O(1): the fixture is not vacuous
+    assert np.sqrt(np.mean((d["out"] - d["mel"]) ** 2)) > 0.5
+    # sessions and calls are independent: a session alone gives the same rows
+    y0 = tail.postnet_forward(sd, torch.from_numpy(d["mel"][1:2])).numpy()
+    assert np.abs(y0 - d["out"][1:2]).max() < 1e-5
