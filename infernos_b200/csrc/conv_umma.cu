@@ -785,7 +785,7 @@ static int launch_conv_umma_v1(const UmmaConvArgs &a, cudaStream_t st) {
 }
 
 
-static int g_occ2[64][4] = {};
+static int g_occ2[64][6] = {};
 
 template <int NT, int MINB>
 static int launch_nt2(const CUtensorMap &tm, const CUtensorMap *tm_half, UmmaParams2 &p, size_t smem, cudaStream_t st, int slot) {
@@ -892,7 +892,13 @@ int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
     switch (nt) {
         case 32: return launch_nt2<32, 3>(tm, nullptr, pp, smem, st, 0);
         case 64: return launch_nt2<64, 2>(tm, nullptr, pp, smem, st, 1);
-        case 128: return launch_nt2<128, 1>(tm, nullptr, pp, smem, st, 2);
+        case 128: {
+            // Experiment (B2_UMMA_P128_OCC=2): two CTAs per SM for upsampler 3 (2.0 GB of traffic in 0.88 ms = 2.3 TB/s).  Measured on
+            // B200: SLOWER (conv_tc class 7.53 -> 9.61 ms per step): the 96-register cap spills the epilogue.  Off by default.
+            static const int occ128 = getenv("B2_UMMA_P128_OCC") ? atoi(getenv("B2_UMMA_P128_OCC")) : 1;
+            if (occ128 >= 2 && smem <= 100 * 1024) return launch_nt2<128, 2>(tm, nullptr, pp, smem, st, 4);
+            return launch_nt2<128, 1>(tm, nullptr, pp, smem, st, 2);
+        }
         default: return launch_nt2<256, 1>(tm, th, pp, smem, st, 3);
     }
 }
