@@ -72,7 +72,9 @@ def test_reference_byte_streams(eng):
 
 def test_float_to_pcm_bit_exact(eng, oc):
     g = torch.Generator().manual_seed(5)
-    x = torch.cat([(torch.rand(100000, generator=g) * 2.4 - 1.2), torch.tensor([0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 3e-5, -3e-5])])
+    x = torch.cat([(torch.rand(100000, generator=g) * 2.4 - 1.2), torch.tensor([0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 3e-5, -3e-5]),
+                   # far out of range, infinities and NaN: the clamp saturates, NaN becomes 0 (one saturating F2I.S16 in the kernel)
+                   torch.tensor([1e9, -1e9, 3.4e38, -3.4e38, float("inf"), float("-inf"), float("nan"), 1.00001, -1.00004, 32768.0 / 32767.0])])
     assert np.array_equal(eng.f32_to_pcm16(x.cuda()).cpu().numpy(), oc.f32_to_pcm16(x.numpy()))
 
 
@@ -112,6 +114,20 @@ def test_decode_upsample_bit_exact_vs_oracle(eng, oc, taps, law):
     if law == 0:   # the reference codec's own 16 kHz decode (torch summation order): close, not bit-equal
         got = eng.g711_decode_upsample(torch.from_numpy(d["inp"]).cuda()[None], 0).cpu().numpy()[0]
         assert np.abs(got - d["out"]).max() < 2e-6
+
+
+@pytest.mark.parametrize("law", [0, 1])
+@pytest.mark.parametrize("rows,L", [(1, 4), (7, 8), (70, 12), (300, 40), (33, 4 * 255), (9, 4 * 257), (2000, 800), (5, 1024 * 3 + 4), (3, 333), (4, 162)])
+def test_decode_upsample_shapes_bit_exact_vs_oracle(eng, oc, taps, law, rows, L):
+    """Row ends on every thread of the flat 8k -> 16k kernel (one- and two-quad rows too), several grid-stride trips, and the
+    scalar kernel's shapes (L % 4 != 0); also the fp32-input form of the same kernels."""
+    g = torch.Generator().manual_seed(rows * 1000 + L)
+    codes = torch.randint(0, 256, (rows, L), generator=g).to(torch.uint8)
+    x8 = oc.decode_f32(codes.numpy(), law)
+    ref = oc.resample_1to2(x8, taps["up"])
+    got = eng.g711_decode_upsample(codes.cuda(), law).cpu().numpy()
+    assert got.shape == (rows, 2 * L) and np.array_equal(got, ref)
+    assert np.array_equal(eng.resample_1to2(torch.from_numpy(x8).cuda()).cpu().numpy(), ref)
 
 
 @pytest.mark.parametrize("law", [0, 1])

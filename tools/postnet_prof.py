@@ -34,6 +34,12 @@ for mode in ("fp32", "bf16"):
         slots = torch.arange(S, dtype=torch.int32).cuda()
         r["tail_ms"] = round(timed(lambda: t.tail(slots, big)), 3)
         r["tail_with_postnet_ms"] = round(timed(lambda: t.tail(slots, big, apply_postnet=True)), 3)
+        r["tail_ms_again"] = round(timed(lambda: t.tail(slots, big)), 3)
+        for name, ap in (("classes_tail", False), ("classes_tail_with_postnet", True)):
+            t.profile_begin()
+            t.tail(slots, big, apply_postnet=ap)
+            ms, n = t.profile_end()
+            r[name] = {k: (round(v, 3), n[k]) for k, v in ms.items()}
     r["gflop"] = round(S * 32 * (80 * 256 + 3 * 256 * 256 + 256 * 80) * 5 * 2 / 1e9, 2)
     out[mode] = r
     t.close()

@@ -17,3 +17,17 @@ for rows, L in ((100_000, 320), (100_000, 1600), (20_000, 8192), (4096, 8192), (
     ms = timed(lambda: engine.resample_g711_encode(x))
     nb = 9.0 * rows * (L // 2)
     print(os.environ.get("B2_RS_BLOCKS", "2"), rows, L, round(ms, 4), "ms", round(nb / ms / 1e6), "GB/s", round(nb / ms / 1e6 / 6446.6, 3))
+
+# 8k -> 16k side (G711Codec.decode + AudioChunk.resample): 0.5 B in + 4 B out per 16 kHz output sample
+for rows, L in ((100_000, 160), (100_000, 800), (20_000, 4096)):
+    codes = torch.randint(0, 256, (rows, L), device="cuda").to(torch.uint8)
+    ms = timed(lambda: engine.g711_decode_upsample(codes))
+    nb = 9.0 * rows * L
+    print("decode+upsample", rows, L, round(ms, 4), "ms", round(nb / ms / 1e6), "GB/s", round(nb / ms / 1e6 / 6446.6, 3))
+# what a read-dominated stream can reach on this GPU: torch's reduction over 4 GB, and a copy (the MEASURED_PEAKS method)
+big = torch.empty(1 << 30, dtype=torch.float32, device="cuda").normal_()
+ms = timed(lambda: big.sum(), iters=5)
+print("read-only probe (torch.sum over 4 GiB):", round(4 * (1 << 30) / ms / 1e6), "GB/s")
+dst = torch.empty_like(big)
+ms = timed(lambda: dst.copy_(big), iters=5)
+print("copy probe (read+write, 8 GiB moved):", round(8 * (1 << 30) / ms / 1e6), "GB/s")
