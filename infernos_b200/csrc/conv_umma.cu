@@ -328,6 +328,9 @@ struct UmmaParams2 {
 };
 
 static constexpr int kThreads2 = 320;
+// B2_UMMA_PDBG=1: clock64 per CTA (first 160) x tile iteration (first 16) x event -- 0 producer past A_EMPTY(kb 0), 1 producer issued the
+// tile's last load, 2 MMA thread past ACC_EMPTY, 3 ... past A_FULL(kb 0), 4 ... committed the tile, 5 epilogue past ACC_FULL, 6 epilogue done
+#define PDBG(ev) do { if (p.dbg && blockIdx.x < 160 && it < 16) p.dbg[((size_t)blockIdx.x * 16 + it) * 8 + (ev)] = (unsigned long long)clock64(); } while (0)
 
 template <int N_TILE, int MINB>
 __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
@@ -426,6 +429,7 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                 if (c0 == 0) {
                     mbar_wait(ACC_FULL(acc), (uint32_t)(use & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (threadIdx.x == 0) PDBG(5);
                 }
                 {
                     uint32_t a32[32];
@@ -441,29 +445,44 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                         *reinterpret_cast<uint4 *>(stg + lane * kStageLd + i * 4) = make_uint4(a32[4 * i], a32[4 * i + 1], a32[4 * i + 2], a32[4 * i + 3]);
                 }
                 __syncwarp();
-                float4 res[8];
+                // Branch-free blocks over the eight row groups (each block guarded by ONE warp-uniform condition): with a branch per row
+                // the single epilogue warp of a scheduler ran the rows as one dependent chain, ~2.3k cycles per 32-column piece
+                // (B2_UMMA_PDBG: the epilogue, not the MMAs, set the tile period of almost every launch of this kernel).
+                float4 v[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) res[i] = res_n[i];
-                if (p.residual && c0 + 32 < N_TILE) fetch(c0 + 32);
+                for (int i = 0; i < 8; i++) v[i] = *reinterpret_cast<const float4 *>(stg + (i * 4 + sub_r) * kStageLd + c4 * 4);
+                if (p.residual) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int g = grow[i];
-                    if (g < 0) continue;
-                    float4 v = *reinterpret_cast<const float4 *>(stg + (i * 4 + sub_r) * kStageLd + c4 * 4);
-                    v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
-                    if (p.residual) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
-                    if (p.acc_src) { v.x = accs[i].x + v.x; v.y = accs[i].y + v.y; v.z = accs[i].z + v.z; v.w = accs[i].w + v.w; }
-                    if (p.div != 1.0f) { v.x = __fdiv_rn(v.x, p.div); v.y = __fdiv_rn(v.y, p.div); v.z = __fdiv_rn(v.z, p.div); v.w = __fdiv_rn(v.w, p.div); }
-                    const size_t o = (size_t)g * p.N + col;
-                    if (p.out32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
-                    if (p.outb) {
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
-                        __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
-                        *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                    for (int i = 0; i < 8; i++) { v[i].x = (v[i].x + bias.x) + res_n[i].x; v[i].y = (v[i].y + bias.y) + res_n[i].y; v[i].z = (v[i].z + bias.z) + res_n[i].z; v[i].w = (v[i].w + bias.w) + res_n[i].w; }
+                    if (c0 + 32 < N_TILE) fetch(c0 + 32);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { v[i].x += bias.x; v[i].y += bias.y; v[i].z += bias.z; v[i].w += bias.w; }
+                }
+                if (p.acc_src) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { v[i].x = accs[i].x + v[i].x; v[i].y = accs[i].y + v[i].y; v[i].z = accs[i].z + v[i].z; v[i].w = accs[i].w + v[i].w; }
+                }
+                if (p.div != 1.0f) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { v[i].x = __fdiv_rn(v[i].x, p.div); v[i].y = __fdiv_rn(v[i].y, p.div); v[i].z = __fdiv_rn(v[i].z, p.div); v[i].w = __fdiv_rn(v[i].w, p.div); }
+                }
+                if (p.out32) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        if (grow[i] >= 0) *reinterpret_cast<float4 *>(p.out32 + (size_t)grow[i] * p.N + col) = v[i];
+                }
+                if (p.outb) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v[i].x, p.outb_slope), lrelu_f(v[i].y, p.outb_slope));
+                        __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v[i].z, p.outb_slope), lrelu_f(v[i].w, p.outb_slope));
+                        if (grow[i] >= 0) *reinterpret_cast<uint2 *>(p.outb + (size_t)grow[i] * p.N + col) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
                     }
                 }
                 __syncwarp();
             }
+            if (threadIdx.x == 0) PDBG(6);
         }
     } else if (warp == 4) {
         // =========================== B producer (TMA) ===========================
@@ -514,11 +533,13 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                 const int abuf = (pp.nA == 2) ? (it & 1) : 0, ause = (pp.nA == 2) ? (it >> 1) : it;
                 mbar_wait(ACC_EMPTY(acc), (uint32_t)((use & 1) ^ 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                PDBG(2);
                 const uint64_t adesc_t = adesc0 + (uint64_t)((uint32_t)abuf * a_buf_16);
                 const uint32_t tmem_acc = tb + (uint32_t)(acc * N_TILE);
                 uint32_t accum = 0;
                 for (int kb = 0; kb < p.nkb; kb++) {
                     mbar_wait(A_FULL(abuf, kb), (uint32_t)(ause & 1));
+                    if (kb == 0) PDBG(3);
                     if (!(p.flags & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     for (int j = 0; j < p.taps; j++) {
                         uint64_t bdesc_s;
@@ -542,6 +563,7 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                     umma_commit(A_EMPTY(abuf, kb));     // this K block of the A buffer may be refilled once these MMAs retire
                 }
                 umma_commit(ACC_FULL(acc));
+                PDBG(4);
             }
         }
         __syncwarp();
@@ -572,6 +594,7 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
             }
             for (int kb = 0; kb < p.nkb; kb++) {
                 mbar_wait(A_EMPTY(abuf, kb), (uint32_t)((ause & 1) ^ 1));
+                if (kb == 0 && ptid == 0) PDBG(0);
 #pragma unroll
                 for (int i = 0; i < 12; i++) {
                     const int r = r_first + i * rstep;
@@ -582,6 +605,7 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                 }
                 cp_async_arrive_noinc(A_FULL(abuf, kb));
             }
+            if (ptid == 0) PDBG(1);
         }
     }
 
@@ -808,9 +832,43 @@ static int launch_nt2(const CUtensorMap &tm, const CUtensorMap *tm_half, UmmaPar
     p.mc = (mc_on && tm_half && p.ntiles == 1 && !p.resident && grid >= 2 && occ == 1) ? 1 : 0;
     if (p.mc) grid &= ~1;
     p.iters = cdiv(p.total_tiles, grid);
+    static const bool pdbg_on = getenv("B2_UMMA_PDBG") != nullptr;
+    static unsigned long long *pdbg_buf = nullptr;
+    constexpr size_t kPdbgWords = 160 * 16 * 8;
+    if (pdbg_on) {
+        if (!pdbg_buf) cudaMalloc(&pdbg_buf, kPdbgWords * 8);
+        cudaMemsetAsync(pdbg_buf, 0, kPdbgWords * 8, st);
+        p.b.dbg = pdbg_buf;
+    }
     if (!p.mc) {
         k_conv_umma_p<NT, MINB><<<grid, kThreads2, smem, st>>>(tm, tm, p);
         B2_LAUNCH_OK("k_conv_umma_p");
+        if (pdbg_on) {
+            cudaStreamSynchronize(st);
+            static std::vector<unsigned long long> h(kPdbgWords);
+            cudaMemcpy(h.data(), pdbg_buf, kPdbgWords * 8, cudaMemcpyDeviceToHost);
+            // steady state: tile iterations 3..min(iters,16)-2 of every CTA
+            double d[8] = {0}; int cnt = 0;
+            const int hi = std::min(p.iters, 16) - 1;
+            for (int c = 0; c < std::min(grid, 160); c++)
+                for (int it = 3; it < hi; it++) {
+                    const unsigned long long *e = &h[((size_t)c * 16 + it) * 8], *pe = e - 8;
+                    if (!e[0] || !e[6] || !pe[4]) continue;
+                    cnt++;
+                    d[0] += (double)(e[4] - pe[4]);     // tile period (MMA commit to MMA commit)
+                    d[1] += (double)(e[4] - e[3]);      // MMA loop: A(kb 0) seen -> tile committed (incl. waiting for weights / later K blocks)
+                    d[2] += (double)(e[3] - e[2]);      // MMA thread waiting for the tile's first A block
+                    d[3] += (double)((long long)e[2] - (long long)pe[4]);   // MMA thread waiting for a free accumulator
+                    d[4] += (double)(e[1] - e[0]);      // producer: issuing the tile's loads (incl. waiting for free K blocks)
+                    d[5] += (double)(e[6] - e[5]);      // epilogue of the tile
+                    d[6] += (double)((long long)e[5] - (long long)pe[6]);   // epilogue waiting for the next accumulator
+                    d[7] += (double)((long long)e[3] - (long long)e[1]);    // last load issued -> first A block seen (negative: loads trail)
+                }
+            if (cnt) fprintf(stderr, "[umma_p dbg] N=%d Cin=%d taps=%d dil=%d T=%d res=%d out32=%d outb=%d nA=%d stages=%d resident=%d iters=%d | cycles per tile: period %.0f, "
+                             "mma-loop %.0f, mma-wait-A %.0f, mma-wait-acc %.0f, producer %.0f, epilogue %.0f, epi-wait-acc %.0f, issue->A-seen %.0f (n=%d)\n",
+                             p.b.N, p.b.Cin, p.b.taps, p.b.dil, p.b.T, p.b.residual != nullptr, p.b.out32 != nullptr, p.b.outb != nullptr, p.nA, p.b.stages, p.resident, p.iters,
+                             d[0] / cnt, d[1] / cnt, d[2] / cnt, d[3] / cnt, d[4] / cnt, d[5] / cnt, d[6] / cnt, d[7] / cnt, cnt);
+        }
         return 0;
     }
     cudaLaunchConfig_t cfg = {};
