@@ -933,10 +933,13 @@ int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
     size_t b_bytes;
     if (pp.resident) { b_bytes = all_w; p.stages = 0; pp.nA = 2; }
     else {
+        // Streamed weights need a DEEP ring before a second A buffer: an N=256 tile consumes 64 B of weights per cycle, i.e. 4 x 32 KB
+        // in flight at ~1 us of L2 latency.  (B2_UMMA_PDBG: with two A buffers and a 2-deep ring the MMA loop of the C=256 layers ran
+        // at 1.8x its tensor-pipe time, with one A buffer -- K blocks recycled as their MMAs retire -- and 3-4 stages at 1.4x.)
+        static const int prefer_na = getenv("B2_UMMA_P_NA") ? atoi(getenv("B2_UMMA_P_NA")) : 0;      // 0 = policy below
         int stages = 4;
         pp.nA = 2;
-        while (stages > 2 && stages * b_tile + pp.nA * a_bytes + fixed > budget) stages--;
-        if (stages * b_tile + pp.nA * a_bytes + fixed > budget) { pp.nA = 1; stages = 4; }
+        if (prefer_na == 1 || (prefer_na == 0 && stages * b_tile + 2 * a_bytes + fixed > budget)) pp.nA = 1;
         while (stages > 2 && stages * b_tile + pp.nA * a_bytes + fixed > budget) stages--;
         static const int st_cap = getenv("B2_UMMA_P_STAGES") ? atoi(getenv("B2_UMMA_P_STAGES")) : 4;     // analysis: fewer weight tiles in flight
         stages = std::max(1, std::min(stages, st_cap));
