@@ -389,9 +389,30 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
         const int sub_r = lane >> 3, c4 = lane & 7;
         // in multicast mode both CTAs of a cluster run the same number of tiles (the weight ring is shared): tiles past the end are
         // dummies whose rows are all masked (w >= W)
+        // The fp32 residual / MRF-sum rows a tile's epilogue will add come from HBM (the tensors are larger than L2): they are pulled
+        // into L2 one TILE ahead (lane = row, one 128-byte line per 32-column piece), so that the register prefetch one PIECE ahead
+        // only has to cover an L2 hit.  No registers are held across the wait.
+        auto l2_prefetch_tile = [&](int tile_n) {
+            if (!(p.residual || p.acc_src) || tile_n >= pp.total_tiles) return;
+            int w0n, t0n, n0n;
+            tile_coords(tile_n, w0n, t0n, n0n);
+            const int mn = warp * 32 + lane;
+            const int sn = (p.nseg > 1) ? fdiv(mn, p.m_period) : 0;
+            const int tn = t0n + (mn - sn * p.period);
+            const int wn = w0n + sn;
+            if ((tn < p.T) && (sn < p.nseg) && (wn < p.W)) {
+                const size_t off = (size_t)(wn * p.T + tn) * p.N + n0n;
+                for (int c = 0; c < N_TILE; c += 32) {
+                    if (p.residual) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + off + c));
+                    if (p.acc_src) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc_src + off + c));
+                }
+            }
+        };
+        l2_prefetch_tile((int)blockIdx.x);
         for (int it = 0; it < pp.iters; ++it) {
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             if (!pp.mc && tile >= pp.total_tiles) break;
+            l2_prefetch_tile(tile + (int)gridDim.x);
             int w0, t0, n0;
             tile_coords(tile, w0, t0, n0);
             const int acc = it & 1, use = it >> 1;
@@ -464,8 +485,16 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                     for (int i = 0; i < 8; i++) { v[i].x = accs[i].x + v[i].x; v[i].y = accs[i].y + v[i].y; v[i].z = accs[i].z + v[i].z; v[i].w = accs[i].w + v[i].w; }
                 }
                 if (p.div != 1.0f) {
+                    // v / div as a reciprocal multiply and one Newton step (q = v * r; q + r * (v - div * q)): no IEEE-division sequence per element
+                    const float rcp = __frcp_rn(p.div), nd = -p.div;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) { v[i].x = __fdiv_rn(v[i].x, p.div); v[i].y = __fdiv_rn(v[i].y, p.div); v[i].z = __fdiv_rn(v[i].z, p.div); v[i].w = __fdiv_rn(v[i].w, p.div); }
+                    for (int i = 0; i < 8; i++) {
+                        float q;
+                        q = v[i].x * rcp; v[i].x = fmaf(fmaf(nd, q, v[i].x), rcp, q);
+                        q = v[i].y * rcp; v[i].y = fmaf(fmaf(nd, q, v[i].y), rcp, q);
+                        q = v[i].z * rcp; v[i].z = fmaf(fmaf(nd, q, v[i].z), rcp, q);
+                        q = v[i].w * rcp; v[i].w = fmaf(fmaf(nd, q, v[i].w), rcp, q);
+                    }
                 }
                 if (p.out32) {
 #pragma unroll
