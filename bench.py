@@ -62,7 +62,7 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.all_rows, self.t0 = index, [], None, [], 0.0
 
     def start(self):
         try:
@@ -74,13 +74,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.all_rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        """nvidia-smi takes a few hundred ms to start streaming, so it is launched before the warm-up; only samples that
+        arrive between mark_begin() (start of the timed region) and stop() are reported."""
+        self.t0 = time.time()
+
+    def samples_under_load(self) -> int:
+        return sum(1 for t, _ in self.all_rows if t >= self.t0)
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
+        self.rows = [r for t, r in self.all_rows if t >= self.t0]
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -199,12 +207,13 @@ def main_b200(args, rank, local_rank, world):
         return sharding.max_over_ranks(ms, device=dev)
 
     # ---- device-resident timing -------------------------------------------------------------------
-    for _ in range(args.warmup):
-        tail.tail(slots_d, mel_d, want_audio=False)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        tail.tail(slots_d, mel_d, want_audio=False)
+    barrier()
+    sampler.mark_begin()
     l0 = kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -213,7 +222,6 @@ def main_b200(args, rank, local_rank, world):
     e1.record()
     barrier()
     launches = kernel_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     audio_s = S * world * F * AUDIO_S_PER_FRAME * args.steps
     value = audio_s / (ms_total / 1e3)
@@ -229,6 +237,15 @@ def main_b200(args, rank, local_rank, world):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     barrier()
     e2e_value = audio_s / (e2e_ms / 1e3)
+    # clocks: sampled every 100 ms across both timed regions; a short run (10 steps = 0.23 s) is extended with untimed steps of
+    # the same load until three samples are in (bounded), so the line never goes out without clocks
+    if rank == 0:
+        t_lim = time.time() + 3.0
+        while sampler.proc is not None and sampler.samples_under_load() < 3 and time.time() < t_lim:
+            tail.tail(slots_d, mel_d, want_audio=False)
+            torch.cuda.synchronize(dev)
+    clocks = sampler.stop() if rank == 0 else None
+    barrier()
 
     # ---- per-kernel-class timing for the roofline (separate pass, events around every launch) --------
     tail.profile_begin()

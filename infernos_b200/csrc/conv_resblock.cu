@@ -62,6 +62,7 @@ struct RbParams {
     int dil0, dil1, dil2;
     unsigned long long m_tpw;
     unsigned long long *dbg;   // optional per-CTA phase timestamps (B2_RB_DBG analysis runs)
+    int dbg_flags;             // bit 0: no L2 prefetch of the slab at CTA start (B2_RB_NOPF=1: A/B switch)
     float bias1[3 * kRbMaxC];  // conv1 biases                                         (constant bank: uniform loads)
     float cbias[3 * kRbMaxC];  // running sum of conv2 biases: cbias[i] = b2[0] + .. + b2[i]
 };
@@ -165,6 +166,25 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
     const int t_base = tile * p.V - p.H;               // time of slab row 0
 
     if (threadIdx.x == 0) RB_DBG(0);
+    // The slab's x rows (and, for the final epilogue, the MRF partial sum's) start their way from HBM into L2 before anything else:
+    // the load phase below keeps only two 4 KB pieces per warp in flight, so at HBM latency it was ~13k cycles of a 34-114k-cycle CTA
+    // (phase timestamps, profiles/); out of L2 it is a few thousand.  One 128-byte line per lane per 32-channel piece.
+    if (warp < NEW && !(p.dbg_flags & 1)) {
+        const int rq0 = (warp & 3) * 32 + lane, cb0 = (warp >> 2) * (CHW * 32);
+#pragma unroll
+        for (int s = 0; s < kS; s++) {
+            const int r = s * 128 + rq0, t = t_base + r;
+            if (t >= 0 && t < p.T) {
+                const size_t off = ((size_t)w * p.T + t) * C + cb0;
+#pragma unroll
+                for (int cc = 0; cc < CHW; cc++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + off + cc * 32));
+                if (p.acc_src && r >= p.H && r < p.H + p.V) {
+#pragma unroll
+                    for (int cc = 0; cc < CHW; cc++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc_src + off + cc * 32));
+                }
+            }
+        }
+    }
     // ---- prologue
     if (warp == NEW) {
         if (lane == 0) {
@@ -732,6 +752,8 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     const size_t dbg_n = (size_t)kRbDbgCtas * kRbDbgEvents;
     if (dbg_on && !dbg_buf) B2_CUDA_OK(cudaMalloc(&dbg_buf, dbg_n * 8));
     p.dbg = dbg_on ? dbg_buf : nullptr;
+    static const int nopf = getenv("B2_RB_NOPF") ? atoi(getenv("B2_RB_NOPF")) : 0;
+    p.dbg_flags = nopf ? 1 : 0;
     if (dbg_on) B2_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, dbg_n * 8, st));
     const int rc = (pk.C == 32) ? launch_rb<32, 4, 2>(tm, p, (unsigned)nct, smem, st, 0)
                    : (pk.C == 64) ? launch_rb<64, 8, 2>(tm, p, (unsigned)nct, smem, st, 1)
