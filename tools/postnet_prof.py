@@ -1,12 +1,18 @@
 #!/usr/bin/env python
-"""Post-net numbers for DESIGN.md: parity against the oracle and device time at the bench's shape (1,024 sessions x 32 frames),
-alone and inside the fused tail call."""
+"""Post-net device time at the bench's shape (1,024 sessions x 32 frames), alone and inside the fused tail call, and the distance
+between the two precision modes.  (Parity against the oracle and the golden vectors is tests/test_gpu_postnet.py's job: tools do not
+import oracle/.)"""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from infernos_b200 import synth
 from infernos_b200.engine import TTSTail
-from oracle.tail import postnet_forward, snr_db
+
+
+def snr_db(ref, x):
+    ref, x = ref.double(), x.double()
+    return float(10 * torch.log10((ref ** 2).sum() / ((ref - x) ** 2).sum()))
+
 
 
 def timed(fn, iters=10, warm=3):
@@ -20,14 +26,18 @@ def timed(fn, iters=10, warm=3):
 
 
 out = {}
+y_by_mode = {}
 sds = synth.hifigan_state_dict(), synth.chunker_state_dict(), synth.postnet_state_dict()
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 for mode in ("fp32", "bf16"):
     t = TTSTail("cuda:0", sds[0], sds[1], mode=mode, max_sessions=S, max_windows=(4 * S if mode == "bf16" else 256), postnet_sd=sds[2])
     mel = synth.synth_mel(64, 32, seed=5)
-    ref = postnet_forward(sds[2], mel)
     y = t.postnet(mel.cuda()).cpu()
-    r = {"max_abs_err": float((y - ref).abs().max()), "snr_db": float(snr_db(ref, y)), "snr_db_layers_only": float(snr_db(ref - mel, y - mel))}
+    y_by_mode[mode] = y
+    r = {}
+    if mode == "bf16":      # the fp32 mode (1e-5 from the reference module, tests) as the yardstick for the tensor-core mode
+        ref = y_by_mode["fp32"]
+        r = {"max_abs_vs_fp32_mode": float((y - ref).abs().max()), "snr_db_vs_fp32_mode": snr_db(ref, y), "snr_db_layers_only": snr_db(ref - mel, y - mel)}
     big = synth.synth_mel(S, 32, seed=6).cuda()
     r["postnet_ms_%d_sessions" % S] = round(timed(lambda: t.postnet(big)), 4)
     if mode == "bf16":
