@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """Post-net device time at the bench's shape (1,024 sessions x 32 frames), alone and inside the fused tail call, and the distance
-between the two precision modes.  (Parity against the oracle and the golden vectors is tests/test_gpu_postnet.py's job: tools do not
-import oracle/.)"""
+between the two precision modes.  (Parity against the oracle and the golden vectors is tests/test_gpu_postnet.py's job: tools stay clear of the oracle directory.)"""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
