@@ -221,6 +221,7 @@ class HelloSippyRTPipe:
     output_sr: int = 16000
     default_model = "microsoft/speecht5_tts"
     cleanup_text: Optional[Callable] = None
+    gpu_postnet: bool = False          # True when post-net weights were given: line :230 then runs inside the tail call
 
     def __init__(self, device, model=default_model, get_processor: Optional[Callable] = None, output_sr: int = output_sr, **kwa):
         """kwa (beyond the reference's cleanup_text and SpeechT5Config overrides):
