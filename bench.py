@@ -99,7 +99,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_tail_fn():
+def cpu_tail_fn(dtype=None):
     """The reference's own CPU arithmetic for the path: transformers SpeechT5HifiGan (the third-party module the
     reference calls) when importable, the oracle's restatements for AmendmentNetwork1 / Resample / G711Codec.encode
     (their sources live in /root/reference, which does not exist on the GPU box)."""
@@ -108,11 +108,16 @@ def cpu_tail_fn():
     from oracle import codec as ocodec
     from oracle import tail as otail
     vsd, csd = synth.hifigan_state_dict(), synth.chunker_state_dict()
+    dtype = dtype or torch.float32
+    if dtype != torch.float32:          # the reference's product precision: maybe_half() on every module (HelloSippyRTPipe.py:57,171-186)
+        vsd = {k: v.to(dtype) for k, v in vsd.items()}
+        csd = {k: v.to(dtype) for k, v in csd.items()}
     kind = "port"
     try:
         from transformers import SpeechT5HifiGan, SpeechT5HifiGanConfig
         voc = SpeechT5HifiGan(SpeechT5HifiGanConfig())
-        voc.load_state_dict(vsd, strict=True)
+        voc.load_state_dict({k: v.float() for k, v in vsd.items()}, strict=True)
+        voc = voc.to(dtype)
         voc.eval()
         vocoder = lambda win: voc(win)
         desc = "transformers.SpeechT5HifiGan + oracle AmendmentNetwork1/Resample/G.711 restatements"
@@ -126,7 +131,7 @@ def cpu_tail_fn():
             win, new_pre = otail.build_windows(pre, mel)
             audio = vocoder(win)
             audio = otail.chunker_forward(csd, win, audio)
-            audio = torch.cat(audio.split(B, dim=0), dim=1)
+            audio = torch.cat(audio.split(B, dim=0), dim=1).float()
             audio = otail.resample(audio, 16000, 8000)
             by = ocodec.encode_f32(audio.numpy(), 0)
         return new_pre, by
@@ -134,13 +139,14 @@ def cpu_tail_fn():
     return step, kind, desc
 
 
-def run_cpu(sessions: int, steps: int, warmup: int, frames: int = 32):
+def run_cpu(sessions: int, steps: int, warmup: int, frames: int = 32, dtype=None):
     import torch
     from infernos_b200 import synth
     torch.set_num_threads(os.cpu_count() or 1)
-    step, kind, desc = cpu_tail_fn()
-    mel = synth.synth_mel(sessions, frames, seed=7)
-    pre = torch.zeros(sessions, 4, 80)
+    dtype = dtype or torch.float32
+    step, kind, desc = cpu_tail_fn(dtype)
+    mel = synth.synth_mel(sessions, frames, seed=7).to(dtype)
+    pre = torch.zeros(sessions, 4, 80, dtype=dtype)
     for _ in range(warmup):
         pre, _ = step(pre, mel)
     t0 = time.perf_counter()
@@ -149,12 +155,33 @@ def run_cpu(sessions: int, steps: int, warmup: int, frames: int = 32):
     dt = time.perf_counter() - t0
     streams = sessions * frames * AUDIO_S_PER_FRAME * steps / dt
     return dict(value=streams, ms_per_step=dt / steps * 1e3, kind=kind, cores=torch.get_num_threads(),
-                sample=f"{sessions} sessions x {frames} mel frames per step, {steps} steps, fp32, {desc}")
+                sample=f"{sessions} sessions x {frames} mel frames per step, {steps} steps, {'fp32' if dtype == torch.float32 else 'bf16'}, {desc}")
+
+
+def main_cpu_sweep(args):
+    """SURVEY section 8(d) CPU baseline table: the reference tail on this box's host cores, fp32 and bf16, B in {1, 8, 64},
+    one warm-up + three timed steps each (bf16 B=64 is skipped when bf16 B=8 already takes > 20 s per step)."""
+    import torch
+    rows = []
+    for dtype, name in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        slow = False
+        for B in (1, 8, 64):
+            if slow:
+                rows.append({"dtype": name, "sessions": B, "skipped": "previous batch size took > 20 s per step"})
+                continue
+            r = run_cpu(B, 3, 1, dtype=dtype)
+            rows.append({"dtype": name, "sessions": B, "ms_per_step": round(r["ms_per_step"], 1), "streams_rtf1": round(r["value"], 2),
+                         "vocoder_msamples_per_s": round(B * 32 * 256 / r["ms_per_step"] / 1e3, 3), "cores": r["cores"], "kind": r["kind"]})
+            print(rows[-1], file=sys.stderr, flush=True)
+            slow = r["ms_per_step"] > 20000
+    print(json.dumps({"impl": "reference", "cpu_sweep": rows, "os_cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads()}), flush=True)
 
 
 def main_reference(args, rank, world):
     if rank != 0:
         return
+    if args.cpu_sweep:
+        return main_cpu_sweep(args)
     sessions = args.ref_sessions
     r = run_cpu(sessions, args.steps, min(args.warmup, 1) if args.warmup else 0)
     out = {
@@ -365,6 +392,7 @@ def main():
     ap.add_argument("--max-windows", type=int, default=4096, help="workspace capacity in 12-frame windows (sub-batch size)")
     ap.add_argument("--ref-sessions", type=int, default=16, help="sessions per step of the CPU arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sweep", action="store_true", help="with --impl reference: fp32/bf16 x B in {1,8,64} CPU table (SURVEY 8d)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
