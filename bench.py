@@ -182,13 +182,16 @@ def main_reference(args, rank, world):
         return
     if args.cpu_sweep:
         return main_cpu_sweep(args)
+    import torch
     sessions = args.ref_sessions
-    r = run_cpu(sessions, args.steps, min(args.warmup, 1) if args.warmup else 0)
+    rdt = torch.bfloat16 if args.ref_dtype == "bf16" else torch.float32
+    r = run_cpu(sessions, args.steps, min(args.warmup, 1) if args.warmup else 0, dtype=rdt)
     out = {
         "impl": "reference", "metric": "real-time G.711 TTS streams (RTF<=1)", "value": round(r["value"], 3), "unit": "streams",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(r["ms_per_step"], 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"TTS tail (HiFiGAN+chunker+16k->8k+G.711), {sessions} sessions x 32-frame calls on host CPU cores",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.ref_dtype == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"TTS tail (HiFiGAN+chunker+16k->8k+G.711), {sessions} sessions x 32-frame calls on host CPU cores, {args.ref_dtype} "
+                               "(the reference casts every module to bf16, HelloSippyRTPipe.py:57,164-186, and batches 8 requests, Cluster/InfernTTSWorker.py:57)",
                    "sessions_per_step": sessions, "frames_per_call": 32},
         "cpu_baseline": {"value": round(r["value"], 3), "unit": "streams", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": round(r["value"], 3), "unit": "streams", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -347,7 +350,7 @@ def main_b200(args, rank, local_rank, world):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = run_cpu(args.ref_sessions, 3, 1)
+        r = run_cpu(args.ref_sessions, 3, 1, dtype=torch.bfloat16 if args.ref_dtype == "bf16" else torch.float32)
         cpu = {"value": round(r["value"], 3), "unit": "streams", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
     if rank == 0:
@@ -390,7 +393,8 @@ def main():
     ap.add_argument("--frames", type=int, default=32, help="mel frames per session per call (reference: 32)")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--max-windows", type=int, default=4096, help="workspace capacity in 12-frame windows (sub-batch size)")
-    ap.add_argument("--ref-sessions", type=int, default=16, help="sessions per step of the CPU arm's bounded sample")
+    ap.add_argument("--ref-sessions", type=int, default=8, help="sessions per step of the CPU arm's bounded sample (reference: max_batch_size = 8)")
+    ap.add_argument("--ref-dtype", default="bf16", choices=["bf16", "fp32"], help="precision of the CPU arm (the reference runs bf16: maybe_half)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sweep", action="store_true", help="with --impl reference: fp32/bf16 x B in {1,8,64} CPU table (SURVEY 8d)")
     args = ap.parse_args()
