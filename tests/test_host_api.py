@@ -85,3 +85,25 @@ def test_product_package_never_imports_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h")):
                     src = open(os.path.join(dp, f)).read()
                     assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_postnet_layers_picks_the_25_tensors_whatever_the_prefix():
+    """engine.postnet_layers: the post-net's conv / batch-norm tensors out of a SpeechT5SpeechDecoderPostnet state_dict, out of
+    a whole-model state_dict (prefix `speech_decoder_postnet.`), never the encoder/decoder `layers.*`, never feat_out / prob_out."""
+    import torch
+    from infernos_b200 import synth
+    from infernos_b200.engine import postnet_layers
+    from transformers import SpeechT5Config
+    from transformers.models.speecht5.modeling_speecht5 import SpeechT5SpeechDecoderPostnet
+    real = SpeechT5SpeechDecoderPostnet(SpeechT5Config()).state_dict()
+    got = postnet_layers(real)
+    assert len(got) == 25 and set(got) == set(synth.postnet_state_dict())
+    for k, v in synth.postnet_state_dict().items():
+        assert tuple(v.shape) == tuple(real[k].shape), k
+    whole = {"speech_decoder_postnet." + k: v for k, v in real.items()}
+    whole["speecht5.decoder.wrapped_decoder.layers.0.self_attn.k_proj.weight"] = torch.zeros(4, 4)
+    whole["speecht5.encoder.wrapped_encoder.layers.0.feed_forward.intermediate_dense.weight"] = torch.zeros(4, 4)
+    got2 = postnet_layers(whole)
+    assert set(got2) == set(got) and all(torch.equal(got2[k], got[k]) for k in got)
+    with pytest.raises(RuntimeError):
+        postnet_layers({k: v for k, v in real.items() if "layers.3" not in k})
