@@ -1,5 +1,9 @@
 """Audio container (mirror of /root/reference/Core/AudioChunk.py:8-24).  resample() runs the library's
-8 kHz <-> 16 kHz polyphase kernels; other rate pairs are not on this path and raise."""
+8 kHz <-> 16 kHz polyphase kernels; other rate pairs are not on this path and raise.
+
+G711AudioChunk additionally carries the G.711 payload the GPU produced in the same pass as the audio, so that
+the RTP side (RTP/RTPOutputWorker.py:118 `self.codec.encode(chunk)`) can skip its per-call CPU encode when the call has a single
+active track; the float samples stay available for the mixing path (Core/OutputMuxer.py:81 needs linear PCM)."""
 from __future__ import annotations
 
 import torch
@@ -38,3 +42,22 @@ class AudioChunk:
 
     def duration(self) -> float:
         return self.audio.size(0) / self.samplerate
+
+
+class G711AudioChunk(AudioChunk):
+    """8 kHz audio together with its pre-encoded G.711 payload (one byte per sample, `ename` 'PCMU' or 'PCMA').  The payload is
+    dropped by anything that changes the samples (resample), after which the chunk behaves like a plain AudioChunk."""
+
+    def __init__(self, audio: torch.Tensor, samplerate: int, payload: bytes, ename: str = "PCMU"):
+        super().__init__(audio, samplerate)
+        if samplerate != 8000:
+            raise ValueError("a G.711 payload is 8 kHz audio")
+        if len(payload) != audio.size(0):
+            raise ValueError(f"payload has {len(payload)} bytes for {audio.size(0)} samples")
+        if ename not in ("PCMU", "PCMA"):
+            raise ValueError(f"unknown G.711 variant {ename!r}")
+        self.payload, self.ename = bytes(payload), ename
+
+    def resample(self, sample_rate: int):
+        self.payload = None
+        return super().resample(sample_rate)

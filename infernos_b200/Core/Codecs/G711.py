@@ -15,7 +15,7 @@ import torch
 
 from infernos_b200 import engine
 from infernos_b200._lib import LAW_ALAW, LAW_ULAW
-from infernos_b200.Core.AudioChunk import AudioChunk
+from infernos_b200.Core.AudioChunk import AudioChunk, G711AudioChunk
 from .GenCodec import GenCodec
 
 
@@ -36,8 +36,14 @@ class G711Codec(GenCodec):
             self._device = torch.device("cuda", torch.cuda.current_device())
         return self._device
 
-    def encode(self, audio_tensor: torch.Tensor) -> bytes:
+    def encode(self, audio_tensor) -> bytes:
+        """Tensor -> bytes like the reference.  Also takes an AudioChunk; a G711AudioChunk whose payload was produced on the GPU with
+        this codec's law is returned as is (no second encode on the RTP side)."""
         x = audio_tensor
+        if isinstance(x, G711AudioChunk) and x.payload is not None and x.ename == self.ename and x.samplerate == self.srate:
+            return x.payload
+        if isinstance(x, AudioChunk):
+            x = x.audio
         if not x.is_cuda:
             x = x.to(self._dev(), non_blocking=True)
         if x.dtype != torch.int16:

@@ -107,3 +107,28 @@ def test_postnet_layers_picks_the_25_tensors_whatever_the_prefix():
     assert set(got2) == set(got) and all(torch.equal(got2[k], got[k]) for k in got)
     with pytest.raises(RuntimeError):
         postnet_layers({k: v for k, v in real.items() if "layers.3" not in k})
+
+
+def test_g711_audio_chunk_carries_its_payload_past_the_encoder():
+    """a chunk that already has its GPU-made payload is not encoded again (no CUDA needed for that path), a plain
+    chunk or a payload of the other law is; resample drops the payload."""
+    import torch
+    from infernos_b200.Core.AudioChunk import AudioChunk, G711AudioChunk
+    from infernos_b200.Core.Codecs.G711 import G711ACodec, G711Codec
+    audio = torch.linspace(-0.5, 0.5, 160)
+    payload = bytes(range(160))
+    ch = G711AudioChunk(audio, 8000, payload, "PCMU")
+    assert isinstance(ch, AudioChunk) and ch.duration() == 0.02
+    assert G711Codec().encode(ch) is ch.payload == payload
+    with pytest.raises(ValueError):
+        G711AudioChunk(audio, 8000, payload[:-1])
+    with pytest.raises(ValueError):
+        G711AudioChunk(audio, 16000, payload)
+    with pytest.raises(ValueError):
+        G711AudioChunk(audio, 8000, payload, "G722")
+    if not torch.cuda.is_available():
+        # the other law / a plain chunk have to go through the CUDA encoder: without a GPU that fails loudly (no CPU fallback)
+        with pytest.raises(RuntimeError):
+            G711ACodec().encode(ch)
+        with pytest.raises(RuntimeError):
+            G711Codec().encode(AudioChunk(audio, 8000))
