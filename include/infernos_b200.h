@@ -102,6 +102,17 @@ B2_API int b2_tts_tail2(b2_ctx *ctx, const int32_t *d_slots, const float *d_mel,
                  uint8_t *d_g711, float *d_audio, void *stream);
 B2_API int b2_tts_tail_host2(b2_ctx *ctx, const int32_t *h_slots, const float *h_mel, int B, int nframes, int law, int flags,
                       uint8_t *h_g711, float *h_audio, void *stream);
+/* Slot ids handed over in DEVICE memory (b2_tts_tail / b2_tts_tail2) are validated by the window-builder kernel itself: an id outside
+ * [0, max_sessions) or the same id twice in one call is computed with zero pre_frames, leaves the pool untouched, and raises a flag that
+ * the NEXT call on the context reports, or this call once `stream` has been synchronised (returns non-zero + b2_last_error).  The host
+ * entries check their slot ids before launching anything.  (The reference keeps pre_frames inside the batch state, HelloSippyRTPipe.py:67,
+ * so it has no such failure mode; a slot pool does.) */
+B2_API int b2_ctx_poll_errors(b2_ctx *ctx, void *stream);
+/* Debug taps for the parity tests (BASELINE config 2: "every stage boundary"): nine device pointers, any of them NULL, in the order
+ * conv_pre, upsampler0, stage0 (MRF mean), upsampler1, stage1, upsampler2, stage2, upsampler3, stage3; each receives the fp32 channels-last
+ * tensor [W][T_stage][C_stage] of the next b2_vocoder_forward / b2_tts_tail sub-batch (modeling_speecht5.py:3062-3072).  B2_MODE_FP32 fills all
+ * nine; B2_MODE_BF16 only the upsampler outputs (the other boundaries never leave the chip there).  d_taps == NULL clears them. */
+B2_API int b2_debug_set_taps(b2_ctx *ctx, float *const *d_taps);
 /* zero the pre_frames of the given slots (HelloSippyPipeState.__init__, HelloSippyRTPipe.py:77); h_slots host */
 B2_API int b2_session_reset(b2_ctx *ctx, const int32_t *h_slots, int n, void *stream);
 /* read / write one session's pre_frames (4x80 fp32, host) — used to migrate or checkpoint a session */
@@ -124,6 +135,12 @@ B2_API int b2_resample_g711_encode(const float *d_in, size_t rows, size_t L, int
 B2_API int b2_g711_decode_upsample(const uint8_t *d_in, size_t rows, size_t L, int law, float *d_out, void *stream);
 /* AudioChunk.resample 8k -> 16k on its own: (rows, L) -> (rows, 2L) */
 B2_API int b2_resample_1to2(const float *d_in, size_t rows, size_t L, float *d_out, void *stream);
+/* Batched inbound decode (RTP/InfernRTPIngest.py:63-100 decodes per packet group, feeding Core/VAD/SileroVAD.py:27-35 and
+ * Cluster/STTSession.py:93-94): `rows` packets of ANY lengths in one launch.  Row r = bytes [offsets[r], offsets[r+1]) of d_in; output row r
+ * starts at float offsets[r] (x2 when upsample != 0: 8k -> 16k with the per-call zero padding of Core/AudioChunk.py:19-24 at each row's ends). */
+B2_API int b2_g711_decode_ragged(const uint8_t *d_in, const unsigned long long *d_offsets, size_t rows, int law, int upsample, float *d_out, void *stream);
+/* same from HOST memory: one H2D, one launch (the flat kernels when all rows have one length), one D2H, stream synchronised on return */
+B2_API int b2_g711_decode_many_host(const uint8_t *h_in, const unsigned long long *h_offsets, size_t rows, int law, int upsample, float *h_out, void *stream);
 
 /* ---- single-layer entry points (unit tests of the two convolution kernel families) -----------------
  * One Conv1d(Cin, Cout, k, dilation=dil, padding=(k-1)*dil/2) over channels-last activations [W][T][C]:

@@ -54,13 +54,31 @@ class InfernTTSWorker(InfernBatchedWorker):
             device = get_torch_hw()
         kwa = dict(lang2model[lang])
         kwa.update(engine_kwa)
+        want_batch = kwa.pop("max_batch_size", None)          # a worker knob, not a SpeechT5Config override
         self.tts_engine = HelloSippyRTPipe(device, output_sr=output_sr, **kwa)
         self.output_sr = output_sr
-        self.max_batch_size = engine_kwa.get("max_batch_size", self.tts_engine.tail.max_sessions)
+        pool = self.tts_engine.tail.max_sessions
+        self.max_batch_size = pool if want_batch is None else max(1, min(int(want_batch), pool))
+
+    def _new_cohort(self, wis: List[HelloSippyPlayRequest]):
+        """Builds the batch state of newly admitted requests.  Anything that goes wrong here (tokenisation, a missing script
+        entry, an exhausted slot pool) ends those requests' sentences (`dispatch(None)`) and leaves the worker running: the
+        sessions already in flight must not be stranded by a bad newcomer."""
+        try:
+            return HelloSippyPipeStateBatched([HelloSippyPipeState(self.tts_engine, r) for r in wis], self.tts_engine)
+        except Exception as e:
+            print(f"InfernTTSWorker: could not admit {len(wis)} request(s): {e!r}")
+            for r in wis:
+                try:
+                    r.dispatch(None)
+                except Exception:
+                    pass
+            return None
 
     def process_batch(self, wis: List[HelloSippyPlayRequest]):
-        new_states = [HelloSippyPipeState(self.tts_engine, r) for r in wis]
-        state = HelloSippyPipeStateBatched(new_states, self.tts_engine)
+        state = self._new_cohort(wis)
+        if state is None:
+            return
         while True:
             try:
                 self.tts_engine.infer(state)
@@ -86,7 +104,9 @@ class InfernTTSWorker(InfernBatchedWorker):
                     cb = getattr(wi, "_proc_start_cb", None)
                     if cb is not None:
                         cb()
-                cohorts.append(HelloSippyPipeStateBatched([HelloSippyPipeState(self.tts_engine, r) for r in wis], self.tts_engine))
+                cohort = self._new_cohort(wis)
+                if cohort is not None:
+                    cohorts.append(cohort)
             if not cohorts:
                 continue
             try:

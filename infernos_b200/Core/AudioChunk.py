@@ -46,9 +46,31 @@ class AudioChunk:
 
 class G711AudioChunk(AudioChunk):
     """8 kHz audio together with its pre-encoded G.711 payload (one byte per sample, `ename` 'PCMU' or 'PCMA').  The payload is
-    dropped by anything that changes the samples (resample), after which the chunk behaves like a plain AudioChunk."""
+    dropped by anything that changes the samples — resample(), or ASSIGNING `.audio` (what Core/OutputMuxer.py:26-27 does) —
+    after which the chunk behaves like a plain AudioChunk.  In-place edits of the tensor (`chunk.audio *= gain`) cannot be seen
+    from here: whoever does that must call drop_payload()."""
+
+    @property
+    def audio(self) -> torch.Tensor:
+        return self._audio
+
+    @audio.setter
+    def audio(self, value: torch.Tensor) -> None:
+        old = getattr(self, "_audio", None)
+        self._audio = value
+        if old is None or getattr(self, "payload", None) is None:
+            return
+        # a device / dtype move of the same samples (RTP/RTPOutputWorker.py:80 `chunk.audio = chunk.audio.to(self.device)`) keeps the
+        # payload; anything else (concatenation, gain, a different tensor) invalidates it
+        same = value.shape == old.shape and torch.equal(value.detach().to("cpu", torch.float32), old.detach().to("cpu", torch.float32))
+        if not same:
+            self.payload = None
+
+    def drop_payload(self) -> None:
+        self.payload = None
 
     def __init__(self, audio: torch.Tensor, samplerate: int, payload: bytes, ename: str = "PCMU"):
+        self.payload = None
         super().__init__(audio, samplerate)
         if samplerate != 8000:
             raise ValueError("a G.711 payload is 8 kHz audio")

@@ -51,6 +51,9 @@ class G711Codec(GenCodec):
         return engine.g711_encode(x, self._law).cpu().numpy().tobytes()
 
     def decode(self, ulaw_bytes: bytes, resample: bool = True, sample_rate: int = GenCodec.srate) -> AudioChunk:
+        if len(ulaw_bytes) == 0:                        # the reference returns an empty chunk (G711.py:36-47 on b'')
+            rate = sample_rate if resample else self.srate
+            return AudioChunk(torch.empty(0, dtype=torch.float32, device=self._dev()), rate)
         codes = torch.frombuffer(bytearray(ulaw_bytes), dtype=torch.uint8).to(self._dev())
         if resample and sample_rate != self.srate:
             if sample_rate != 16000:
@@ -58,6 +61,17 @@ class G711Codec(GenCodec):
             audio = engine.g711_decode_upsample(codes[None], self._law)[0]      # one fused kernel
             return AudioChunk(audio, sample_rate)
         return AudioChunk(engine.g711_decode(codes, self._law), self.srate)
+
+    def decode_many(self, packets, resample: bool = True, sample_rate: int = GenCodec.srate):
+        """decode() for the payloads of MANY calls at once: one staging copy, one launch, one copy back instead of
+        a `torch.tensor(list(bytes))` per packet group (RTP/InfernRTPIngest.py:63-100).  -> list of AudioChunk on the CPU, in order;
+        every packet is decoded (and resampled) on its own, exactly as len(packets) decode() calls would."""
+        up = bool(resample and sample_rate != self.srate)
+        if up and sample_rate != 16000:
+            raise RuntimeError(f"G711Codec.decode_many: resampling to {sample_rate} Hz is not on the accelerated path")
+        outs = engine.g711_decode_many(packets, self._law, upsample=up, device=self._dev())
+        rate = sample_rate if up else self.srate
+        return [AudioChunk(a, rate) for a in outs]
 
     def device(self):
         return self._dev()

@@ -34,6 +34,7 @@ from typing import Callable, List, Optional
 import torch
 
 from infernos_b200._lib import LAW_ALAW, LAW_ULAW
+from infernos_b200.Core.AudioChunk import G711AudioChunk
 from infernos_b200.engine import TTSTail
 
 
@@ -61,11 +62,15 @@ class HelloSippyPlayRequest(SessDispatchCmd):
     dispatch: Callable
 
     def __init__(self, session_id: uuid.UUID, text: str, speaker: torch.Tensor, dispatch: Callable,
-                 dispatch_g711: Optional[Callable] = None):
-        """dispatch_g711 (extension): called with the G.711 payload `bytes` of exactly the samples
-        handed to `dispatch`, encoded on the GPU in the same pass, so a single-track call can skip the CPU encoder of
-        RTP/RTPOutputWorker.py:118."""
+                 dispatch_g711: Optional[Callable] = None, pre_encoded: bool = False):
+        """Extensions, both optional:
+        dispatch_g711: called with the G.711 payload `bytes` of exactly the samples just handed to `dispatch`, encoded on the GPU
+        in the same pass.
+        pre_encoded=True: `dispatch` receives a G711AudioChunk (the same 1-D CPU tensor as `.audio` + those bytes as `.payload`)
+        instead of the bare tensor, which TTSSndDispatch / the payload-aware OutputMuxer / G711Codec.encode carry to the RTP
+        packetiser without a second encode (RTP/RTPOutputWorker.py:118).  End of sentence is `dispatch(None)` either way."""
         self.text, self.speaker, self.dispatch, self.dispatch_g711 = text, speaker, dispatch, dispatch_g711
+        self.pre_encoded = pre_encoded
         super().__init__(session_id)
 
 
@@ -79,6 +84,7 @@ class HelloSippyPipeState:
     def __init__(self, pp: "HelloSippyRTPipe", req: HelloSippyPlayRequest):
         self.session, self.dispatch = req.session, req.dispatch
         self.dispatch_g711 = getattr(req, "dispatch_g711", None)
+        self.pre_encoded = bool(getattr(req, "pre_encoded", False))
         text = req.text if pp.cleanup_text is None else pp.cleanup_text(req.text)
         self.text = text
         self.inputs = pp.frontend.tokenize(text)
@@ -98,6 +104,7 @@ class HelloSippyPipeStateBatched:
     def merge(self, states: List[HelloSippyPipeState], pp: "HelloSippyRTPipe"):
         self.dispatch = [s.dispatch for s in states]
         self.dispatch_g711 = [getattr(s, "dispatch_g711", None) for s in states]
+        self.pre_encoded = [bool(getattr(s, "pre_encoded", False)) for s in states]
         self.sessions = [s.session for s in states]
         self.starts_at = torch.cat([s.starts_at for s in states])      # host tensors: no per-session sync later
         self.ends_at = torch.cat([s.ends_at for s in states])
@@ -180,7 +187,9 @@ class SpeechT5Frontend:
         pad = lambda t: torch.nn.functional.pad(t, (0, n - t.size(1)))
         state.inputs = torch.cat([pad(s.inputs) for s in states]).to(dev)
         state.encoder_attention_mask = torch.cat([pad(s.encoder_attention_mask) for s in states]).to(dev)
-        state.speaker_embeddings = torch.cat([s.speaker_embeddings for s in states]).to(dev)
+        # the reference casts every speaker vector with maybe_half() (:57,75); the x-vectors and the engine default are fp32
+        mdt = next(self.model.parameters()).dtype
+        state.speaker_embeddings = torch.cat([s.speaker_embeddings for s in states]).to(device=dev, dtype=mdt)
         enc = self.model.speecht5.encoder(input_values=state.inputs, attention_mask=state.encoder_attention_mask, return_dict=True)
         state.encoder_last_hidden_state = enc.last_hidden_state
         state.output_sequence = enc.last_hidden_state.new_zeros(state.inputs.size(0), 1, self.num_mel_bins)
@@ -386,8 +395,10 @@ class HelloSippyRTPipe:
         stepsize = 256 * 2 // sr_rr
         with self.cuda_lock:
             audio = state.audio.cpu()                       # one D2H for the whole batch
-            want_bytes = state.g711 is not None and any(cb is not None for cb in getattr(state, "dispatch_g711", []))
+            pre_enc = getattr(state, "pre_encoded", None) or [False] * len(state.dispatch)
+            want_bytes = state.g711 is not None and (any(cb is not None for cb in getattr(state, "dispatch_g711", [])) or any(pre_enc))
             g711 = state.g711.cpu().numpy() if want_bytes else None
+            ename = "PCMA" if self.law == LAW_ALAW else "PCMU"
             asize = audio.size(1)
             starts, ends = state.starts_at.tolist(), state.ends_at.tolist()
             for i, dispatch in enumerate(state.dispatch):
@@ -397,7 +408,10 @@ class HelloSippyRTPipe:
                 endoff = min(asize, asize - ((state.idx - ends[i]) * stepsize if ends[i] >= 0 else 0))
                 assert startoff <= endoff
                 if startoff != endoff:
-                    dispatch(audio[i][startoff:endoff])
+                    if g711 is not None and pre_enc[i]:
+                        dispatch(G711AudioChunk(audio[i][startoff:endoff], self.output_sr, g711[i, startoff:endoff].tobytes(), ename))
+                    else:
+                        dispatch(audio[i][startoff:endoff])
                     if g711 is not None and state.dispatch_g711[i] is not None:
                         state.dispatch_g711[i](g711[i, startoff:endoff].tobytes())
                 if 0 <= ends[i] <= end_idx:

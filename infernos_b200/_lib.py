@@ -37,6 +37,8 @@ SIGNATURES = {
     "b2_postnet_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "b2_tts_tail2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2_tts_tail_host2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b2_ctx_poll_errors": (c_int, [c_void_p, c_void_p]),
+    "b2_debug_set_taps": (c_int, [c_void_p, c_void_p]),
     "b2_session_reset": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "b2_session_get_pre_frames": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "b2_session_set_pre_frames": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
@@ -48,6 +50,8 @@ SIGNATURES = {
     "b2_resample_g711_encode": (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_void_p, c_void_p]),
     "b2_g711_decode_upsample": (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_void_p, c_void_p]),
     "b2_resample_1to2": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "b2_g711_decode_ragged": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),
+    "b2_g711_decode_many_host": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),
     "b2_conv1d_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]),
     "b2_conv1d_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]),
     "b2_resblock_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -218,14 +218,29 @@ int launch_conv_post(const float *in, const float *wt, const float *bias, float 
 // ---------------------------------------------------------------------------------------------------
 // window builder: one CTA per session
 // ---------------------------------------------------------------------------------------------------
+// Slot ids arrive from the caller in device memory, so they are checked HERE: an id outside [0, max_sessions) would read and
+// write pre_pool out of bounds, and the same id twice in one call races the read of pre[] against its overwrite.  A bad session
+// gets zero pre_frames, writes nothing back and raises bit 0 (range) / bit 1 (duplicate) of *err_flag (host-mapped memory that
+// the C-ABI reads after the stream has been synchronised, tail.cu:poll_slot_errors).  claim[slot] holds the epoch (one per launch) of the
+// last call that used the slot.
 __global__ void __launch_bounds__(256) k_build_windows(const int32_t *__restrict__ slots, const float *__restrict__ mel, float *__restrict__ pre_pool,
                                                       const float *__restrict__ mean, const float *__restrict__ scale,
                                                       float *__restrict__ win_raw, float *__restrict__ win_norm, __nv_bfloat16 *__restrict__ win_norm_b,
-                                                      int B, int nframes) {
+                                                      int B, int nframes, int max_sessions, unsigned *__restrict__ claim, unsigned epoch,
+                                                      int *__restrict__ err_flag) {
     const int nwin = nframes / 8;
+    __shared__ int s_ok;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         const int slot = slots[b];
-        float *pre = pre_pool + (long long)slot * 320;
+        if (threadIdx.x == 0) {
+            int ok = 1;
+            if (slot < 0 || slot >= max_sessions) { ok = 0; atomicOr(err_flag, 1); }
+            else if (claim && atomicExch(claim + slot, epoch) == epoch) { ok = 0; atomicOr(err_flag, 2); }
+            s_ok = ok;
+        }
+        __syncthreads();
+        const bool ok = s_ok != 0;
+        float *pre = pre_pool + (long long)(ok ? slot : 0) * 320;
         const float *m = mel + (long long)b * nframes * 80;
         const long long wbase = (long long)b * nwin * 960;
         // spec frame f (0 .. nframes+3): f < 4 -> pre[f], else mel[f-4]; window i covers frames 8i .. 8i+11
@@ -233,7 +248,7 @@ __global__ void __launch_bounds__(256) k_build_windows(const int32_t *__restrict
             const int i = e / 960, rem = e - i * 960;
             const int fr = rem / 80, bin = rem - fr * 80;
             const int f = 8 * i + fr;
-            const float v = (f < 4) ? pre[f * 80 + bin] : m[(f - 4) * 80 + bin];
+            const float v = (f < 4) ? (ok ? pre[f * 80 + bin] : 0.0f) : m[(f - 4) * 80 + bin];
             win_raw[wbase + e] = v;
             const float nv = __fdiv_rn(v - mean[bin], scale[bin]);
             win_norm[wbase + e] = nv;
@@ -243,15 +258,17 @@ __global__ void __launch_bounds__(256) k_build_windows(const int32_t *__restrict
             for (int e = threadIdx.x; e < nwin * 12 * 48; e += blockDim.x)
                 win_norm_b[((long long)b * nwin * 12 + e / 48) * 128 + 80 + e % 48] = __float2bfloat16_rn(0.0f);
         __syncthreads();   // every read of pre[] is done before it is overwritten
-        for (int e = threadIdx.x; e < 320; e += blockDim.x) pre[e] = m[(nframes - 4) * 80 + e];
+        if (ok)
+            for (int e = threadIdx.x; e < 320; e += blockDim.x) pre[e] = m[(nframes - 4) * 80 + e];
         __syncthreads();
     }
 }
 
 int launch_build_windows(const int32_t *slots, const float *mel, float *pre_pool, const float *mean, const float *scale,
-                         float *win_raw, float *win_norm, __nv_bfloat16 *win_norm_b, int B, int nframes, cudaStream_t st) {
+                         float *win_raw, float *win_norm, __nv_bfloat16 *win_norm_b, int B, int nframes,
+                         int max_sessions, unsigned *claim, unsigned epoch, int *err_flag, cudaStream_t st) {
     if (B <= 0) return 0;
-    k_build_windows<<<B, 256, 0, st>>>(slots, mel, pre_pool, mean, scale, win_raw, win_norm, win_norm_b, B, nframes);
+    k_build_windows<<<B, 256, 0, st>>>(slots, mel, pre_pool, mean, scale, win_raw, win_norm, win_norm_b, B, nframes, max_sessions, claim, epoch, err_flag);
     B2_LAUNCH_OK("k_build_windows");
     return 0;
 }

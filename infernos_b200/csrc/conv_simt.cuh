@@ -35,8 +35,10 @@ int launch_conv_post(const float *in, const float *wt, const float *bias, float 
 // frames back into the session's slot.  Writes the raw windows (chunker input) and the normalised ones
 // ((x - mean) / scale, modeling_speecht5.py:3055-3056), both [B*nwin][12][80], window index = b*nwin + i.
 // win_norm_b (optional): the normalised windows again as bf16 rows padded to 128 bins (operand of conv_pre on tensor cores)
+// Slot ids are validated on the device: see k_build_windows (claim: [max_sessions] epochs, err_flag: host-mapped int).
 int launch_build_windows(const int32_t *slots, const float *mel, float *pre_pool, const float *mean, const float *scale,
-                         float *win_raw, float *win_norm, __nv_bfloat16 *win_norm_b, int B, int nframes, cudaStream_t st);
+                         float *win_raw, float *win_norm, __nv_bfloat16 *win_norm_b, int B, int nframes,
+                         int max_sessions, unsigned *claim, unsigned epoch, int *err_flag, cudaStream_t st);
 // plain normalisation for the stand-alone vocoder callable: out = (mel - mean) / scale, n rows of 80
 int launch_normalise(const float *mel, const float *mean, const float *scale, float *out, __nv_bfloat16 *out_b, size_t rows, cudaStream_t st);
 

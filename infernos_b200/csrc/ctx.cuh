@@ -92,7 +92,14 @@ struct b2_ctx {
     bool has_postnet = false;
     b2::Layer pn[5];
 
-    float *pre_pool = nullptr;                         // [max_sessions][4][80]
+    float *pre_pool = nullptr;                         // [max_sessions + 1][4][80]; the extra slot is the padding session of graph buckets
+    // device-side validation of caller-supplied slot ids (k_build_windows): claim[slot] = epoch of the last launch that used it
+    unsigned *claim = nullptr;                         // [max_sessions + 1]
+    unsigned epoch = 0;
+    int *err_flag_h = nullptr, *err_flag_d = nullptr;  // one host-mapped int: bit 0 slot out of range, bit 1 duplicate slot in a call
+    // debug taps of the vocoder's stage boundaries (b2_debug_set_taps): conv_pre, up0, stage0, up1, stage1, up2, stage2, up3, stage3
+    float *taps[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     b2::Workspace ws;
     size_t host_stage_cap_sessions = 0, host_stage_cap_frames = 0;
+    std::vector<uint8_t> host_seen;                    // scratch of the host-side slot check
 };

@@ -286,8 +286,12 @@ static int finalize(b2_ctx *c) {
         if (bf) { if (dev_alloc(c, &ws.pn_inb, F * 128) || dev_alloc(c, &ws.pn_b0, F * 256) || dev_alloc(c, &ws.pn_b1, F * 256)) return 1; }
         else { if (dev_alloc(c, &ws.pn_f0, F * 256) || dev_alloc(c, &ws.pn_f1, F * 256)) return 1; }
     }
-    if (dev_alloc(c, &c->pre_pool, (size_t)c->max_sessions * 320)) return 1;
-    B2_CUDA_OK(cudaMemset(c->pre_pool, 0, (size_t)c->max_sessions * 320 * sizeof(float)));
+    if (dev_alloc(c, &c->pre_pool, (size_t)(c->max_sessions + 1) * 320) || dev_alloc(c, &c->claim, (size_t)c->max_sessions + 1)) return 1;
+    B2_CUDA_OK(cudaMemset(c->pre_pool, 0, (size_t)(c->max_sessions + 1) * 320 * sizeof(float)));
+    B2_CUDA_OK(cudaMemset(c->claim, 0, ((size_t)c->max_sessions + 1) * sizeof(unsigned)));
+    B2_CUDA_OK(cudaHostAlloc((void **)&c->err_flag_h, sizeof(int), cudaHostAllocMapped));
+    *c->err_flag_h = 0;
+    B2_CUDA_OK(cudaHostGetDevicePointer((void **)&c->err_flag_d, c->err_flag_h, 0));
     c->voc_raw.clear();
     c->chk_raw.clear();
     c->pn_raw.clear();
@@ -315,10 +319,18 @@ static ConvArgs conv_args(const Layer &l, const float *in, float *out, int W, in
         if (_rc) return 1;                   \
     } while (0)
 
+// copies a stage-boundary tensor to the caller's debug buffer when one is set (b2_debug_set_taps); channels-last [W][T][C] fp32
+static int tap(b2_ctx *c, int k, const float *src, size_t n, cudaStream_t st) {
+    if (!c->taps[k]) return 0;
+    B2_CUDA_OK(cudaMemcpyAsync(c->taps[k], src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 static int vocoder_fp32(b2_ctx *c, const float *xn, int W, int T, float *audio, cudaStream_t st) {
     Workspace &ws = c->ws;
     ConvArgs a = conv_args(c->conv_pre, xn, ws.c0, W, T, T, 1.0f);
     PROF(PC_CONV_F32, launch_conv_simt(a, st));
+    if (tap(c, 0, ws.c0, (size_t)W * T * 512, st)) return 1;
     const float *stage_in = ws.c0;
     float *sbuf[2] = {ws.s0, ws.s1};
     int Tc = T;
@@ -327,6 +339,7 @@ static int vocoder_fp32(b2_ctx *c, const float *xn, int W, int T, float *audio, 
         a = conv_args(c->up[i], stage_in, ws.h, W, Tc, Tc, 0.1f);
         PROF(PC_CONV_F32, launch_conv_simt(a, st));
         Tc *= 4;
+        if (tap(c, 1 + 2 * i, ws.h, (size_t)W * Tc * STAGE_C[i], st)) return 1;
         float *S = sbuf[i & 1];
         for (int j = 0; j < 3; j++) {
             for (int d = 0; d < 3; d++) {
@@ -340,6 +353,7 @@ static int vocoder_fp32(b2_ctx *c, const float *xn, int W, int T, float *audio, 
                 PROF(PC_CONV_F32, launch_conv_simt(a, st));
             }
         }
+        if (tap(c, 2 + 2 * i, S, (size_t)W * Tc * STAGE_C[i], st)) return 1;
         stage_in = S;
     }
     PROF(PC_CONV_POST, launch_conv_post(stage_in, c->post_w, c->post_b, audio, W, Tc, st));
@@ -368,6 +382,7 @@ static int vocoder_bf16(b2_ctx *c, const float *xn, int W, int T, float *audio, 
         u.in = stage_in; u.layer = &c->up[i]; u.out32 = ws.h; u.outb = fused ? nullptr : ws.hb; u.outb_slope = 0.1f; u.W = W; u.T = Tc;
         PROF(PC_CONV_TC, launch_conv_umma(u, st));
         Tc *= 4;
+        if (tap(c, 1 + 2 * i, ws.h, (size_t)W * Tc * STAGE_C[i], st)) return 1;
         if (fused) {
             // MRF mean (modeling_speecht5.py:3069-3072): s0 = rb0(x); s0 += rb1(x); (s0 + rb2(x)) / 3
             for (int j = 0; j < 3; j++) {
@@ -506,8 +521,10 @@ static int postnet_fwd(b2_ctx *c, const float *d_in, int B, int T, float *d_out,
     return 0;
 }
 
+// check_dups: duplicate-slot detection through claim[] (needs a fresh epoch per launch, so it is off inside captured graphs, whose
+// callers validate on the host); pad_slot_ok: slot id max_sessions (the padding session of a graph bucket) is legal
 static int tail_device(b2_ctx *c, const int32_t *d_slots, const float *d_mel, int B, int nframes, int law, bool apply_postnet,
-                       uint8_t *d_g711, float *d_audio, cudaStream_t st) {
+                       uint8_t *d_g711, float *d_audio, cudaStream_t st, bool check_dups = true, bool pad_slot_ok = false) {
     const int nwin = nframes / 8;
     const int sess_per_pass = std::max(1, c->max_windows / nwin);
     const size_t Lout = (size_t)nframes * 128;
@@ -521,7 +538,8 @@ static int tail_device(b2_ctx *c, const int32_t *d_slots, const float *d_mel, in
             mel = ws.pn_mel;
         }
         PROF(PC_OTHER, launch_build_windows(d_slots + b0, mel, c->pre_pool, c->mean, c->scale,
-                                            ws.win_raw, ws.win_norm, ws.win_norm_b, nb, nframes, st));
+                                            ws.win_raw, ws.win_norm, ws.win_norm_b, nb, nframes,
+                                            c->max_sessions + (pad_slot_ok ? 1 : 0), check_dups ? c->claim : nullptr, ++c->epoch, c->err_flag_d, st));
         if (vocoder_any(c, ws.win_norm, W, 12, ws.audio, st)) return 1;
         if (c->cwm) { if (chunker_fwd(c, ws.win_raw, ws.audio, W, ws.audio16k, st)) return 1; }
         else { PROF(PC_OTHER, launch_trim(ws.audio, ws.audio16k, W, 3072, 512, 2048, st)); }
@@ -575,6 +593,7 @@ void b2_ctx_destroy(b2_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (void *p : c->allocs) cudaFree(p);
+    if (c->err_flag_h) cudaFreeHost(c->err_flag_h);
     for (int i = 0; i < 4; i++) {
         umma_free_layer(c->up[i]);
         for (int j = 0; j < 3; j++)
@@ -688,6 +707,30 @@ int b2_postnet_forward(b2_ctx *c, const float *d_in, int B, int T, float *d_out,
     return 0;
 }
 
+// Reads (and clears) what k_build_windows has flagged so far.  The flag is host-mapped memory written by the kernel, so it is
+// only complete for work the caller has synchronised with; b2_ctx_poll_errors synchronises the stream first.
+static int poll_slot_errors(b2_ctx *c, const char *who) {
+    if (!c->err_flag_h) return 0;
+    const int f = *(volatile int *)c->err_flag_h;
+    if (!f) return 0;
+    *(volatile int *)c->err_flag_h = 0;
+    return set_error("%s: a tail call on this context was given %s%s%s (valid ids: 0 .. %d, each at most once per call); those sessions were computed "
+                     "with zero pre_frames and their state was not updated", who, (f & 1) ? "a slot id outside the session pool" : "",
+                     (f & 3) == 3 ? " and " : "", (f & 2) ? "the same slot id more than once" : "", c->max_sessions - 1);
+}
+
+int b2_ctx_poll_errors(b2_ctx *c, void *stream) {
+    CTX_GUARD(c);
+    B2_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    return poll_slot_errors(c, "b2_ctx_poll_errors");
+}
+
+int b2_debug_set_taps(b2_ctx *c, float *const *d_taps) {
+    if (!c) return set_error("null context");
+    for (int i = 0; i < 9; i++) c->taps[i] = d_taps ? d_taps[i] : nullptr;
+    return 0;
+}
+
 int b2_tts_tail(b2_ctx *c, const int32_t *d_slots, const float *d_mel, int B, int nframes, int law,
                 uint8_t *d_g711, float *d_audio, void *stream) {
     return b2_tts_tail2(c, d_slots, d_mel, B, nframes, law, 0, d_g711, d_audio, stream);
@@ -705,6 +748,7 @@ int b2_tts_tail2(b2_ctx *c, const int32_t *d_slots, const float *d_mel, int B, i
     if (!d_slots || !d_mel) return set_error("b2_tts_tail: null input");
     if (d_g711 && law != B2_LAW_ULAW && law != B2_LAW_ALAW) return set_error("b2_tts_tail: bad law %d", law);
     if (!d_g711 && !d_audio) return set_error("b2_tts_tail: no output requested");
+    if (poll_slot_errors(c, "b2_tts_tail (reported for an EARLIER asynchronous call)")) return 1;
     return tail_device(c, d_slots, d_mel, B, nframes, law, (flags & B2_TAIL_APPLY_POSTNET) != 0, d_g711, d_audio, (cudaStream_t)stream);
 }
 
@@ -720,6 +764,15 @@ int b2_tts_tail_host2(b2_ctx *c, const int32_t *h_slots, const float *h_mel, int
     if (B < 0 || nframes < 8 || nframes % 8) return set_error("b2_tts_tail_host: nframes must be a positive multiple of 8 (got %d)", nframes);
     if (B == 0) return 0;
     if (!h_slots || !h_mel || (!h_g711 && !h_audio)) return set_error("b2_tts_tail_host: null pointer");
+    {
+        // the slot ids are in host memory here: reject bad ones before anything is launched
+        c->host_seen.assign((size_t)c->max_sessions, 0);
+        for (int i = 0; i < B; i++) {
+            const int s = h_slots[i];
+            if (s < 0 || s >= c->max_sessions) return set_error("b2_tts_tail_host: slot %d (session %d of the call) is outside the pool of %d", s, i, c->max_sessions);
+            if (c->host_seen[(size_t)s]++) return set_error("b2_tts_tail_host: slot %d appears more than once in the call", s);
+        }
+    }
     cudaStream_t st = (cudaStream_t)stream;
     Workspace &ws = c->ws;
     const size_t nout = (size_t)B * nframes * 128;
@@ -727,6 +780,14 @@ int b2_tts_tail_host2(b2_ctx *c, const int32_t *h_slots, const float *h_mel, int
         // grow-only staging buffers (not counted per call: steady state allocates nothing)
         B2_CUDA_OK(cudaStreamSynchronize(st));
         const size_t cs = std::max<size_t>(B, c->host_stage_cap_sessions), cf = std::max<size_t>((size_t)B * nframes, c->host_stage_cap_frames);
+        void *old[4] = {ws.slots, ws.mel_in, ws.g711_out, ws.audio8k_out};
+        for (void *q : old) {
+            if (!q) continue;
+            cudaFree(q);
+            c->allocs.erase(std::remove(c->allocs.begin(), c->allocs.end(), q), c->allocs.end());
+        }
+        ws.slots = nullptr; ws.mel_in = nullptr; ws.g711_out = nullptr; ws.audio8k_out = nullptr;
+        c->host_stage_cap_sessions = c->host_stage_cap_frames = 0;
         if (dev_alloc(c, &ws.slots, cs) || dev_alloc(c, &ws.mel_in, cf * 80) || dev_alloc(c, &ws.g711_out, cf * 128) ||
             dev_alloc(c, &ws.audio8k_out, cf * 128)) return 1;
         c->host_stage_cap_sessions = cs; c->host_stage_cap_frames = cf;
@@ -737,7 +798,7 @@ int b2_tts_tail_host2(b2_ctx *c, const int32_t *h_slots, const float *h_mel, int
     if (h_g711) B2_CUDA_OK(cudaMemcpyAsync(h_g711, ws.g711_out, nout, cudaMemcpyDeviceToHost, st));
     if (h_audio) B2_CUDA_OK(cudaMemcpyAsync(h_audio, ws.audio8k_out, nout * sizeof(float), cudaMemcpyDeviceToHost, st));
     B2_CUDA_OK(cudaStreamSynchronize(st));
-    return 0;
+    return poll_slot_errors(c, "b2_tts_tail_host");
 }
 
 static int single_layer(const void *d_in, const float *h_weight, const float *h_bias, int W, int T, int Cin, int Cout, int k, int dil,

@@ -180,6 +180,35 @@ class TTSTail:
                                                  out_audio.data_ptr() if out_audio is not None else None,
                                                  _stream_ptr(self.device)), "tts_tail_host")
 
+    def poll_errors(self) -> None:
+        """Synchronises the current stream and raises if an earlier asynchronous tail call was handed a slot id outside the pool or
+        twice in one call (the device-side check of k_build_windows)."""
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_ctx_poll_errors(self.ctx, _stream_ptr(self.device)), "poll_errors")
+
+    TAP_NAMES = ("conv_pre", "up0", "stage0", "up1", "stage1", "up2", "stage2", "up3", "stage3")
+    TAP_CH = (512, 256, 256, 128, 128, 64, 64, 32, 32)
+    TAP_UP = (1, 4, 4, 16, 16, 64, 64, 256, 256)
+
+    def vocoder_with_taps(self, spectrogram: torch.Tensor, names: Sequence[str] = TAP_NAMES):
+        """vocoder() plus the fp32 stage-boundary tensors of modeling_speecht5.py:3062-3072, returned channel-FIRST (W, C, T_stage)
+        like the torch module's own intermediates (the library keeps them channels-last).  Parity-test hook (BASELINE config 2)."""
+        x = _require_cuda(spectrogram.to(torch.float32), torch.float32, "spectrogram")
+        W, T, _ = x.shape
+        if W * T > 12 * self.max_windows:
+            raise RuntimeError("vocoder_with_taps: the call must fit one sub-batch (W*T <= 12*max_windows)")
+        bufs, ptrs = {}, (ctypes.c_void_p * 9)()
+        for i, n in enumerate(self.TAP_NAMES):
+            if n in names:
+                bufs[n] = torch.empty(W, T * self.TAP_UP[i], self.TAP_CH[i], device=x.device, dtype=torch.float32)
+                ptrs[i] = bufs[n].data_ptr()
+        _lib.check(self.lib.b2_debug_set_taps(self.ctx, ptrs), "debug_set_taps")
+        try:
+            audio = self.vocoder(x)
+        finally:
+            _lib.check(self.lib.b2_debug_set_taps(self.ctx, None), "debug_set_taps")
+        return audio, {n: b.transpose(1, 2) for n, b in bufs.items()}
+
     def profile_begin(self) -> None:
         _lib.check(self.lib.b2_profile_begin(self.ctx), "profile_begin")
 
@@ -319,6 +348,33 @@ def g711_decode_upsample(codes: torch.Tensor, law: int = LAW_ULAW) -> torch.Tens
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().b2_g711_decode_upsample(rows.data_ptr(), rows.size(0), L, law, out.data_ptr(), _stream_ptr(x.device)), "g711_decode_upsample")
     return out.reshape(tuple(shape[:-1]) + (2 * L,))
+
+
+def g711_decode_many(packets: Sequence[bytes], law: int = LAW_ULAW, upsample: bool = False, device=None) -> list:
+    """Batched inbound decode: the RTP payloads of any number of calls -> one pinned staging buffer, one H2D,
+    one kernel launch, one D2H.  Returns a list of 1-D fp32 CPU tensors (views of one pinned buffer), 8 kHz or, with upsample, 16 kHz,
+    each packet zero-padded on its own like the reference's per-call G711Codec.decode (Core/Codecs/G711.py:34-47)."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("g711_decode_many needs a CUDA device (no CPU fallback)")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    n = len(packets)
+    if n == 0:
+        return []
+    lens = torch.tensor([len(p) for p in packets], dtype=torch.int64)
+    offs = torch.zeros(n + 1, dtype=torch.int64)
+    torch.cumsum(lens, 0, out=offs[1:])
+    total = int(offs[-1])
+    mul = 2 if upsample else 1
+    out = torch.empty(total * mul, dtype=torch.float32).pin_memory()
+    if total:
+        src = torch.frombuffer(bytearray(b"".join(packets)), dtype=torch.uint8).pin_memory()
+        ensure_taps(dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.b2_g711_decode_many_host(src.data_ptr(), offs.data_ptr(), n, law, 1 if upsample else 0, out.data_ptr(), _stream_ptr(dev)),
+                       "g711_decode_many_host")
+    o = (offs * mul).tolist()
+    return [out[o[i]:o[i + 1]] for i in range(n)]
 
 
 def kernel_launch_count() -> int:

@@ -151,6 +151,35 @@ def test_round_trip_properties_at_full_size(eng, law):
     assert torch.equal(torch.cat([eng.g711_encode(x[:h], law), eng.g711_encode(x[h:], law)]), codes)
 
 
+@pytest.mark.parametrize("law", [0, 1])
+@pytest.mark.parametrize("up", [False, True])
+def test_decode_many_ragged_and_uniform_bit_exact_vs_oracle(eng, oc, taps, law, up):
+    """the packets of many calls in one staging copy + one launch; every packet is decoded / resampled on its own
+    (per-packet zero padding), exactly like one G711Codec.decode per packet."""
+    from infernos_b200.Core.Codecs.G711 import G711ACodec, G711Codec
+    rng = np.random.default_rng(17 + law)
+
+    def ref_one(b):
+        x8 = oc.decode_f32(np.frombuffer(b, dtype=np.uint8)[None], law)
+        return (oc.resample_1to2(x8, taps["up"]) if up else x8)[0]
+    for lens in ([160] * 257, [160, 80, 0, 1, 7, 333, 160, 1024, 3, 160, 800, 5]):       # uniform (flat kernel) / ragged, incl. empty
+        pk = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+        l0 = eng.kernel_launch_count()
+        got = eng.g711_decode_many(pk, law, upsample=up)
+        assert eng.kernel_launch_count() - l0 == 1                                       # one launch for all packets
+        assert len(got) == len(pk)
+        for b, g in zip(pk, got):
+            r = ref_one(b) if len(b) else np.empty(0, np.float32)
+            assert g.shape == r.shape and np.array_equal(g.numpy(), r)
+    codec = (G711ACodec if law else G711Codec)().to("cuda:0")
+    pk = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (160, 160, 320)]
+    many = codec.decode_many(pk, sample_rate=16000 if up else 8000)
+    for b, ch in zip(pk, many):
+        one = codec.decode(b, sample_rate=16000 if up else 8000)
+        assert ch.samplerate == one.samplerate and np.array_equal(ch.audio.numpy(), one.audio.cpu().numpy())
+    assert codec.decode(b"").audio.numel() == 0 and eng.g711_decode_many([]) == []
+
+
 def test_empty_inputs(eng):
     assert eng.g711_encode(torch.empty(0, device="cuda")).numel() == 0
     assert eng.resample_g711_encode(torch.empty(0, 64, device="cuda")).shape == (0, 32)

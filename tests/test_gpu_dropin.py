@@ -71,6 +71,60 @@ def test_engine_replays_real_infer(fused):
             assert bytes(payload[i]) == ocodec.encode_f32(full, 0).tobytes()
 
 
+def test_pre_encoded_dispatch_reaches_the_packetiser_without_an_encode(monkeypatch):
+    """SURVEY 8 f1 end to end on the GPU: engine -> dispatch(G711AudioChunk) -> TTSSndDispatch -> soundout -> payload-aware OutputMTMuxer
+    -> G711Codec.encode (pass-through) -> 160-byte packets == G.711 codes of the dispatched samples, with zero encode calls."""
+    import queue
+    from infernos_b200 import engine
+    from infernos_b200.Cluster.TTSSession import TTSSndDispatch
+    from infernos_b200.Core.AudioChunk import G711AudioChunk
+    from infernos_b200.Core.Codecs.G711 import G711Codec
+    from infernos_b200.Core.OutputMuxer import OutputMTMuxer
+    from infernos_b200.HelloSippyTTSRT.HelloSippyRTPipe import HelloSippyPipeState, HelloSippyPipeStateBatched, HelloSippyPlayRequest, HelloSippyRTPipe
+    from oracle import codec as ocodec
+    d = np.load(os.path.join(G, "infer_golden.npz"))
+    B = d["plan"].shape[0]
+    pp = HelloSippyRTPipe("cuda:0", output_sr=8000, **_engine_kwargs(d))
+    codec = G711Codec().to("cuda:0")
+    qs = [queue.Queue() for _ in range(B)]
+    samples = [[] for _ in range(B)]
+
+    def soundout(i):
+        def f(chunk):
+            if isinstance(chunk, G711AudioChunk):
+                samples[i].append(chunk.audio.clone())
+                chunk.audio = chunk.audio.to("cpu")                     # RTPOutputWorker.soundout's device move (:80)
+            qs[i].put(chunk)
+        return f
+    disp = [TTSSndDispatch(soundout(i), 8000) for i in range(B)]
+    reqs = [HelloSippyPlayRequest(uuid.uuid4(), "hello", pp.get_voice(0), disp[i].sound_dispatch, pre_encoded=True) for i in range(B)]
+    state = HelloSippyPipeStateBatched([HelloSippyPipeState(pp, r) for r in reqs], pp)
+    while True:
+        pp.infer(state)
+        if not pp.unbatch_and_dispatch(state):
+            break
+    monkeypatch.setattr(engine, "g711_encode", lambda *a, **k: (_ for _ in ()).throw(AssertionError("encode ran")))
+    for i in range(B):
+        mix, packets = OutputMTMuxer(8000, 800, "cpu"), []
+        while True:
+            try:
+                mix.chunk_in(qs[i].get(block=False))
+                continue
+            except queue.Empty:
+                q = mix.idle(None)
+                if q is None:
+                    break
+            by = codec.encode(q)
+            while len(by) >= 160:
+                packets.append(by[:160])
+                by = by[160:]
+        full = torch.cat(samples[i]).numpy()
+        assert full.shape == d[f"session{i}_audio"].shape
+        want = ocodec.encode_f32(full, 0).tobytes()
+        got = b"".join(packets)
+        assert len(got) >= (len(want) // 800) * 800 and got == want[:len(got)]
+
+
 def test_worker_thread_end_to_end_and_codec():
     from infernos_b200.Cluster.InfernTTSWorker import InfernTTSWorker
     from infernos_b200.Core.Codecs.G711 import G711ACodec, G711Codec
@@ -101,7 +155,8 @@ def test_worker_thread_end_to_end_and_codec():
         ref = d[f"session{i}_audio"]
         assert full.numel() == ref.shape[0]
         snr = 10 * np.log10((ref ** 2).sum() / ((ref - full.numpy()) ** 2).sum())
-        assert snr >= 39.0
+        print(f'worker end-to-end bf16 SNR session {i}: {snr:.2f} dB')
+        assert snr >= 40.0        # north_star's bf16 bar, on the dispatched 8 kHz audio
         by = codec.encode(full)                           # RTPOutputWorker's call (RTP/RTPOutputWorker.py:118)
         assert isinstance(by, bytes) and len(by) == full.numel()
         assert by == ocodec.encode_f32(full.numpy(), 0).tobytes()

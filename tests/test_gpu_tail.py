@@ -146,7 +146,8 @@ def test_tail_bf16_snr_and_state(tail16):
     d, audios, codes, _ = _replay(tail16, law=1)
     ref = np.stack([d["audio"][c] for c in range(len(audios))])
     got = np.stack([a.numpy() for a in audios])
-    assert snr(ref, got) >= BF16_SNR_DB - 1.0        # after the chunker's tanh(gain * x) and the resampler
+    print("bf16 tail SNR (after the chunker's tanh(gain * x) and the resampler) vs the real fp32 infer(): %.2f dB" % snr(ref, got))
+    assert snr(ref, got) >= BF16_SNR_DB
     # pre_frames carried per session = last four mel frames of the last call
     last = d["plan"][:, 32 * len(audios) - 4:32 * len(audios)]
     for b, slot in enumerate([5, 0, 9]):
