@@ -200,6 +200,108 @@ def main_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------- serving-loop legs
+def _poll_all(sched, want, out_rows, stop_evt=None, timeout_s=120.0):
+    """Consumer: drains completions into out_rows (numpy structured arrays) until `want` chunks have arrived."""
+    import numpy as np
+    from infernos_b200.engine import _Completion
+    dt = np.dtype([("tag", "u8"), ("t_enq", "i8"), ("t_launch", "i8"), ("t_done", "i8"), ("off", "i8"), ("slot", "i4"), ("nbytes", "i4"),
+                   ("bs", "i4"), ("pad", "i4")])
+    assert dt.itemsize == __import__("ctypes").sizeof(_Completion)
+    n, t0 = 0, time.time()
+    while n < want and time.time() - t0 < timeout_s and not (stop_evt is not None and stop_evt.is_set() and n >= want):
+        recs, _ = sched.poll(timeout_ms=20, want_bytes=True)
+        if len(recs):
+            out_rows.append(np.frombuffer(sched._recs, dtype=dt, count=len(recs)).copy())
+            n += len(recs)
+    return n
+
+
+def run_e2e_pipelined(tail, slots_h, mel_h, steps, warmup):
+    """e2e through the serving loop with HOST buffers: every step's mel is copied H2D from pinned staging and its G.711 bytes D2H into
+    pinned memory inside the timed region; step n+1's copy-in overlaps step n's compute (two sub-batches in flight)."""
+    import numpy as np
+    from infernos_b200.engine import TailScheduler
+    S, F = mel_h.size(0), mel_h.size(1)
+    sched = TailScheduler(tail, nframes=F, depth=2, use_graphs=True, max_batch=S, poll_capacity=max(4096, S))
+    rows = []
+    try:
+        for phase, k in (("warm", max(5, warmup)), ("timed", steps)):      # >= one step per staging buffer: each has its own graph
+            rows.clear()
+            th = threading.Thread(target=_poll_all, args=(sched, k * S, rows))
+            th.start()
+            t0 = time.monotonic_ns()
+            for _ in range(k):
+                sched.submit(slots_h, mel_h)
+            th.join()
+            r = np.concatenate(rows)
+            assert r.shape[0] == k * S, "the serving loop lost chunks"
+            ms = (int(r["t_done"].max()) - t0) / 1e6
+        st = sched.stats()
+    finally:
+        sched.close()
+    return ms, st
+
+
+def run_latency(dev, sessions, seconds, chunk_frames=8, mode="bf16", max_windows=2048, tick_ms=0.5):
+    """north_star's joint target: `sessions` concurrent real-time streams, each delivering one chunk_frames-frame mel chunk every
+    chunk period (8 frames = 128 ms), arrivals staggered uniformly over the period; latency of a chunk = its nominal arrival time ->
+    its G.711 bytes in pinned host memory.  Served by the native sub-batch scheduler (b2_sched_*)."""
+    import numpy as np
+    import torch
+    from infernos_b200 import synth
+    from infernos_b200.engine import TailScheduler, TTSTail
+    period_ns = int(chunk_frames * AUDIO_S_PER_FRAME * 1e9)
+    tail = TTSTail(dev, synth.hifigan_state_dict(), synth.chunker_state_dict(), mode=mode, max_sessions=sessions, max_windows=max_windows)
+    sched = TailScheduler(tail, nframes=chunk_frames, depth=2, use_graphs=True, poll_capacity=8192)
+    mel = synth.synth_mel(sessions, chunk_frames, seed=11).pin_memory()
+    slots = torch.arange(sessions, dtype=torch.int32)
+    phase = (np.arange(sessions, dtype=np.int64) * period_ns) // sessions          # staggered: session i arrives at phase_i + k * period
+    rows, stop = [], threading.Event()
+    nper = max(2, int(round(seconds * 1e9 / period_ns)))
+    warm_periods = 3                                                              # graph buckets get captured here; not reported
+    total = (nper + warm_periods) * sessions
+    th = threading.Thread(target=_poll_all, args=(sched, total, rows, None, seconds + 60))
+    th.start()
+    t0 = time.monotonic_ns() + 2_000_000
+    sent = 0                                                                      # chunks submitted so far, in arrival order
+    late_ticks = 0
+    try:
+        while sent < total:
+            now = time.monotonic_ns()
+            due = min(total, int((now - t0) // period_ns) * sessions + int(np.searchsorted(phase, (now - t0) % period_ns, side="right"))) if now >= t0 else 0
+            while sent < due:
+                k, i = divmod(sent, sessions)
+                j = min(sessions, i + (due - sent))
+                te = torch.from_numpy(t0 + k * period_ns + phase[i:j])
+                sched.submit(slots[i:j], mel[i:j], t_enqueue_ns=te)
+                sent += j - i
+            spent = (time.monotonic_ns() - now) / 1e6
+            if spent > 2 * tick_ms:
+                late_ticks += 1
+            time.sleep(max(0.0, (tick_ms - spent) / 1e3))
+        th.join()
+        st = sched.stats()
+    finally:
+        sched.close()
+        tail.close()
+    r = np.concatenate(rows) if rows else np.zeros(0)
+    r = r[r["t_enq"] >= t0 + warm_periods * period_ns]
+    lat = (r["t_done"] - r["t_enq"]) / 1e6
+    qd = (r["t_launch"] - r["t_enq"]) / 1e6
+    wall_s = (int(r["t_done"].max()) - int(r["t_enq"].min())) / 1e9
+    return {"sessions": sessions, "chunk_frames": chunk_frames, "chunk_period_ms": period_ns / 1e6, "chunks": int(lat.size),
+            "steps": int(st["sub_batches"]), "p50_ms": round(float(np.percentile(lat, 50)), 3), "p99_ms": round(float(np.percentile(lat, 99)), 3),
+            "p999_ms": round(float(np.percentile(lat, 99.9)), 3), "max_ms": round(float(lat.max()), 3), "mean_ms": round(float(lat.mean()), 3),
+            "queue_p99_ms": round(float(np.percentile(qd, 99)), 3),
+            "mean_sub_batch": round(st["sessions"] / max(1, st["sub_batches"]), 1), "max_sub_batch": int(st["max_sub_batch"]),
+            "padded_frac": round(st["padded_sessions"] / max(1, st["sessions"]), 4), "graphs_built": int(st["graphs_built"]),
+            "streams_sustained": round(lat.size * chunk_frames * AUDIO_S_PER_FRAME / wall_s, 1), "rtf_ok": bool(lat.max() < period_ns / 1e6),
+            "loadgen_late_ticks": late_ticks, "target_p99_ms": 20.0, "met": bool(np.percentile(lat, 99) < 20.0),
+            "definition": "latency = nominal arrival of a session's mel chunk (staggered uniformly over the chunk period) -> its G.711 bytes in "
+                          "pinned host memory; H2D and D2H inside; sub-batches formed adaptively, one CUDA graph launch each"}
+
+
 # ----------------------------------------------------------------------------------------------- GPU arm
 def main_b200(args, rank, local_rank, world):
     import torch
@@ -222,6 +324,7 @@ def main_b200(args, rank, local_rank, world):
     nwin = F // 8
     max_windows = min(S * nwin, args.max_windows)
     tail = TTSTail(dev, synth.hifigan_state_dict(), synth.chunker_state_dict(), mode=args.mode, max_sessions=S, max_windows=max_windows)
+    ctx_bytes = tail.device_bytes
     mel_h = synth.synth_mel(S, F, seed=7 + rank).pin_memory()
     slots_h = torch.arange(S, dtype=torch.int32).pin_memory()
     g_h = torch.empty(S, F * 128, dtype=torch.uint8).pin_memory()
@@ -256,7 +359,8 @@ def main_b200(args, rank, local_rank, world):
     audio_s = S * world * F * AUDIO_S_PER_FRAME * args.steps
     value = audio_s / (ms_total / 1e3)
 
-    # ---- end-to-end timing through the host-buffer entry ------------------------------------------
+    # ---- end-to-end timing with HOST buffers -----------------------------------------------------------
+    # (a) the blocking C-ABI call (b2_tts_tail_host: H2D -> tail -> D2H -> sync, nothing overlapped): what a caller pays per call
     for _ in range(min(args.warmup, 3)):
         tail.tail_host(slots_h, mel_h, g_h)
     barrier()
@@ -264,7 +368,11 @@ def main_b200(args, rank, local_rank, world):
     for _ in range(args.steps):
         tail.tail_host(slots_h, mel_h, g_h)
     torch.cuda.synchronize(dev)
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    sync_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    barrier()
+    # (b) the serving loop (b2_sched_*): the same steps from the same pinned host buffers, step n+1's H2D and step n-1's D2H under step n
+    e2e_ms, e2e_st = run_e2e_pipelined(tail, slots_h, mel_h, args.steps, min(args.warmup, 3))
+    e2e_ms = max_over_ranks(e2e_ms)
     barrier()
     e2e_value = audio_s / (e2e_ms / 1e3)
     # clocks: sampled every 100 ms across both timed regions; a short run (10 steps = 0.23 s) is extended with untimed steps of
@@ -348,6 +456,50 @@ def main_b200(args, rank, local_rank, world):
     allstats = sharding.gather_stats({"sessions": S, "steps": args.steps, "g711_bytes": S * F * 128 * args.steps,
                                       "kernel_launches": launches, "device_ms": e0.elapsed_time(e1)}, device=dev)
 
+    # ---- BASELINE config 3 as written: 1,024 calls in TOTAL, block-partitioned over the GPUs (strong scaling) ---------------------
+    strong = None
+    if not args.no_strong:
+        shapes = [args.strong_total // world] if world > 1 else [args.strong_total // g for g in (2, 4, 8)]
+        rows_s = []
+        for Ss in shapes:
+            Ss = max(1, min(Ss, S))
+            sl, ml = slots_d[:Ss].contiguous(), mel_d[:Ss].contiguous()
+            for _ in range(3):
+                tail.tail(sl, ml, want_audio=False)
+            barrier()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for a, b in evs:
+                a.record()
+                tail.tail(sl, ml, want_audio=False)
+                b.record()
+            barrier()
+            per = sorted(a.elapsed_time(b) for a, b in evs)
+            tot = max_over_ranks(evs[0][0].elapsed_time(evs[-1][1]))
+            worst = max_over_ranks(per[-1])
+            rows_s.append({"sessions_per_gpu": Ss, "sessions_total": Ss * world, "value": round(Ss * world * F * AUDIO_S_PER_FRAME * args.steps / (tot / 1e3), 1),
+                           "ms_per_step": round(tot / args.steps, 3), "call_ms_median": round(per[len(per) // 2], 3), "call_ms_max": round(worst, 3),
+                           "per_gpu_efficiency_vs_1024": round((Ss * F * AUDIO_S_PER_FRAME * args.steps / (tot / 1e3)) / (value / world), 4)})
+        strong = {"config": "BASELINE configs[2]: 1,024 concurrent calls in total, sharded by session across the GPUs (bf16)",
+                  "n_gpus": world, "rows": rows_s,
+                  "note": ("this run: one row, the shape each GPU gets at this GPU count" if world > 1 else
+                           "single GPU: the per-GPU shapes of 2 / 4 / 8 GPUs (512 / 256 / 128 sessions) timed on one GPU; there is no data-plane "
+                           "collective, so the N-GPU strong-scaling value is N x these") +
+                          "; efficiency is against this run's own 1,024-sessions-per-GPU rate; what it loses is wave quantisation of the small "
+                          "grids (stage 0/1 at 512 windows) and the fixed ~41 launches per call"}
+
+    # ---- north_star's joint target: p99 chunk latency at >= 5,000 concurrent real-time streams ---------------------------------------
+    latency = None
+    if rank == 0 and world == 1 and not args.no_latency:
+        tail.close()
+        tail = None
+        torch.cuda.empty_cache()
+        latency = []
+        for nsess in args.latency_sessions:
+            try:
+                latency.append(run_latency(dev, nsess, args.latency_seconds, mode=args.mode))
+            except Exception as e:                                      # keep the line: report what failed
+                latency.append({"sessions": nsess, "error": repr(e)[:300]})
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = run_cpu(args.ref_sessions, 5, 2, dtype=torch.bfloat16 if args.ref_dtype == "bf16" else torch.float32)
@@ -365,20 +517,25 @@ def main_b200(args, rank, local_rank, world):
                        "vocoder_msamples_per_s": round(S * world * F * 256 * args.steps / (ms_total / 1e3) / 1e6, 1)},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "streams", "h2d_bytes_per_step": int(mel_h.numel() * 4 + slots_h.numel() * 4) * world,
-                    "d2h_bytes_per_step": int(g_h.numel()) * world, "ms_per_step": round(e2e_ms / args.steps, 3)},
+                    "d2h_bytes_per_step": int(g_h.numel()) * world, "ms_per_step": round(e2e_ms / args.steps, 3),
+                    "path": "b2_sched_submit / b2_sched_poll (native serving loop): pinned H2D + one CUDA-graph launch + D2H per step, two steps in flight",
+                    "blocking_call_ms_per_step": round(sync_ms / args.steps, 3),
+                    "blocking_call_value": round(audio_s / (sync_ms / 1e3), 1)},
             "gpu_launches": int(sum(s["kernel_launches"] for s in allstats)),
             "roofline": roofline, "roofline_conv_family": family_roof, "roofline_codec": codec_roof,
             "kernel_ms_per_step": {k: round(v / psteps, 3) for k, v in ms_cls.items()},
             "cpu_baseline": cpu,
+            "latency": latency, "strong": strong,
             "per_gpu_stats": [{"sessions": int(s["sessions"]), "steps": int(s["steps"]), "g711_bytes": int(s["g711_bytes"]),
                                "device_ms": round(s["device_ms"], 3)} for s in allstats],
-            "hbm_bytes_ctx": tail.device_bytes,
+            "hbm_bytes_ctx": ctx_bytes,
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(out), flush=True)
         os.dup2(2, 1)
-    tail.close()
+    if tail is not None:
+        tail.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -396,6 +553,11 @@ def main():
     ap.add_argument("--ref-sessions", type=int, default=8, help="sessions per step of the CPU arm's bounded sample (reference: max_batch_size = 8)")
     ap.add_argument("--ref-dtype", default="bf16", choices=["bf16", "fp32"], help="precision of the CPU arm (the reference runs bf16: maybe_half)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the p99 chunk-latency legs (5,000 / 20,000 staggered real-time sessions)")
+    ap.add_argument("--latency-sessions", type=int, nargs="*", default=[5000, 20000])
+    ap.add_argument("--latency-seconds", type=float, default=3.0)
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (BASELINE config 3 as written)")
+    ap.add_argument("--strong-total", type=int, default=1024)
     ap.add_argument("--cpu-sweep", action="store_true", help="with --impl reference: fp32/bf16 x B in {1,8,64} CPU table (SURVEY 8d)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -119,6 +119,43 @@ B2_API int b2_session_reset(b2_ctx *ctx, const int32_t *h_slots, int n, void *st
 B2_API int b2_session_get_pre_frames(b2_ctx *ctx, int slot, float *h_out, void *stream);
 B2_API int b2_session_set_pre_frames(b2_ctx *ctx, int slot, const float *h_in, void *stream);
 
+/* ---- latency-bounded serving loop ---------------------------------------------------------------------------
+ * Replaces the reference's strictly serial worker loop  infer() -> unbatch_and_dispatch()  (Cluster/InfernTTSWorker.py:83-92) and the
+ * three executors its own load test overlaps generation and dispatch with (HelloSippyTTSRT/HelloSippyRTPipeTest.py:126-161).
+ * Callers submit (slot, mel chunk) pairs from any thread; a native launcher thread forms sub-batches adaptively (whatever has arrived
+ * when the pipeline has room), runs each as  pinned H2D -> ONE CUDA-graph launch of the fused tail -> D2H  on three streams with
+ * `depth` sub-batches in flight, and a completer thread stamps the time at which a chunk's G.711 bytes are in pinned host memory.
+ * The scheduler owns the context's workspaces while it exists: do not call the other b2_* entry points of `ctx` concurrently. */
+typedef struct b2_sched b2_sched;
+typedef struct b2_completion {
+    uint64_t tag;            /* the caller's tag (default: the slot id) */
+    int64_t t_enqueue_ns;    /* CLOCK_MONOTONIC: the caller's arrival stamp, or the time of b2_sched_submit */
+    int64_t t_launch_ns;     /* the sub-batch was closed and handed to the GPU */
+    int64_t t_done_ns;       /* its G.711 bytes were in pinned host memory */
+    int64_t g711_offset;     /* offset of this chunk's nbytes in the h_g711 buffer given to b2_sched_poll (-1 if none was given) */
+    int32_t slot, nbytes, batch_sessions, reserved_;
+} b2_completion;
+typedef struct b2_sched_stats {
+    uint64_t sub_batches, sessions, padded_sessions, graph_launches, graphs_built, max_sub_batch, capacity, depth;
+} b2_sched_stats;
+/* nframes: mel frames per chunk (multiple of 8; 8 = one 128 ms chunk, 32 = the reference's infer() call); max_batch: sessions per
+ * sub-batch (<= 0: as many as the context's workspace holds in one pass); depth: sub-batches in flight (2 = double buffering);
+ * use_graphs: run each sub-batch as one captured CUDA graph (sessions are padded to a bucket size with a scratch session). */
+B2_API b2_sched *b2_sched_create(b2_ctx *ctx, int nframes, int law, int flags, int max_batch, int depth, int use_graphs);
+B2_API void b2_sched_destroy(b2_sched *s);
+/* optional batching policy: a sub-batch with fewer than min_batch sessions waits up to max_wait_us after its first chunk (default 0/0:
+ * launch whatever is there as soon as the pipeline has room) */
+B2_API int b2_sched_set_policy(b2_sched *s, int min_batch, int max_wait_us);
+/* n chunks: h_slots[n], h_mel (n, nframes, 80) fp32, optional arrival stamps and tags.  Copies into pinned staging and returns; blocks
+ * only when every staging buffer is in use (back-pressure).  A session's chunks are processed in submission order. */
+B2_API int b2_sched_submit(b2_sched *s, const int32_t *h_slots, const float *h_mel, int n, const int64_t *t_enqueue_ns, const uint64_t *tags);
+/* up to max_out finished chunks, oldest first; their bytes are copied to h_g711 (may be NULL) at out[i].g711_offset.
+ * timeout_ms: 0 = do not wait, < 0 = wait.  Returns the count, or a negative value on error. */
+B2_API int b2_sched_poll(b2_sched *s, b2_completion *out, int max_out, uint8_t *h_g711, size_t g711_capacity, int timeout_ms);
+/* returns when everything submitted so far has completed (its completions may still be waiting for b2_sched_poll) */
+B2_API int b2_sched_flush(b2_sched *s, int timeout_ms);
+B2_API int b2_sched_get_stats(b2_sched *s, b2_sched_stats *out);
+
 /* ---- Core/Codecs (G711.py:25-47), ctx-less, stateless ----------------------------------------------- */
 /* G711Codec.encode: clamp(x*32767,-32768,32767) -> int16 (trunc toward zero) -> G.711 code.  n samples. */
 B2_API int b2_g711_encode_f32(const float *d_in, size_t n, int law, uint8_t *d_out, void *stream);

@@ -39,6 +39,13 @@ SIGNATURES = {
     "b2_tts_tail_host2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2_ctx_poll_errors": (c_int, [c_void_p, c_void_p]),
     "b2_debug_set_taps": (c_int, [c_void_p, c_void_p]),
+    "b2_sched_create": (c_void_p, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "b2_sched_destroy": (None, [c_void_p]),
+    "b2_sched_set_policy": (c_int, [c_void_p, c_int, c_int]),
+    "b2_sched_submit": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "b2_sched_poll": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int]),
+    "b2_sched_flush": (c_int, [c_void_p, c_int]),
+    "b2_sched_get_stats": (c_int, [c_void_p, c_void_p]),
     "b2_session_reset": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "b2_session_get_pre_frames": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "b2_session_set_pre_frames": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),

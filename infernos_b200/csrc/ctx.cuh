@@ -103,3 +103,11 @@ struct b2_ctx {
     size_t host_stage_cap_sessions = 0, host_stage_cap_frames = 0;
     std::vector<uint8_t> host_seen;                    // scratch of the host-side slot check
 };
+
+namespace b2 {
+// The fused tail over device buffers (tail.cu); the scheduler (sched.cu) captures it into CUDA graphs.
+// check_dups: duplicate-slot detection through claim[] (needs a fresh epoch per launch, so it is off inside captured graphs, whose
+// callers validate on the host); pad_slot_ok: slot id max_sessions (the padding session of a graph bucket) is legal.
+int tail_device(b2_ctx *c, const int32_t *d_slots, const float *d_mel, int B, int nframes, int law, bool apply_postnet,
+                uint8_t *d_g711, float *d_audio, cudaStream_t st, bool check_dups, bool pad_slot_ok);
+}  // namespace b2

@@ -523,8 +523,8 @@ static int postnet_fwd(b2_ctx *c, const float *d_in, int B, int T, float *d_out,
 
 // check_dups: duplicate-slot detection through claim[] (needs a fresh epoch per launch, so it is off inside captured graphs, whose
 // callers validate on the host); pad_slot_ok: slot id max_sessions (the padding session of a graph bucket) is legal
-static int tail_device(b2_ctx *c, const int32_t *d_slots, const float *d_mel, int B, int nframes, int law, bool apply_postnet,
-                       uint8_t *d_g711, float *d_audio, cudaStream_t st, bool check_dups = true, bool pad_slot_ok = false) {
+int tail_device(b2_ctx *c, const int32_t *d_slots, const float *d_mel, int B, int nframes, int law, bool apply_postnet,
+                uint8_t *d_g711, float *d_audio, cudaStream_t st, bool check_dups, bool pad_slot_ok) {
     const int nwin = nframes / 8;
     const int sess_per_pass = std::max(1, c->max_windows / nwin);
     const size_t Lout = (size_t)nframes * 128;
@@ -749,7 +749,7 @@ int b2_tts_tail2(b2_ctx *c, const int32_t *d_slots, const float *d_mel, int B, i
     if (d_g711 && law != B2_LAW_ULAW && law != B2_LAW_ALAW) return set_error("b2_tts_tail: bad law %d", law);
     if (!d_g711 && !d_audio) return set_error("b2_tts_tail: no output requested");
     if (poll_slot_errors(c, "b2_tts_tail (reported for an EARLIER asynchronous call)")) return 1;
-    return tail_device(c, d_slots, d_mel, B, nframes, law, (flags & B2_TAIL_APPLY_POSTNET) != 0, d_g711, d_audio, (cudaStream_t)stream);
+    return tail_device(c, d_slots, d_mel, B, nframes, law, (flags & B2_TAIL_APPLY_POSTNET) != 0, d_g711, d_audio, (cudaStream_t)stream, true, false);
 }
 
 int b2_tts_tail_host(b2_ctx *c, const int32_t *h_slots, const float *h_mel, int B, int nframes, int law,

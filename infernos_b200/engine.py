@@ -239,6 +239,79 @@ class TTSTail:
             _lib.check(self.lib.b2_session_set_pre_frames(self.ctx, int(slot), f.data_ptr(), _stream_ptr(self.device)), "set_pre_frames")
 
 
+class _Completion(ctypes.Structure):
+    _fields_ = [("tag", ctypes.c_uint64), ("t_enqueue_ns", ctypes.c_int64), ("t_launch_ns", ctypes.c_int64), ("t_done_ns", ctypes.c_int64),
+                ("g711_offset", ctypes.c_int64), ("slot", ctypes.c_int32), ("nbytes", ctypes.c_int32), ("batch_sessions", ctypes.c_int32),
+                ("reserved_", ctypes.c_int32)]
+
+
+class _SchedStats(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_uint64) for k in ("sub_batches", "sessions", "padded_sessions", "graph_launches", "graphs_built", "max_sub_batch",
+                                               "capacity", "depth")]
+
+
+class TailScheduler:
+    """Latency-bounded serving loop over one TTSTail (include/infernos_b200.h, b2_sched_*): submit (slot, mel chunk) pairs from any
+    thread; sub-batches are formed adaptively and run as H2D -> one CUDA-graph launch -> D2H with `depth` of them in flight.
+    While a scheduler exists it owns the tail's workspaces: do not call tail.tail()/vocoder() concurrently."""
+
+    def __init__(self, tail: "TTSTail", nframes: int = 8, law: int = LAW_ULAW, apply_postnet: bool = False, max_batch: int = 0,
+                 depth: int = 2, use_graphs: bool = True, poll_capacity: int = 4096):
+        self.tail, self.lib, self.nframes = tail, tail.lib, int(nframes)
+        with torch.cuda.device(tail.index):
+            self.h = self.lib.b2_sched_create(tail.ctx, self.nframes, law, TAIL_APPLY_POSTNET if apply_postnet else 0, int(max_batch), int(depth),
+                                              1 if use_graphs else 0)
+        if not self.h:
+            raise RuntimeError("b2_sched_create: " + self.lib.b2_last_error(None).decode())
+        self._cap = int(poll_capacity)
+        self._recs = (_Completion * self._cap)()
+        self._bytes = torch.empty(self._cap * self.nframes * 128, dtype=torch.uint8)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2_sched_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_policy(self, min_batch: int = 0, max_wait_us: int = 0) -> None:
+        _lib.check(self.lib.b2_sched_set_policy(self.h, int(min_batch), int(max_wait_us)), "sched_set_policy")
+
+    def submit(self, slots: torch.Tensor, mel: torch.Tensor, t_enqueue_ns: Optional[torch.Tensor] = None, tags: Optional[torch.Tensor] = None) -> None:
+        """slots (n,) int32, mel (n, nframes, 80) fp32, both on the HOST (any memory; they are copied into pinned staging);
+        t_enqueue_ns (n,) int64 CLOCK_MONOTONIC arrival stamps (default: now); tags (n,) uint64 (default: the slot id)."""
+        n = slots.numel()
+        assert not slots.is_cuda and not mel.is_cuda and slots.dtype == torch.int32 and mel.dtype == torch.float32
+        assert slots.is_contiguous() and mel.is_contiguous() and mel.numel() == n * self.nframes * 80
+        te = t_enqueue_ns.data_ptr() if t_enqueue_ns is not None else None
+        tg = tags.data_ptr() if tags is not None else None
+        if t_enqueue_ns is not None:
+            assert t_enqueue_ns.dtype == torch.int64 and t_enqueue_ns.numel() == n and t_enqueue_ns.is_contiguous()
+        if tags is not None:
+            assert tags.dtype in (torch.int64, torch.uint64) and tags.numel() == n and tags.is_contiguous()
+        _lib.check(self.lib.b2_sched_submit(self.h, slots.data_ptr(), mel.data_ptr(), n, te, tg), "sched_submit")
+
+    def poll(self, timeout_ms: int = 0, want_bytes: bool = True):
+        """-> (records, bytes): records is a ctypes array slice of finished chunks (tag, slot, t_enqueue_ns, t_launch_ns, t_done_ns,
+        batch_sessions, g711_offset), bytes the uint8 tensor their offsets point into (valid until the next poll)."""
+        n = self.lib.b2_sched_poll(self.h, self._recs, self._cap, self._bytes.data_ptr() if want_bytes else None, self._bytes.numel(), int(timeout_ms))
+        if n < 0:
+            raise RuntimeError("infernos_b200 sched_poll: " + self.lib.b2_last_error(None).decode())
+        return self._recs[:n], self._bytes
+
+    def flush(self, timeout_ms: int = 60000) -> None:
+        _lib.check(self.lib.b2_sched_flush(self.h, int(timeout_ms)), "sched_flush")
+
+    def stats(self) -> dict:
+        st = _SchedStats()
+        _lib.check(self.lib.b2_sched_get_stats(self.h, ctypes.byref(st)), "sched_get_stats")
+        return {k: int(getattr(st, k)) for k, _ in _SchedStats._fields_}
+
+
 def postnet_layers(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """Picks the post-net's conv / batch-norm tensors out of a SpeechT5 state_dict, whatever prefix they carry
     (`layers.0.conv.weight`, `speech_decoder_postnet.layers.0.conv.weight`, ...)."""
