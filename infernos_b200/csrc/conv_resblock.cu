@@ -132,20 +132,27 @@ static constexpr int kRbDbgEvents = 48, kRbDbgCtas = 4096;
 // EPI selects the final epilogue at compile time (its code is a third of the kernel, and the kernel has to fit the instruction
 // cache): 0 out32 = r;  1 out32 = acc + r;  2 outb = bf16(lrelu((acc + r) / div));  3 out32 = (acc + r) / div;  4 everything decided at run time;
 // 5 (C = 32 only) the vocoder's last step fused in: audio = tanh(conv_post(lrelu((acc + r) / div, 0.01))), nothing else written.
+// C = 32 with NEW = 8 ("sub-tile split"): two CTAs still share an SM, and warps 4..7 take the ODD sub-tiles of every phase (slab load,
+// the six conv epilogues, the final epilogue) that warps 0..3 used to do alone: the epilogue chain of a conv, which bounded the C = 32
+// launches (profiles/r1d_resblock_phase_timestamps.txt: ~3k cycles per conv for ~1k cycles of MMA issue), is walked by twice the warps.
 template <int C, int NEW, int NMW, int EPI, bool DBG>
-__global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 128 : 168) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ RbParams p) {
+__global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? (NEW == 8 ? 88 : 128) : 168) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ RbParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using G = RbGeom<C>;
     constexpr int kS = G::kS, kRows = G::kRows, kRtot = G::kRtot, KB = G::KB, NKB = G::NKB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kThreads = (NEW + 1 + NMW) * 32;
     constexpr int CH = C / 32;                                  // 32-column chunks per row
-    constexpr int CHW = CH / (NEW / 4);                         // ... of which one epilogue warp handles CHW
-    constexpr int NCHW = kS * CHW;
+    constexpr bool SSPLIT = (C == 32 && NEW == 8);              // epilogue warps 4..7 own the odd sub-tiles instead of a column slice
+    constexpr int SSTEP = SSPLIT ? 2 : 1;
+    constexpr int CHW = SSPLIT ? CH : CH / (NEW / 4);           // ... of which one epilogue warp handles CHW
+    constexpr int NCHW = (kS / SSTEP) * CHW;                    // 32x32 pieces per epilogue warp
+    constexpr int READY_CNT = SSPLIT ? 4 : NEW;                 // warps that publish one sub-tile
+    constexpr uint32_t kStgBytes = SSPLIT ? 4096u : 8192u;      // per-warp staging of the slab load (A2 holds NEW of them)
     constexpr int SPW = kS / NMW;                               // sub-tiles per MMA warp
     constexpr uint32_t kTapKbBytes = (uint32_t)C * KB * 2;      // one tap, one K block
     constexpr uint32_t kABytes = G::kABytes;
-    static_assert(CH % (NEW / 4) == 0 && kS % NMW == 0 && 2 * kS * C <= 512, "unsupported geometry");
+    static_assert((SSPLIT || CH % (NEW / 4) == 0) && kS % NMW == 0 && 2 * kS * C <= 512 && NEW * kStgBytes <= G::kABytes, "unsupported geometry");
     const uint32_t slot_bytes = (uint32_t)p.tps * kTapKbBytes;
     uint8_t *sW = smem;
     uint8_t *sA1 = smem + (size_t)p.nslots * slot_bytes;
@@ -170,9 +177,9 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
     // the load phase below keeps only two 4 KB pieces per warp in flight, so at HBM latency it was ~13k cycles of a 34-114k-cycle CTA
     // (phase timestamps, profiles/); out of L2 it is a few thousand.  One 128-byte line per lane per 32-channel piece.
     if (warp < NEW && !(p.dbg_flags & 1)) {
-        const int rq0 = (warp & 3) * 32 + lane, cb0 = (warp >> 2) * (CHW * 32);
+        const int rq0 = (warp & 3) * 32 + lane, cb0 = SSPLIT ? 0 : (warp >> 2) * (CHW * 32);
 #pragma unroll
-        for (int s = 0; s < kS; s++) {
+        for (int s = SSPLIT ? (warp >> 2) : 0; s < kS; s += SSTEP) {
             const int r = s * 128 + rq0, t = t_base + r;
             if (t >= 0 && t < p.T) {
                 const size_t off = ((size_t)w * p.T + t) * C + cb0;
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
             if (smem_u32(smem) & 1023u) __trap();
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
             for (int s = 0; s < 4; s++) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), NMW); }
-            for (int s = 0; s < kS; s++) { mbar_init(A1_READY(s), NEW); mbar_init(T1_FULL(s), 1); mbar_init(A2_READY(s), NEW); mbar_init(X_FULL(s), 1); }
+            for (int s = 0; s < kS; s++) { mbar_init(A1_READY(s), READY_CNT); mbar_init(T1_FULL(s), 1); mbar_init(A2_READY(s), READY_CNT); mbar_init(X_FULL(s), 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -221,7 +228,8 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
     if (warp < NEW) {
         // ======================================================================================= slab load + epilogues
         const int quad = warp & 3;                             // TMEM lane quadrant this warp may touch
-        const int cbase = (warp >> 2) * (CHW * 32);            // first column of this warp's slice
+        const int cbase = SSPLIT ? 0 : (warp >> 2) * (CHW * 32);   // first column of this warp's slice
+        const int s0 = SSPLIT ? (warp >> 2) : 0;               // first sub-tile this warp owns (then every SSTEP-th)
         const int rq = quad * 32 + lane;                       // row inside a sub-tile == TMEM lane
         const uint32_t tm_lane = (uint32_t)(quad * 32) << 16;
         const uint32_t a1_u32 = smem_u32(sA1), a2_u32 = smem_u32(sA2);
@@ -245,11 +253,11 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
         {
             // two 4 KB staging buffers per warp, 128-byte rows with the 16-byte piece index XOR-ed with (row & 7): conflict-free
             // for the 8-lanes-per-row writes of cp.async and for the row-per-lane reads
-            const uint32_t stg_u32 = a2_u32 + (uint32_t)(warp * 8192);
+            const uint32_t stg_u32 = a2_u32 + (uint32_t)warp * kStgBytes;
             const float *xq = p.x + ((size_t)w * p.T + (t_base + quad * 32 + sub_r)) * C + cbase + c4 * 4;   // row sub_r of this warp's rows in sub-tile 0
             auto issue_piece = [&](int q) {
-                const int s1 = q / CHW, c1 = (q % CHW) * 32;
-                const uint32_t dst0 = stg_u32 + (uint32_t)((q & 1) * 4096);
+                const int s1 = s0 + (q / CHW) * SSTEP, c1 = (q % CHW) * 32;
+                const uint32_t dst0 = stg_u32 + (SSPLIT ? 0u : (uint32_t)((q & 1) * 4096));
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const int row = j * 4 + sub_r;
@@ -262,8 +270,8 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
             issue_piece(0);
 #pragma unroll 1
             for (int q = 0; q < NCHW; q++) {
-                const int s = q / CHW, c0 = cbase + (q % CHW) * 32;
-                if (q + 1 < NCHW) {
+                const int s = s0 + (q / CHW) * SSTEP, c0 = cbase + (q % CHW) * 32;
+                if (!SSPLIT && q + 1 < NCHW) {
                     issue_piece(q + 1);
                     asm volatile("cp.async.wait_group 1;" ::: "memory");
                 } else {
@@ -272,13 +280,14 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                 __syncwarp();
                 uint32_t v[32];
                 {
-                    const uint32_t src0 = stg_u32 + (uint32_t)((q & 1) * 4096 + lane * 128);
+                    const uint32_t src0 = stg_u32 + (SSPLIT ? 0u : (uint32_t)((q & 1) * 4096)) + (uint32_t)(lane * 128);
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
                                      : "r"(src0 + (uint32_t)((j ^ (lane & 7)) << 4)) : "memory");
                 }
-                __syncwarp();                  // the buffer is refilled two pieces later
+                __syncwarp();                  // the buffer is refilled two pieces later (SSPLIT: one buffer per warp, refilled right away --
+                if (SSPLIT && q + 1 < NCHW) issue_piece(q + 1);      // its contents are in registers by now)
                 tmem_st32(tmem_X + tm_lane + (uint32_t)(s * C + c0), v);
                 write_operand_row<kRtot>(a1_u32, s * 128 + rq, c0, v, nullptr, p.slope, true);
                 if ((q % CHW) == CHW - 1) {
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
             // A2 after this warp's epilogue-1 publication, which comes later in program order)
             {
                 constexpr int kGuardRows = kRtot - kRows;
-                const uint32_t lo = (uint32_t)(warp * 8192), hi = lo + 8192;
+                const uint32_t lo = (uint32_t)warp * kStgBytes, hi = lo + kStgBytes;
                 for (int q = lane; q < kGuardRows * (C / 8); q += 32) {
                     const int ch = q / kGuardRows, g = q - ch * kGuardRows;
                     const int row = (g < kGuard) ? g : (kRows + g);
@@ -317,7 +326,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                 const float *bias = (e ? p.cbias : p.bias1) + i * C + cbase;
                 const uint32_t full0 = e ? X_FULL(0) : T1_FULL(0), ready0 = e ? A1_READY(0) : A2_READY(0);
 #pragma unroll 1
-                for (int s = 0; s < kS; s++) {
+                for (int s = s0; s < kS; s += SSTEP) {
                     mbar_wait(full0 + 8u * (uint32_t)s, par);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (threadIdx.x == 0 && s == 0) RB_DBG(3 + 4 * i + 2 * e);
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                     // writing the fp32 mean and reading it back in k_conv_post (modeling_speecht5.py:3074-3078).  Every MMA of the
                     // CTA has to be complete first, because the whole 512 x 32 fp32 slab V is laid over the weight ring and A1
                     // (rows of 128 bytes, 16-byte pieces XOR-ed with row & 7) and the conv_post weights over A2.
-                    static_assert(EPI != 5 || (C == 32 && NEW == 4), "conv_post is fused into the C = 32 stage only");
+                    static_assert(EPI != 5 || C == 32, "conv_post is fused into the C = 32 stage only");
 #pragma unroll 1
                     for (int s = 0; s < kS; s++) mbar_wait(X_FULL(s), par);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -347,7 +356,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                     for (int q = threadIdx.x; q < 7 * 32; q += NEW * 32) wp[q] = __ldg(p.post_w + q);
                     // pass A (lane owns a row): X + running bias -> V
 #pragma unroll 1
-                    for (int s = 0; s < kS; s++) {
+                    for (int s = s0; s < kS; s += SSTEP) {
                         uint32_t a32[32];
                         tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C), a32);
                         const float *cb = p.cbias + 2 * C;
@@ -366,7 +375,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                         const float rcp = p.rdiv, nd = -p.div;
                         const float *aq = p.acc_src + ((size_t)w * p.T + (t_base + quad * 32 + sub_r)) * C + c4 * 4;
 #pragma unroll 1
-                        for (int s = 0; s < kS; s++) {
+                        for (int s = s0; s < kS; s += SSTEP) {
                             float4 acc4[8];
 #pragma unroll
                             for (int j = 0; j < 8; j++)
@@ -427,7 +436,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                 const size_t row0 = (size_t)w * p.T + (t_base + quad * 32 + sub_r);        // global row of (sub-tile 0, j = 0)
                 const float *aq = p.acc_src + row0 * C + cbase + c4 * 4;            // only dereferenced when the epilogue has an acc_src
                 auto ld_acc = [&](int q, float4 (&b)[8]) {
-                    const int s1 = q / CHW, c1 = (q % CHW) * 32;
+                    const int s1 = s0 + (q / CHW) * SSTEP, c1 = (q % CHW) * 32;
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                         b[j] = ((out_t[j] >> s1) & 1u) ? *reinterpret_cast<const float4 *>(aq + ((size_t)s1 * 128 + j * 4) * C + c1) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -436,8 +445,11 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                 const bool has_div = (EPI == 4) ? (p.div != 1.0f) : (EPI >= 2);
                 const bool has_o32 = (EPI == 4) ? (p.out32 != nullptr) : (EPI != 2);
                 const bool has_ob = (EPI == 4) ? (p.outb != nullptr) : (EPI == 2);
+                // register prefetch of the NEXT piece's partial sums; not with eight epilogue warps at C = 32 (88 registers per thread:
+                // the second buffer would spill), where the loads of the current piece are issued ahead of its TMEM read instead
+                constexpr bool PF = !SSPLIT;
                 float4 accA[8], accB[8];
-                if (has_acc) ld_acc(0, accA);
+                if (has_acc && PF) ld_acc(0, accA);
                 if (threadIdx.x == 0) RB_DBG(40);
                 const float rcp = p.rdiv, nd = -p.div;
                 // (one copy of this body: the next piece's partial sums are fetched into accB and moved over, which is cheaper
@@ -446,13 +458,14 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                 for (int q = 0; q < NCHW; q++) {
                     float4 (&acur)[8] = accA;
                     float4 (&anx)[8] = accB;
-                    const int s = q / CHW, c0 = cbase + (q % CHW) * 32;
+                    const int s = s0 + (q / CHW) * SSTEP, c0 = cbase + (q % CHW) * 32;
                     if ((q % CHW) == 0) {
                         mbar_wait(X_FULL(s), par);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (threadIdx.x == 0 && s == 0) RB_DBG(5 + 4 * i);
                         if (threadIdx.x == 0) RB_DBG(32 + s);
                     }
+                    if (has_acc && !PF) ld_acc(q, accA);
                     {
                         uint32_t a32[32];
                         tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C + c0), a32);
@@ -464,7 +477,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                             *reinterpret_cast<uint4 *>(stg + lane * kRbStageLd + j * 4) = make_uint4(a32[4 * j], a32[4 * j + 1], a32[4 * j + 2], a32[4 * j + 3]);
                     }
                     __syncwarp();
-                    if (has_acc && q + 1 < NCHW) ld_acc(q + 1, anx);
+                    if (has_acc && PF && q + 1 < NCHW) ld_acc(q + 1, anx);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         if (!((out_t[j] >> s) & 1u)) continue;
@@ -488,7 +501,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                         }
                     }
                     __syncwarp();
-                    if (has_acc) {
+                    if (has_acc && PF) {
 #pragma unroll
                         for (int j = 0; j < 8; j++) accA[j] = accB[j];
                     }
@@ -677,7 +690,7 @@ void resblock_free(ResBlockPack &p) {
 }
 
 
-static bool g_rb_attr[64][3][7] = {};
+static bool g_rb_attr[64][4][7] = {};
 
 template <int C, int NEW, int NMW, int EPI, bool DBG>
 static int launch_rb_(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int wslot) {
@@ -755,7 +768,12 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     static const int nopf = getenv("B2_RB_NOPF") ? atoi(getenv("B2_RB_NOPF")) : 0;
     p.dbg_flags = nopf ? 1 : 0;
     if (dbg_on) B2_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, dbg_n * 8, st));
-    const int rc = (pk.C == 32) ? launch_rb<32, 4, 2>(tm, p, (unsigned)nct, smem, st, 0)
+    // C = 32: four epilogue warps.  B2_RB32_NEW=8 runs the eight-warp variant (warps 4..7 own the odd sub-tiles, 88 registers per thread so
+    // that two CTAs still share an SM).  Measured on the B200 (profiles/r2b_ab_rb32_epilogue_warps.json): SLOWER, 18.3 ms against 15.1 ms for the
+    // nine ResBlock launches of a 1,024-session step -- twice the warps on the same TMEM/shared-memory ports do not shorten the per-conv
+    // epilogue chain, and the single-buffered slab load loses its overlap.  Kept for A/B runs only.
+    static const int new32 = getenv("B2_RB32_NEW") ? atoi(getenv("B2_RB32_NEW")) : 4;
+    const int rc = (pk.C == 32) ? (new32 == 8 ? launch_rb<32, 8, 2>(tm, p, (unsigned)nct, smem, st, 3) : launch_rb<32, 4, 2>(tm, p, (unsigned)nct, smem, st, 0))
                    : (pk.C == 64) ? launch_rb<64, 8, 2>(tm, p, (unsigned)nct, smem, st, 1)
                    : launch_rb<128, 8, 2>(tm, p, (unsigned)nct, smem, st, 2);
     if (dbg_on && !rc) {

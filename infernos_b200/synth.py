@@ -119,3 +119,65 @@ def synth_audio(batch: int, nsamples: int, seed: int = 20240101) -> torch.Tensor
     """U(-0.9, 0.9) audio used by the codec sweeps (vector G2)."""
     g = torch.Generator().manual_seed(seed)
     return (torch.rand(batch, nsamples, generator=g) * 2 - 1) * 0.9
+
+
+DECODER_SEED = 1357
+# Gains of the random decoder.  With larger ones (He-style 1.4, sharper attention) the autoregressive loop is chaotic: a 1e-5 perturbation of
+# the first frame grows to O(1) within ~10 steps, so no two summation orders (let alone bf16) agree and a parity test means nothing.  With
+# these the loop is neutral (the same perturbation stays ~5e-6 over 48 steps) while every frame still depends on the previous one.
+G_PRE0, G_PRE1, G_FINAL, G_SPK, G_QK, G_FFN, G_FEAT = 0.3, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0
+DEC_HIDDEN, DEC_LAYERS, DEC_HEADS, DEC_FFN, DEC_PRENET_UNITS, DEC_SPK_DIM, DEC_REDUCTION = 768, 6, 12, 3072, 256, 512, 2
+
+
+def decoder_state_dict(seed: int = DECODER_SEED) -> Dict[str, torch.Tensor]:
+    """Random weights with the state_dict keys of the SpeechT5 speech decoder as the reference uses it (HelloSippyRTPipe.py:195-216):
+    `speecht5.decoder.prenet.*`, `speecht5.decoder.wrapped_decoder.layers.{0..5}.*` and `speech_decoder_postnet.{feat_out,prob_out}.*`
+    (default SpeechT5Config: hidden 768, 6 layers, 12 heads, FFN 3072, prenet 2 x 256, speaker 512, reduction factor 2;
+    modeling_speecht5.py:648-697, 1070-1160, 740-750), fp32, CPU.  Scaled so that activations stay O(1), feat_out emits
+    log-mel-like frames (~N(-4, 1)) and the stop probability stays low."""
+    g = torch.Generator().manual_seed(seed)
+
+    def lin(cout, cin, gain=1.0):
+        return torch.randn(cout, cin, generator=g) * (gain / math.sqrt(cin))
+
+    sd: Dict[str, torch.Tensor] = {}
+    P = "speecht5.decoder.prenet."
+    sd[P + "layers.0.weight"] = lin(DEC_PRENET_UNITS, NUM_MELS, G_PRE0)          # inputs are mel frames ~N(-4, 1): keep pre-activations O(1)
+    sd[P + "layers.0.bias"] = _bias(g, DEC_PRENET_UNITS) + 0.5
+    sd[P + "layers.1.weight"] = lin(DEC_PRENET_UNITS, DEC_PRENET_UNITS, G_PRE1)
+    sd[P + "layers.1.bias"] = _bias(g, DEC_PRENET_UNITS) + 0.2
+    sd[P + "final_layer.weight"] = lin(DEC_HIDDEN, DEC_PRENET_UNITS, G_FINAL)
+    sd[P + "final_layer.bias"] = _bias(g, DEC_HIDDEN)
+    sd[P + "encode_positions.alpha"] = torch.tensor(0.7)
+    sd[P + "speaker_embeds_layer.weight"] = lin(DEC_HIDDEN, DEC_HIDDEN + DEC_SPK_DIM, G_SPK)
+    sd[P + "speaker_embeds_layer.bias"] = _bias(g, DEC_HIDDEN)
+    for i in range(DEC_LAYERS):
+        L = f"speecht5.decoder.wrapped_decoder.layers.{i}."
+        for att in ("self_attn", "encoder_attn"):
+            for pj in ("k_proj", "v_proj", "q_proj", "out_proj"):
+                sd[L + f"{att}.{pj}.weight"] = lin(DEC_HIDDEN, DEC_HIDDEN, G_QK if pj in ("q_proj", "k_proj") else 1.0)
+                sd[L + f"{att}.{pj}.bias"] = _bias(g, DEC_HIDDEN)
+            sd[L + f"{att}_layer_norm.weight"] = torch.rand(DEC_HIDDEN, generator=g) * 0.4 + 0.8
+            sd[L + f"{att}_layer_norm.bias"] = _bias(g, DEC_HIDDEN) * 5
+        sd[L + "feed_forward.intermediate_dense.weight"] = lin(DEC_FFN, DEC_HIDDEN, 1.0)
+        sd[L + "feed_forward.intermediate_dense.bias"] = _bias(g, DEC_FFN)
+        sd[L + "feed_forward.output_dense.weight"] = lin(DEC_HIDDEN, DEC_FFN, G_FFN)
+        sd[L + "feed_forward.output_dense.bias"] = _bias(g, DEC_HIDDEN)
+        sd[L + "final_layer_norm.weight"] = torch.rand(DEC_HIDDEN, generator=g) * 0.4 + 0.8
+        sd[L + "final_layer_norm.bias"] = _bias(g, DEC_HIDDEN) * 5
+    sd["speech_decoder_postnet.feat_out.weight"] = lin(NUM_MELS * DEC_REDUCTION, DEC_HIDDEN, G_FEAT)
+    sd["speech_decoder_postnet.feat_out.bias"] = _bias(g, NUM_MELS * DEC_REDUCTION) - 4.0
+    sd["speech_decoder_postnet.prob_out.weight"] = lin(DEC_REDUCTION, DEC_HIDDEN, 1.0)
+    sd["speech_decoder_postnet.prob_out.bias"] = torch.full((DEC_REDUCTION,), -3.0)
+    return sd
+
+
+def synth_encoder_states(batch: int, length: int, seed: int = 99) -> torch.Tensor:
+    """Stand-in for `encoder_last_hidden_state` (B, L, 768): the text encoder is context glue outside the path (HelloSippyRTPipe.py:111-116)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, length, DEC_HIDDEN, generator=g)
+
+
+def synth_speakers(batch: int, seed: int = 98) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, DEC_SPK_DIM, generator=g) * 3.0
