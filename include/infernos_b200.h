@@ -156,6 +156,35 @@ B2_API int b2_sched_poll(b2_sched *s, b2_completion *out, int max_out, uint8_t *
 B2_API int b2_sched_flush(b2_sched *s, int timeout_ms);
 B2_API int b2_sched_get_stats(b2_sched *s, b2_sched_stats *out);
 
+/* ---- the step before the path: the autoregressive SpeechT5 speech decoder, HelloSippyRTPipe.py:195-229 ----------------------
+ * prenet -> wrapped_decoder (six layers, KV cache) -> feat_out / prob_out, batched over sessions whose state (self-attention KV cache,
+ * cross-attention keys / values of the sentence, normalised speaker vector, last frame, step counter) lives in slots on the device.
+ * Weights by state_dict key of transformers SpeechT5ForTextToSpeech: `speecht5.decoder.prenet.*`, `speecht5.decoder.wrapped_decoder.layers.*`,
+ * `speech_decoder_postnet.feat_out.*`, `speech_decoder_postnet.prob_out.*`, plus key `pe` = the (max_steps, 768) position table
+ * (SpeechT5ScaledPositionalEncoding.pe, modeling_speecht5.py:405-412; passed in so that it is torch's own).  Default SpeechT5Config sizes.
+ * The text encoder (HelloSippyRTPipe.py:111-116, once per sentence) stays with the caller: its output is an input here.
+ * B2_MODE_FP32: CUDA-core fp32 Linears, fp32 caches.  B2_MODE_BF16: tcgen05 GEMMs fed by TMA, bf16 caches, fp32 residual stream / LayerNorm. */
+typedef struct b2_dec b2_dec;
+/* max_rows: sessions per internal pass (workspace); max_steps: decoder steps a sentence may run (KV cache depth = positions of `pe`);
+ * max_enc_len: encoder positions per sentence */
+B2_API b2_dec *b2_dec_create(int device, int mode, int max_sessions, int max_rows, int max_steps, int max_enc_len);
+B2_API void b2_dec_destroy(b2_dec *dec);
+B2_API size_t b2_dec_device_bytes(const b2_dec *dec);
+B2_API int b2_dec_load_tensor(b2_dec *dec, const char *key, const float *h_data, const int64_t *shape, int ndim);
+B2_API int b2_dec_finalize(b2_dec *dec);
+/* HelloSippyPipeStateBatched.merge (HelloSippyRTPipe.py:97-118) for n new sentences: d_enc (n, L, 768) fp32 = encoder_last_hidden_state,
+ * d_enc_len (n) int32 = number of unmasked encoder positions (NULL: all L), d_speaker (n, 512) fp32 (normalised here, :696).  Projects the
+ * cross-attention keys / values of all six layers into the slots, zeroes the first frame and the step counter. */
+B2_API int b2_dec_start(b2_dec *dec, const int32_t *d_slots, const float *d_enc, const int32_t *d_enc_len, const float *d_speaker, int n, int L, void *stream);
+/* nsteps trips of the reference's while loop (:195-223) for n sessions: d_mel (n, 2*nsteps, 80) = the feat_out frames (BEFORE the post-net:
+ * feed them to b2_tts_tail2 with B2_TAIL_APPLY_POSTNET), d_prob (n, nsteps, 2) = sigmoid(prob_out).  d_masks (nsteps, 2, 256) fp32 0/1 =
+ * the prenet's dropout keep-masks (always on, even in eval: modeling_speecht5.py:671-691), shared by the batch like the reference's; NULL
+ * draws them on the device from (seed, call counter).  Asynchronous on `stream`. */
+B2_API int b2_dec_steps(b2_dec *dec, const int32_t *d_slots, int n, int nsteps, const float *d_masks, uint64_t seed, float *d_mel, float *d_prob, void *stream);
+/* synchronises `stream` and reports what the kernels flagged (slot outside the pool, step past max_steps, bad encoder length) */
+B2_API int b2_dec_poll_errors(b2_dec *dec, void *stream);
+B2_API int b2_dec_get_step(b2_dec *dec, int slot, int32_t *h_step, void *stream);
+
 /* ---- Core/Codecs (G711.py:25-47), ctx-less, stateless ----------------------------------------------- */
 /* G711Codec.encode: clamp(x*32767,-32768,32767) -> int16 (trunc toward zero) -> G.711 code.  n samples. */
 B2_API int b2_g711_encode_f32(const float *d_in, size_t n, int law, uint8_t *d_out, void *stream);

@@ -46,6 +46,15 @@ SIGNATURES = {
     "b2_sched_poll": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int]),
     "b2_sched_flush": (c_int, [c_void_p, c_int]),
     "b2_sched_get_stats": (c_int, [c_void_p, c_void_p]),
+    "b2_dec_create": (c_void_p, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "b2_dec_destroy": (None, [c_void_p]),
+    "b2_dec_device_bytes": (c_size_t, [c_void_p]),
+    "b2_dec_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int]),
+    "b2_dec_finalize": (c_int, [c_void_p]),
+    "b2_dec_start": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "b2_dec_steps": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p]),
+    "b2_dec_poll_errors": (c_int, [c_void_p, c_void_p]),
+    "b2_dec_get_step": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "b2_session_reset": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "b2_session_get_pre_frames": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "b2_session_set_pre_frames": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),

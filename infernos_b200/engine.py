@@ -312,6 +312,118 @@ class TailScheduler:
         return {k: int(getattr(st, k)) for k, _ in _SchedStats._fields_}
 
 
+def decoder_position_table(max_len: int, dim: int = 768) -> torch.Tensor:
+    """SpeechT5ScaledPositionalEncoding.pe (transformers modeling_speecht5.py:405-412), computed with the same torch expressions so that
+    the table the library adds is bit-identical to the module's buffer."""
+    import math
+    pe = torch.zeros(max_len, dim)
+    position = torch.arange(0, max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, dim, 2, dtype=torch.int64).float() * -(math.log(10000.0) / dim))
+    pe[:, 0::2] = torch.sin(position.float() * div_term)
+    pe[:, 1::2] = torch.cos(position.float() * div_term)
+    return pe
+
+
+class TTSDecoder:
+    """The autoregressive SpeechT5 speech decoder on the GPU (b2_dec_*): prenet -> six decoder layers with a slot KV
+    cache -> feat_out / prob_out, the front half of the reference's infer() (HelloSippyRTPipe.py:195-229).  `sd` is a state_dict that
+    holds the `speecht5.decoder.*` and `speech_decoder_postnet.{feat_out,prob_out}.*` tensors of transformers SpeechT5ForTextToSpeech
+    (the whole model's state_dict will do)."""
+
+    def __init__(self, device, sd: Dict[str, torch.Tensor], mode="bf16", max_sessions: int = 64, max_rows: int = 0, max_steps: int = 512,
+                 max_enc_len: int = 128):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("infernos_b200 runs on CUDA devices only (no CPU fallback)")
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.index)
+        self.mode = _MODES[mode]
+        self.max_sessions, self.max_steps, self.max_enc_len = int(max_sessions), int(max_steps), int(max_enc_len)
+        self.max_rows = int(max_rows) if max_rows else min(self.max_sessions, 1024)
+        self.h = self.lib.b2_dec_create(self.index, self.mode, self.max_sessions, self.max_rows, self.max_steps, self.max_enc_len)
+        if not self.h:
+            raise RuntimeError("b2_dec_create: " + self.lib.b2_last_error(None).decode())
+        try:
+            n = 0
+            for k, v in sd.items():
+                if not (k.startswith("speecht5.decoder.prenet.") or k.startswith("speecht5.decoder.wrapped_decoder.") or
+                        k.startswith("speech_decoder_postnet.feat_out.") or k.startswith("speech_decoder_postnet.prob_out.")):
+                    continue
+                if k.endswith("encode_positions.pe"):
+                    continue
+                self._load(k, v)
+                n += 1
+            if n != 8 + 1 + 6 * 26 + 4:
+                raise RuntimeError(f"decoder state_dict: expected {8 + 1 + 6 * 26 + 4} tensors, found {n}")
+            self._load("pe", decoder_position_table(self.max_steps))
+            with torch.cuda.device(self.index):
+                _lib.check(self.lib.b2_dec_finalize(self.h), "dec_finalize")
+        except Exception:
+            self.close()
+            raise
+
+    def _load(self, k, v):
+        t = v.detach().to("cpu", torch.float32).contiguous()
+        shape = (ctypes.c_int64 * max(1, t.dim()))(*t.shape)
+        _lib.check(self.lib.b2_dec_load_tensor(self.h, k.encode(), ctypes.c_void_p(t.data_ptr()), shape, t.dim()), f"dec load {k}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2_dec_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.b2_dec_device_bytes(self.h))
+
+    def start(self, slots: torch.Tensor, enc: torch.Tensor, enc_len: Optional[torch.Tensor], speaker: torch.Tensor) -> None:
+        """New sentences: slots (n,) int32 cuda, enc (n, L, 768) = encoder_last_hidden_state, enc_len (n,) int32 valid prefix lengths (or
+        None), speaker (n, 512)."""
+        s = _require_cuda(slots, torch.int32, "slots")
+        e = _require_cuda(enc.to(torch.float32), torch.float32, "enc")
+        sp = _require_cuda(speaker.to(torch.float32), torch.float32, "speaker")
+        n, L, hdim = e.shape
+        if hdim != 768 or tuple(sp.shape) != (n, 512) or s.numel() != n:
+            raise RuntimeError("decoder.start expects enc (n, L, 768), speaker (n, 512), slots (n,)")
+        el = _require_cuda(enc_len, torch.int32, "enc_len") if enc_len is not None else None
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_dec_start(self.h, s.data_ptr(), e.data_ptr(), el.data_ptr() if el is not None else None, sp.data_ptr(), n, L,
+                                             _stream_ptr(self.device)), "dec_start")
+
+    def steps(self, slots: torch.Tensor, nsteps: int = 16, masks: Optional[torch.Tensor] = None, seed: int = 0):
+        """-> (mel (n, 2*nsteps, 80) fp32 cuda: feat_out's frames, BEFORE the post-net; prob (n, nsteps, 2) fp32 cuda)."""
+        s = _require_cuda(slots, torch.int32, "slots")
+        n = s.numel()
+        mel = torch.empty(n, 2 * nsteps, 80, device=self.device, dtype=torch.float32)
+        prob = torch.empty(n, nsteps, 2, device=self.device, dtype=torch.float32)
+        mk = None
+        if masks is not None:
+            mk = _require_cuda(masks.to(torch.float32), torch.float32, "masks")
+            if tuple(mk.shape) != (nsteps, 2, 256):
+                raise RuntimeError("masks must be (nsteps, 2, 256)")
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_dec_steps(self.h, s.data_ptr(), n, int(nsteps), mk.data_ptr() if mk is not None else None, int(seed) & (2 ** 64 - 1),
+                                             mel.data_ptr(), prob.data_ptr(), _stream_ptr(self.device)), "dec_steps")
+        return mel, prob
+
+    def poll_errors(self) -> None:
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_dec_poll_errors(self.h, _stream_ptr(self.device)), "dec_poll_errors")
+
+    def get_step(self, slot: int) -> int:
+        v = ctypes.c_int32(0)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b2_dec_get_step(self.h, int(slot), ctypes.byref(v), _stream_ptr(self.device)), "dec_get_step")
+        return int(v.value)
+
+
 def postnet_layers(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """Picks the post-net's conv / batch-norm tensors out of a SpeechT5 state_dict, whatever prefix they carry
     (`layers.0.conv.weight`, `speech_decoder_postnet.layers.0.conv.weight`, ...)."""

@@ -1,0 +1,125 @@
+"""GPU parity of the autoregressive front half (b2_dec_*) against oracle/decoder.py (pinned to the live transformers modules
+by tests/test_oracle_decoder.py) and against the golden produced by the REAL modules (tests/golden/decoder_golden.npz): same synthetic
+weights, same encoder states, same prenet dropout masks.  fp32 mode: max-abs <= 1e-3 on the mel frames; bf16 mode: >= 40 dB SNR."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from infernos_b200 import synth
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return synth.decoder_state_dict()
+
+
+def _snr(ref, x):
+    from oracle.tail import snr_db
+    return snr_db(torch.as_tensor(ref), torch.as_tensor(x))
+
+
+def _oracle(sd, enc, enc_mask, speaker, masks):
+    from oracle import decoder as odec
+    st = odec.DecoderState(sd, enc, enc_mask, speaker)
+    specs, probs = [], []
+    with torch.no_grad():
+        for s in range(masks.size(0)):
+            sp, pr = odec.step(sd, st, masks[s])
+            specs.append(sp); probs.append(pr)
+    return torch.cat(specs, 1), torch.stack(probs, 1)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_decoder_replays_the_real_modules_golden(sd, mode):
+    """16 steps (one reference infer() call) of 3 sentences with ragged encoder lengths, slots out of order."""
+    from infernos_b200.engine import TTSDecoder
+    d = np.load(os.path.join(G, "decoder_golden.npz"))
+    enc, mask, spk, masks = (torch.from_numpy(d[k]) for k in ("enc", "enc_mask", "speaker", "masks"))
+    dec = TTSDecoder("cuda:0", sd, mode=mode, max_sessions=8, max_steps=64, max_enc_len=16)
+    try:
+        slots = torch.tensor([5, 0, 3], dtype=torch.int32).cuda()
+        dec.start(slots, enc.cuda(), mask.sum(1).to(torch.int32).cuda(), spk.cuda())
+        mel, prob = dec.steps(slots, 16, masks=masks.cuda())
+        dec.poll_errors()
+        assert [dec.get_step(s) for s in (5, 0, 3)] == [16, 16, 16]
+    finally:
+        dec.close()
+    mel, prob = mel.cpu().numpy(), prob.cpu().numpy()
+    assert mel.shape == d["mel"].shape == (3, 32, 80) and prob.shape == d["prob"].shape
+    err, snr = float(np.abs(mel - d["mel"]).max()), _snr(d["mel"] - d["mel"].mean(), mel - d["mel"].mean())
+    print(f"decoder {mode}: max |d mel| {err:.2e}, SNR on the mean-removed mel {snr:.2f} dB, max |d prob| {np.abs(prob - d['prob']).max():.2e}")
+    if mode == "fp32":
+        assert err <= 1e-3 and np.abs(prob - d["prob"]).max() <= 1e-4
+    else:
+        assert snr >= 40.0
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_decoder_two_calls_continuous_batching_and_sub_passes(sd, mode):
+    """Two consecutive 16-step calls (the KV cache carries over), a second cohort admitted between them, max_rows smaller than the batch
+    (internal passes), against the oracle run per cohort."""
+    from infernos_b200.engine import TTSDecoder
+    g = torch.Generator().manual_seed(4)
+    encA, encB = synth.synth_encoder_states(5, 9, seed=21), synth.synth_encoder_states(2, 14, seed=22)
+    mA, mB = torch.ones(5, 9, dtype=torch.int), (torch.arange(14)[None] < torch.tensor([14, 6])[:, None]).to(torch.int)
+    sA, sB = synth.synth_speakers(5, seed=23), synth.synth_speakers(2, seed=24)
+    masks1 = (torch.rand(16, 2, 256, generator=g) < 0.5).float()
+    masks2 = (torch.rand(16, 2, 256, generator=g) < 0.5).float()
+    refA, _ = _oracle(sd, encA, mA, sA, torch.cat([masks1, masks2]))
+    refB, _ = _oracle(sd, encB, mB, sB, masks2)
+    dec = TTSDecoder("cuda:0", sd, mode=mode, max_sessions=16, max_rows=4, max_steps=40, max_enc_len=14)
+    try:
+        slA = torch.tensor([1, 2, 3, 4, 9], dtype=torch.int32).cuda()
+        slB = torch.tensor([7, 0], dtype=torch.int32).cuda()
+        dec.start(slA, encA.cuda(), None, sA.cuda())
+        mel1, _ = dec.steps(slA, 16, masks=masks1.cuda())
+        dec.start(slB, encB.cuda(), mB.sum(1).to(torch.int32).cuda(), sB.cuda())
+        both = torch.cat([slB, slA])                                    # one batched call over both cohorts, newcomers first
+        mel2, _ = dec.steps(both, 16, masks=masks2.cuda())
+        dec.poll_errors()
+        assert dec.get_step(9) == 32 and dec.get_step(7) == 16
+        with pytest.raises(RuntimeError, match="max_steps"):            # 40 positions only: the third call runs the first cohort past them
+            dec.steps(slA, 16, masks=masks1.cuda())
+            dec.poll_errors()
+    finally:
+        dec.close()
+    gotA = torch.cat([mel1.cpu(), mel2[2:].cpu()], dim=1)
+    gotB = mel2[:2].cpu()
+    if mode == "fp32":
+        assert float((gotA - refA).abs().max()) <= 1e-3 and float((gotB - refB).abs().max()) <= 1e-3
+    else:
+        c = refA.mean()
+        print(f"decoder bf16, 32 steps: SNR {_snr(refA - c, gotA - c):.2f} dB (cohort A), {_snr(refB - c, gotB - c):.2f} dB (cohort B)")
+        assert _snr(refA - c, gotA - c) >= 40.0 and _snr(refB - c, gotB - c) >= 40.0
+
+
+def test_decoder_feeds_the_tail_without_leaving_the_device(sd):
+    """front half + tail: the decoder's feat_out frames go straight into b2_tts_tail2(B2_TAIL_APPLY_POSTNET)."""
+    from infernos_b200.engine import TTSDecoder, TTSTail
+    from oracle import codec as ocodec
+    from oracle import tail as otail
+    d = np.load(os.path.join(G, "decoder_golden.npz"))
+    enc, mask, spk, masks = (torch.from_numpy(d[k]) for k in ("enc", "enc_mask", "speaker", "masks"))
+    vsd, csd, psd = synth.hifigan_state_dict(), synth.chunker_state_dict(), synth.postnet_state_dict()
+    dec = TTSDecoder("cuda:0", sd, mode="fp32", max_sessions=4, max_steps=32, max_enc_len=16)
+    tail = TTSTail("cuda:0", vsd, csd, mode="fp32", max_sessions=4, max_windows=16, postnet_sd=psd)
+    try:
+        slots = torch.tensor([2, 0, 1], dtype=torch.int32).cuda()
+        tail.reset_sessions([0, 1, 2])
+        dec.start(slots, enc.cuda(), mask.sum(1).to(torch.int32).cuda(), spk.cuda())
+        mel, _ = dec.steps(slots, 16, masks=masks.cuda())
+        g, a = tail.tail(slots, mel, apply_postnet=True)
+        tail.poll_errors()
+        a, g = a.cpu(), g.cpu()
+    finally:
+        dec.close(); tail.close()
+    with torch.no_grad():
+        ref_mel = otail.postnet_forward(psd, torch.from_numpy(d["mel"]))
+        ref, _ = otail.tts_tail(vsd, csd, torch.zeros(3, 4, 80), ref_mel)
+    assert float((a - ref).abs().max()) <= 1e-3
+    assert np.array_equal(g.numpy(), ocodec.encode_f32(a.numpy(), 0))
