@@ -306,6 +306,50 @@ def run_latency(dev, sessions, seconds, chunk_frames=8, mode="bf16", max_windows
                           "pinned host memory; H2D and D2H inside; sub-batches formed adaptively, one CUDA graph launch each"}
 
 
+def run_front_half(dev, tail, slots_d, sessions, calls=8, enc_len=64, mode="bf16"):
+    """the autoregressive decoder (b2_dec_*) in front of the tail, both on the GPU, frames never leaving the device.
+    `calls` consecutive reference infer() calls (16 decoder steps + post-net + tail each) for `sessions` sentences of `enc_len` encoder
+    positions; the decoder's attention cost grows with the step count, so per-call times are reported from the first to the last call."""
+    import torch
+    from infernos_b200 import synth
+    from infernos_b200.engine import TTSDecoder
+    dec = TTSDecoder(dev, synth.decoder_state_dict(), mode=mode, max_sessions=sessions, max_rows=min(sessions, 1024), max_steps=16 * (calls + 2) + 1,
+                     max_enc_len=enc_len)
+    try:
+        enc = synth.synth_encoder_states(min(sessions, 64), enc_len, seed=5).to(dev).repeat((sessions + 63) // 64, 1, 1)[:sessions].contiguous()
+        spk = synth.synth_speakers(sessions, seed=6).to(dev)
+        tail.reset_sessions(list(range(sessions)))
+        # two warm-up calls: the first runs every kernel eagerly, the second captures the decoder's graph
+        dec.start(slots_d, enc, None, spk)
+        for _ in range(2):
+            mel, _ = dec.steps(slots_d, 16)
+            tail.tail(slots_d, mel, want_audio=False, apply_postnet=tail.has_postnet)
+        dec.start(slots_d, enc, None, spk)
+        torch.cuda.synchronize(dev)
+        rows = []
+        for c in range(calls):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            mel, prob = dec.steps(slots_d, 16)
+            e[1].record()
+            tail.tail(slots_d, mel, want_audio=False, apply_postnet=tail.has_postnet)
+            e[2].record()
+            torch.cuda.synchronize(dev)
+            rows.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])))
+        dec.poll_errors()
+        dms, tms = [r[0] for r in rows], [r[1] for r in rows]
+        tot = sum(dms) + sum(tms)
+        return {"sessions": sessions, "calls": calls, "encoder_positions": enc_len, "decoder_ms_per_call_first_last": [round(dms[0], 3), round(dms[-1], 3)],
+                "decoder_ms_per_call_mean": round(sum(dms) / calls, 3), "tail_ms_per_call_mean": round(sum(tms) / calls, 3),
+                "streams_front_plus_tail": round(sessions * 32 * AUDIO_S_PER_FRAME * calls / (tot / 1e3), 1),
+                "decoder_hbm_bytes": dec.device_bytes,
+                "note": "decoder: prenet + 6 layers + feat_out/prob_out, 16 steps per call as one CUDA graph launch, bf16 tcgen05 GEMMs fed by TMA, "
+                        "bf16 KV cache; tail: post-net + vocoder + chunker + resample + G.711 on the decoder's frames in HBM; the text encoder (once "
+                        "per sentence) is outside"}
+    finally:
+        dec.close()
+
+
 # ----------------------------------------------------------------------------------------------- GPU arm
 def main_b200(args, rank, local_rank, world):
     import torch
@@ -491,6 +535,14 @@ def main_b200(args, rank, local_rank, world):
                           "; efficiency is against this run's own 1,024-sessions-per-GPU rate; what it loses is wave quantisation of the small "
                           "grids (stage 0/1 at 512 windows) and the fixed ~41 launches per call"}
 
+    # ---- AR decoder + tail, both on the GPU ------------------------------------------------------------------------------
+    front = None
+    if rank == 0 and world == 1 and not args.no_front and args.mode == "bf16":
+        try:
+            front = run_front_half(dev, tail, slots_d, S)
+        except Exception as e:
+            front = {"error": repr(e)[:300]}
+
     # ---- north_star's joint target: p99 chunk latency at >= 5,000 concurrent real-time streams ---------------------------------------
     latency = None
     if rank == 0 and world == 1 and not args.no_latency:
@@ -529,7 +581,7 @@ def main_b200(args, rank, local_rank, world):
             "roofline": roofline, "roofline_conv_family": family_roof, "roofline_codec": codec_roof,
             "kernel_ms_per_step": {k: round(v / psteps, 3) for k, v in ms_cls.items()},
             "cpu_baseline": cpu,
-            "latency": latency, "strong": strong,
+            "latency": latency, "strong": strong, "front_half": front,
             "per_gpu_stats": [{"sessions": int(s["sessions"]), "steps": int(s["steps"]), "g711_bytes": int(s["g711_bytes"]),
                                "device_ms": round(s["device_ms"], 3)} for s in allstats],
             "hbm_bytes_ctx": ctx_bytes,
@@ -560,6 +612,7 @@ def main():
     ap.add_argument("--no-latency", action="store_true", help="skip the p99 chunk-latency legs (5,000 / 20,000 staggered real-time sessions)")
     ap.add_argument("--latency-sessions", type=int, nargs="*", default=[5000, 20000])
     ap.add_argument("--latency-seconds", type=float, default=3.0)
+    ap.add_argument("--no-front", action="store_true", help="skip the AR-decoder + tail leg (SURVEY 8 f3)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (BASELINE config 3 as written)")
     ap.add_argument("--strong-total", type=int, default=1024)
     ap.add_argument("--cpu-sweep", action="store_true", help="with --impl reference: fp32/bf16 x B in {1,8,64} CPU table (SURVEY 8d)")

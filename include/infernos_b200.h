@@ -184,6 +184,9 @@ B2_API int b2_dec_steps(b2_dec *dec, const int32_t *d_slots, int n, int nsteps, 
 /* synchronises `stream` and reports what the kernels flagged (slot outside the pool, step past max_steps, bad encoder length) */
 B2_API int b2_dec_poll_errors(b2_dec *dec, void *stream);
 B2_API int b2_dec_get_step(b2_dec *dec, int slot, int32_t *h_step, void *stream);
+/* b2_dec_steps runs as ONE CUDA graph launch per call (cached per padded batch size and step count; a call is ~74 kernels per step).
+ * on = 0 launches the kernels one by one instead (default: 1). */
+B2_API int b2_dec_set_graphs(b2_dec *dec, int on);
 
 /* ---- Core/Codecs (G711.py:25-47), ctx-less, stateless ----------------------------------------------- */
 /* G711Codec.encode: clamp(x*32767,-32768,32767) -> int16 (trunc toward zero) -> G.711 code.  n samples. */

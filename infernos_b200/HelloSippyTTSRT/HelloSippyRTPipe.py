@@ -219,6 +219,66 @@ class SpeechT5Frontend:
         return self.model.speech_decoder_postnet.postnet(spectrogram)
 
 
+class B200Frontend:
+    """The autoregressive front half on the GPU: prenet -> six-layer decoder with a slot KV cache -> feat_out /
+    prob_out run inside the CUDA library (engine.TTSDecoder, b2_dec_*), 16 steps per engine call in one C-ABI call, and the frames never leave
+    the device on their way into the tail.  What stays outside is what the reference runs once per sentence: the tokenizer and the text
+    encoder (:111-116), reached through two callables:
+        tokenizer(text) -> (1, n) LongTensor          (default: the SpeechT5 processor of `model`)
+        encoder(input_ids, attention_mask) -> (B, L, 768) tensor     (default: model.speecht5.encoder(...).last_hidden_state)
+    `mask_fn(call_index) -> (16, 2, 256) 0/1 tensor` injects the prenet's dropout keep-masks (tests); by default they are drawn on the device."""
+
+    reduction_factor = 2
+    num_mel_bins = 80
+    steps_per_call = 16
+
+    def __init__(self, decoder, tokenizer: Callable, encoder: Callable, mask_fn: Optional[Callable] = None, seed: int = 0):
+        self.decoder, self._tokenize, self._encode, self.mask_fn, self.seed = decoder, tokenizer, encoder, mask_fn, seed
+
+    @classmethod
+    def from_model(cls, model, processor, device, mode="bf16", max_sessions=64, max_steps=512, max_enc_len=128, **kw):
+        from infernos_b200.engine import TTSDecoder
+        dec = TTSDecoder(device, model.state_dict(), mode=mode, max_sessions=max_sessions, max_steps=max_steps, max_enc_len=max_enc_len)
+
+        @torch.no_grad()
+        def encode(ids, mask):
+            dev = next(model.parameters()).device
+            return model.speecht5.encoder(input_values=ids.to(dev), attention_mask=mask.to(dev), return_dict=True).last_hidden_state
+        return cls(dec, lambda text: processor(text=text, return_tensors="pt")["input_ids"], encode, **kw)
+
+    def tokenize(self, text):
+        return self._tokenize(text)
+
+    def start(self, state, states):
+        n = max(s.inputs.size(1) for s in states)
+        pad = lambda t: torch.nn.functional.pad(t, (0, n - t.size(1)))
+        state.inputs = torch.cat([pad(s.inputs) for s in states])
+        state.encoder_attention_mask = torch.cat([pad(s.encoder_attention_mask) for s in states])
+        enc = self._encode(state.inputs, state.encoder_attention_mask)
+        dev = self.decoder.device
+        spk = torch.cat([s.speaker_embeddings for s in states]).to(device=dev, dtype=torch.float32)
+        state._enc_positions = int(enc.size(1))
+        state._fe_call = 0
+        self.decoder.start(state.slots, enc.to(device=dev, dtype=torch.float32).contiguous(),
+                           state.encoder_attention_mask.sum(dim=1).to(device=dev, dtype=torch.int32), spk)
+
+    def length_bounds(self, state, minlenratio, maxlenratio):
+        n = state._enc_positions
+        return int(n * minlenratio / self.reduction_factor), min(int(n * maxlenratio / self.reduction_factor), self.decoder.max_steps - 1)
+
+    def call(self, state):
+        """One engine call = 16 decoder steps: -> (frames (B, 32, 80) fp32 on the device, BEFORE the post-net; stop probabilities (B, 16, 2) on the host)."""
+        masks = self.mask_fn(state._fe_call) if self.mask_fn is not None else None
+        if masks is not None:
+            masks = masks.to(self.decoder.device)
+        mel, prob = self.decoder.steps(state.slots, self.steps_per_call, masks=masks, seed=self.seed)
+        state._fe_call += 1
+        return mel, prob.cpu()
+
+    def postnet(self, spectrogram):
+        raise RuntimeError("B200Frontend leaves the post-net to the tail call (pass postnet_state_dict to the engine)")
+
+
 class HelloSippyRTPipe:
     minlenratio: float = 0.0
     maxlenratio: float = 20.0
@@ -314,9 +374,21 @@ class HelloSippyRTPipe:
     def _front_half(self, state: HelloSippyPipeStateBatched) -> torch.Tensor:
         """Reference :195-230 for one batch state: 16 decoder steps (32 frames), stop bookkeeping, postnet.  -> mel (B, 32, 80);
         with gpu_postnet the frames are returned as feat_out produced them and the post-net is left to the tail call."""
+        eframes = self.pre_nframes + self.post_nframes
+        if hasattr(self.frontend, "call"):
+            # GPU front half: the 16 steps are one library call; the stop rule of :225-228 is replayed step by step on the host from one
+            # copy of the stop probabilities
+            spectrogram, prob = self.frontend.call(state)
+            for s in range(prob.size(1)):
+                stop = (prob[:, s] >= self.threshold).sum(dim=1) > 0
+                fire = (state.ends_at < 0) & (state.minlen <= state.idx) & (stop | (state.maxlen <= state.idx))
+                state.ends_at = torch.where(fire, state.idx + eframes // self.reduction_factor, state.ends_at)
+                state.idx += 1
+            if not self.gpu_postnet:
+                spectrogram = self.frontend.postnet(spectrogram)
+            return spectrogram.to(device=self.device, dtype=torch.float32).contiguous()
         frames = []
         nframes = 0
-        eframes = self.pre_nframes + self.post_nframes
         while nframes < self.chunk_size * 4:
             spectrum, prob = self.frontend.step(state)
             frames.append(spectrum)

@@ -54,6 +54,7 @@ SIGNATURES = {
     "b2_dec_start": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b2_dec_steps": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p]),
     "b2_dec_poll_errors": (c_int, [c_void_p, c_void_p]),
+    "b2_dec_set_graphs": (c_int, [c_void_p, c_int]),
     "b2_dec_get_step": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "b2_session_reset": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "b2_session_get_pre_frames": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),

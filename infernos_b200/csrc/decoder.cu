@@ -176,10 +176,11 @@ __global__ void k_dec_gather(const int32_t *__restrict__ slots, const float *__r
     const int m = blockIdx.x, c = threadIdx.x;            // 128 threads
     if (m >= M) return;
     int sl = slots[m];
-    if (sl < 0 || sl >= max_sessions) { if (c == 0) atomicOr(err, 1); sl = max_sessions; }
+    if (sl == -1) sl = max_sessions;                       // padding row of a graph bucket: computed on the scratch slot, not an error
+    else if (sl < 0 || sl >= max_sessions) { if (c == 0) atomicOr(err, 1); sl = max_sessions; }
     if (c == 0) rowslot[m] = sl;
     int t = step[sl];
-    if (t >= max_steps) { if (c == 0) atomicOr(err, 4); t = max_steps - 1; }
+    if (t >= max_steps) { if (c == 0 && sl != max_sessions) atomicOr(err, 4); t = max_steps - 1; }
     if (c == 0) rowpos[m] = t;
     const float v = c < NMEL ? last[(size_t)sl * NMEL + c] : 0.0f;
     if (BF) x0b[(size_t)m * 128 + c] = __float2bfloat16_rn(v);
@@ -325,7 +326,7 @@ __global__ void k_relu_dual(const float *__restrict__ x, float *__restrict__ h, 
 
 // out[m] = feat (2 x 80) | prob logits (2) -> the call's mel [M][2*nsteps][80], the stop probabilities [M][nsteps][2], the slot's last frame and step
 __global__ void k_dec_finish(const float *__restrict__ out, const int32_t *__restrict__ slots, int M, int s, int nsteps,
-                             float *__restrict__ mel, float *__restrict__ prob, float *__restrict__ last, int32_t *__restrict__ step) {
+                             float *__restrict__ mel, float *__restrict__ prob, float *__restrict__ last, int32_t *__restrict__ step, int max_sessions) {
     const int m = blockIdx.x, c = threadIdx.x;           // 192 threads
     if (m >= M) return;
     const int sl = slots[m];
@@ -336,7 +337,7 @@ __global__ void k_dec_finish(const float *__restrict__ out, const int32_t *__res
     } else if (c < 2 * NMEL + 2) {
         prob[((size_t)m * nsteps + s) * 2 + (c - 2 * NMEL)] = 1.0f / (1.0f + expf(-v));
     }
-    if (c == 0) step[sl] += 1;
+    if (c == 0 && sl != max_sessions) step[sl] += 1;       // the scratch slot (padding rows, rejected ids) stays at step 0
 }
 
 // start of a sentence: zero frame, step 0, normalised speaker vector (F.normalize: x / max(||x||, 1e-12)), encoder length
@@ -428,6 +429,12 @@ struct b2_dec {
     CUtensorMap tm_x0, tm_p1, tm_p2, tm_cat, tm_h, tm_ctx, tm_f1, tm_enc;
     int *err_h = nullptr, *err_d = nullptr;
     unsigned long long calls = 0;
+    // one CUDA graph per (padded batch size, steps per call): a call is ~74 launches per step, 16 steps (b2_dec_steps)
+    bool use_graphs = true;
+    std::map<unsigned long long, std::pair<cudaGraphExec_t, int>> graphs;    // key -> (exec, kernel nodes); exec == nullptr: seen once, run eagerly
+    int32_t *g_slots = nullptr;
+    float *g_mel = nullptr, *g_prob = nullptr;
+    size_t g_cap_rows = 0;
 };
 
 namespace {
@@ -718,7 +725,7 @@ int steps_impl(b2_dec *d, const int32_t *d_slots, int n, int nsteps, float *d_me
                 B2_LAUNCH_OK("k_add_ln");
             }
             if (linear(d, d->outl, d->h, &d->tm_h, M, 0, nullptr, d->out, nullptr, st)) return 1;
-            k_dec_finish<<<M, OUTP, 0, st>>>(d->out, slots, M, s, nsteps, mel, prob, d->last, d->step);
+            k_dec_finish<<<M, OUTP, 0, st>>>(d->out, slots, M, s, nsteps, mel, prob, d->last, d->step, d->max_sessions);
             B2_LAUNCH_OK("k_dec_finish");
         }
     }
@@ -776,6 +783,7 @@ void b2_dec_destroy(b2_dec *d) {
     if (!d) return;
     cudaSetDevice(d->device);
     cudaDeviceSynchronize();
+    for (auto &kv : d->graphs) if (kv.second.first) cudaGraphExecDestroy(kv.second.first);
     for (void *p : d->allocs) cudaFree(p);
     if (d->err_h) cudaFreeHost(d->err_h);
     delete d;
@@ -825,7 +833,58 @@ int b2_dec_steps(b2_dec *d, const int32_t *d_slots, int n, int nsteps, const flo
     cudaStream_t st = (cudaStream_t)stream;
     k_make_scales<<<cdiv(nsteps * 2 * PRE, 256), 256, 0, st>>>(d_masks, (unsigned long long)seed, d->calls++, nsteps, d->scales);
     B2_LAUNCH_OK("k_make_scales");
-    return d->mode == B2_MODE_BF16 ? steps_impl<__nv_bfloat16>(d, d_slots, n, nsteps, d_mel, d_prob, st) : steps_impl<float>(d, d_slots, n, nsteps, d_mel, d_prob, st);
+    auto run = [&](const int32_t *sl, int rows, float *mel, float *prob) {
+        return d->mode == B2_MODE_BF16 ? steps_impl<__nv_bfloat16>(d, sl, rows, nsteps, mel, prob, st) : steps_impl<float>(d, sl, rows, nsteps, mel, prob, st);
+    };
+    if (!d->use_graphs) return run(d_slots, n, d_mel, d_prob);
+    // Graph path.  The batch is padded to a bucket size with rows on the scratch slot (id -1) so that a few graphs cover every batch size;
+    // slots and outputs go through fixed staging buffers (a graph replays fixed addresses).  A (bucket, nsteps) pair runs eagerly the first
+    // time it is seen (every kernel sets its attributes outside a capture) and is captured on its second use.
+    const int nb = n <= 64 ? ((n + 7) / 8) * 8 : n <= 512 ? ((n + 31) / 32) * 32 : ((n + 127) / 128) * 128;
+    if ((size_t)nb > d->g_cap_rows) {
+        B2_CUDA_OK(cudaStreamSynchronize(st));
+        for (auto &kv : d->graphs) if (kv.second.first) cudaGraphExecDestroy(kv.second.first);
+        d->graphs.clear();                                   // they point into the old staging buffers
+        const size_t cap = std::max<size_t>((size_t)nb, std::min<size_t>((size_t)d->max_sessions + 128, d->g_cap_rows * 2));
+        if (dalloc(d, &d->g_slots, cap) || dalloc(d, &d->g_mel, cap * 2 * 64 * NMEL) || dalloc(d, &d->g_prob, cap * 64 * 2)) return 1;
+        d->g_cap_rows = cap;
+    }
+    const unsigned long long key = ((unsigned long long)nb << 8) | (unsigned long long)nsteps;
+    B2_CUDA_OK(cudaMemsetAsync(d->g_slots, 0xFF, (size_t)nb * sizeof(int32_t), st));          // -1 = padding row
+    B2_CUDA_OK(cudaMemcpyAsync(d->g_slots, d_slots, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    auto it = d->graphs.find(key);
+    if (it == d->graphs.end()) {
+        d->graphs.emplace(key, std::make_pair((cudaGraphExec_t) nullptr, 0));
+        if (run(d->g_slots, nb, d->g_mel, d->g_prob)) return 1;
+    } else {
+        if (!it->second.first) {
+            cudaGraph_t g = nullptr;
+            cudaGraphExec_t ge = nullptr;
+            const uint64_t l0 = g_launches.load();
+            B2_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            const int rc = run(d->g_slots, nb, d->g_mel, d->g_prob);
+            cudaError_t e = cudaStreamEndCapture(st, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+            if (e != cudaSuccess) return set_error("b2_dec_steps: cudaStreamEndCapture: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&ge, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return set_error("b2_dec_steps: cudaGraphInstantiate: %s", cudaGetErrorString(e));
+            const int nk = (int)(g_launches.load() - l0);
+            g_launches.fetch_sub((uint64_t)nk);
+            it->second = std::make_pair(ge, nk);
+        }
+        B2_CUDA_OK(cudaGraphLaunch(it->second.first, st));
+        count_launch(it->second.second);
+    }
+    B2_CUDA_OK(cudaMemcpyAsync(d_mel, d->g_mel, (size_t)n * 2 * nsteps * NMEL * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    B2_CUDA_OK(cudaMemcpyAsync(d_prob, d->g_prob, (size_t)n * nsteps * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int b2_dec_set_graphs(b2_dec *d, int on) {
+    if (!d) return set_error("null decoder handle");
+    d->use_graphs = on != 0;
+    return 0;
 }
 
 int b2_dec_poll_errors(b2_dec *d, void *stream) {

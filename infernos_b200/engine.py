@@ -413,6 +413,9 @@ class TTSDecoder:
                                              mel.data_ptr(), prob.data_ptr(), _stream_ptr(self.device)), "dec_steps")
         return mel, prob
 
+    def set_graphs(self, on: bool) -> None:
+        _lib.check(self.lib.b2_dec_set_graphs(self.h, 1 if on else 0), "dec_set_graphs")
+
     def poll_errors(self) -> None:
         with torch.cuda.device(self.index):
             _lib.check(self.lib.b2_dec_poll_errors(self.h, _stream_ptr(self.device)), "dec_poll_errors")

@@ -123,3 +123,84 @@ def test_decoder_feeds_the_tail_without_leaving_the_device(sd):
         ref, _ = otail.tts_tail(vsd, csd, torch.zeros(3, 4, 80), ref_mel)
     assert float((a - ref).abs().max()) <= 1e-3
     assert np.array_equal(g.numpy(), ocodec.encode_f32(a.numpy(), 0))
+
+
+def test_engine_end_to_end_with_the_gpu_front_half(sd):
+    """HelloSippyRTPipe with B200Frontend: text -> (scripted tokenizer / encoder, the per-sentence glue) -> GPU decoder -> GPU post-net + tail ->
+    unbatch_and_dispatch, against the oracle chain decoder -> post-net -> tail -> unbatch arithmetic with the same dropout masks."""
+    import uuid
+    from infernos_b200.engine import TTSDecoder
+    from infernos_b200.HelloSippyTTSRT.HelloSippyRTPipe import (B200Frontend, HelloSippyPipeState, HelloSippyPipeStateBatched, HelloSippyPlayRequest,
+                                                                 HelloSippyRTPipe)
+    from oracle import decoder as odec
+    from oracle import tail as otail
+    vsd, csd, psd = synth.hifigan_state_dict(), synth.chunker_state_dict(), synth.postnet_state_dict()
+    texts = ["first sentence", "the second one is longer"]
+    encs = {0: synth.synth_encoder_states(1, 9, seed=31)[0], 1: synth.synth_encoder_states(1, 13, seed=32)[0]}
+    g = torch.Generator().manual_seed(8)
+    masks = [(torch.rand(16, 2, 256, generator=g) < 0.5).float() for _ in range(4)]
+
+    def tokenizer(text):
+        i = texts.index(text)
+        return torch.full((1, encs[i].size(0)), i + 4, dtype=torch.long)
+
+    def encoder(ids, mask):
+        L = ids.size(1)
+        return torch.stack([torch.nn.functional.pad(encs[int(r[0]) - 4], (0, 0, 0, L - encs[int(r[0]) - 4].size(0))) for r in ids])
+
+    dec = TTSDecoder("cuda:0", sd, mode="fp32", max_sessions=4, max_steps=64, max_enc_len=16)
+    fe = B200Frontend(dec, tokenizer, encoder, mask_fn=lambda c: masks[c])
+    pp = HelloSippyRTPipe("cuda:0", output_sr=8000, frontend=fe, vocoder_state_dict=vsd, chunker_state_dict=csd, postnet_state_dict=psd,
+                          mode="fp32", max_sessions=4, speaker_embeddings=[synth.synth_speakers(1, seed=33)])
+    pp.maxlenratio = 4.0                                    # maxlen = int(13 * 4 / 2) = 26 decoder steps for the batch: both sentences end in call 2
+    got = [[], []]
+    ended = [0, 0]
+
+    def cb(i):
+        def f(chunk):
+            if chunk is None:
+                ended[i] += 1
+            else:
+                got[i].append(chunk.clone())
+        return f
+    reqs = [HelloSippyPlayRequest(uuid.uuid4(), t, pp.get_voice(0), cb(i)) for i, t in enumerate(texts)]
+    state = HelloSippyPipeStateBatched([HelloSippyPipeState(pp, r) for r in reqs], pp)
+    assert (state.minlen, state.maxlen) == (0, 26)          # batch-wide, from the padded encoder length like the reference (:117-118)
+    ncalls = 0
+    while True:
+        pp.infer(state)
+        ncalls += 1
+        if not pp.unbatch_and_dispatch(state):
+            break
+    dec.close()
+    # oracle chain
+    L = 13
+    enc = torch.stack([torch.nn.functional.pad(encs[i], (0, 0, 0, L - encs[i].size(0))) for i in range(2)])
+    emask = torch.stack([(torch.arange(L) < encs[i].size(0)).to(torch.int) for i in range(2)])
+    spk = synth.synth_speakers(1, seed=33).repeat(2, 1)
+    st = odec.DecoderState(sd, enc, emask, spk)
+    pre = torch.zeros(2, 4, 80)
+    ends, idx, live, starts = [-1, -1], 0, [True, True], [1, 1]
+    ref = [[], []]
+    with torch.no_grad():
+        for c in range(ncalls):
+            frames = []
+            for s in range(16):
+                sp, pr = odec.step(sd, st, masks[c][s])
+                frames.append(sp)
+                for i in range(2):
+                    if ends[i] < 0 and (bool((pr[i] >= 0.5).any()) or 26 <= idx):
+                        ends[i] = idx + 2
+                idx += 1
+            mel = otail.postnet_forward(psd, torch.cat(frames, 1))
+            audio, pre = otail.tts_tail(vsd, csd, pre, mel)
+            sl, fin, more = otail.unbatch_slices(audio.size(1), idx, starts, ends, live)
+            for i in range(2):
+                if sl[i] is not None:
+                    ref[i].append(audio[i, sl[i][0]:sl[i][1]])
+                if fin[i]:
+                    live[i] = False
+    assert ended == [1, 1] and ncalls == 2
+    for i in range(2):
+        a, r = torch.cat(got[i]), torch.cat(ref[i])
+        assert a.shape == r.shape and float((a - r).abs().max()) <= 1e-3
