@@ -432,6 +432,7 @@ struct b2_dec {
     // one CUDA graph per (padded batch size, steps per call): a call is ~74 launches per step, 16 steps (b2_dec_steps)
     bool use_graphs = true;
     std::map<unsigned long long, std::pair<cudaGraphExec_t, int>> graphs;    // key -> (exec, kernel nodes); exec == nullptr: seen once, run eagerly
+    cudaStream_t g_stream = nullptr;           // captures run here: the caller's stream may be the legacy default stream, which cannot capture
     int32_t *g_slots = nullptr;
     float *g_mel = nullptr, *g_prob = nullptr;
     size_t g_cap_rows = 0;
@@ -784,6 +785,7 @@ void b2_dec_destroy(b2_dec *d) {
     cudaSetDevice(d->device);
     cudaDeviceSynchronize();
     for (auto &kv : d->graphs) if (kv.second.first) cudaGraphExecDestroy(kv.second.first);
+    if (d->g_stream) cudaStreamDestroy(d->g_stream);
     for (void *p : d->allocs) cudaFree(p);
     if (d->err_h) cudaFreeHost(d->err_h);
     delete d;
@@ -861,9 +863,15 @@ int b2_dec_steps(b2_dec *d, const int32_t *d_slots, int n, int nsteps, const flo
             cudaGraph_t g = nullptr;
             cudaGraphExec_t ge = nullptr;
             const uint64_t l0 = g_launches.load();
-            B2_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            const int rc = run(d->g_slots, nb, d->g_mel, d->g_prob);
-            cudaError_t e = cudaStreamEndCapture(st, &g);
+            if (!d->g_stream) B2_CUDA_OK(cudaStreamCreateWithFlags(&d->g_stream, cudaStreamNonBlocking));
+            cudaStream_t cs = d->g_stream;
+            auto run_on = [&](cudaStream_t s2) {
+                return d->mode == B2_MODE_BF16 ? steps_impl<__nv_bfloat16>(d, d->g_slots, nb, nsteps, d->g_mel, d->g_prob, s2)
+                                               : steps_impl<float>(d, d->g_slots, nb, nsteps, d->g_mel, d->g_prob, s2);
+            };
+            B2_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+            const int rc = run_on(cs);
+            cudaError_t e = cudaStreamEndCapture(cs, &g);
             if (rc) { if (g) cudaGraphDestroy(g); return 1; }
             if (e != cudaSuccess) return set_error("b2_dec_steps: cudaStreamEndCapture: %s", cudaGetErrorString(e));
             e = cudaGraphInstantiate(&ge, g, 0);
