@@ -63,6 +63,7 @@ struct RbParams {
     unsigned long long m_tpw;
     unsigned long long *dbg;   // optional per-CTA phase timestamps (B2_RB_DBG analysis runs)
     int dbg_flags;             // bit 0: no L2 prefetch of the slab at CTA start (B2_RB_NOPF=1: A/B switch)
+    int pf_dist;               // > 0: also prefetch the slab of CTA blockIdx.x + pf_dist into L2 (the CTA that follows this one on the SM)
     float bias1[3 * kRbMaxC];  // conv1 biases                                         (constant bank: uniform loads)
     float cbias[3 * kRbMaxC];  // running sum of conv2 biases: cbias[i] = b2[0] + .. + b2[i]
 };
@@ -183,6 +184,27 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
             const int r = s * 128 + rq0, t = t_base + r;
             if (t >= 0 && t < p.T) {
                 const size_t off = ((size_t)w * p.T + t) * C + cb0;
+#pragma unroll
+                for (int cc = 0; cc < CHW; cc++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + off + cc * 32));
+                if (p.acc_src && r >= p.H && r < p.H + p.V) {
+#pragma unroll
+                    for (int cc = 0; cc < CHW; cc++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc_src + off + cc * 32));
+                }
+            }
+        }
+    }
+    // ... and the slab of the CTA that will take this one's place on the SM (pf_dist CTAs ahead: one resident set) is requested NOW, a whole
+    // CTA lifetime before it is needed, so that its own load phase finds the rows in L2 instead of waiting ~2 us for HBM.
+    if (warp < NEW && p.pf_dist > 0 && blockIdx.x + (unsigned)p.pf_dist < gridDim.x) {
+        const int b2i = (int)blockIdx.x + p.pf_dist;
+        const int w2 = fdiv(b2i, p.m_tpw);
+        const int tb2 = (b2i - w2 * p.tiles_per_win) * p.V - p.H;
+        const int rq0 = (warp & 3) * 32 + lane, cb0 = SSPLIT ? 0 : (warp >> 2) * (CHW * 32);
+#pragma unroll
+        for (int s = SSPLIT ? (warp >> 2) : 0; s < kS; s += SSTEP) {
+            const int r = s * 128 + rq0, t = tb2 + r;
+            if (t >= 0 && t < p.T) {
+                const size_t off = ((size_t)w2 * p.T + t) * C + cb0;
 #pragma unroll
                 for (int cc = 0; cc < CHW; cc++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + off + cc * 32));
                 if (p.acc_src && r >= p.H && r < p.H + p.V) {
@@ -767,6 +789,9 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     p.dbg = dbg_on ? dbg_buf : nullptr;
     static const int nopf = getenv("B2_RB_NOPF") ? atoi(getenv("B2_RB_NOPF")) : 0;
     p.dbg_flags = nopf ? 1 : 0;
+    // look-ahead prefetch distance in CTAs: one resident set (two CTAs per SM at C = 32, one otherwise); B2_RB_PFDIST=0 switches it off
+    static const int pfd_env = getenv("B2_RB_PFDIST") ? atoi(getenv("B2_RB_PFDIST")) : -1;
+    p.pf_dist = pfd_env >= 0 ? pfd_env : sm_count() * (pk.C == 32 ? 2 : 1);
     if (dbg_on) B2_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, dbg_n * 8, st));
     // C = 32: four epilogue warps.  B2_RB32_NEW=8 runs the eight-warp variant (warps 4..7 own the odd sub-tiles, 88 registers per thread so
     // that two CTAs still share an SM).  Measured on the B200 (profiles/r2b_ab_rb32_epilogue_warps.json): SLOWER, 18.3 ms against 15.1 ms for the

@@ -8,7 +8,7 @@
 //     feat_out -> 2 mel frames, prob_out -> 2 stop probabilities   :740-750
 //
 // batched over sessions that live in SLOTS (the same ids as the tail's pre_frames slots): per slot a self-attention KV cache
-// [layer][slot][step][K 768 | V 768], the cross-attention keys / values [slot][pos][layer][K | V], the normalised speaker vector, the last
+// [slot][layer][step][K 768 | V 768], the cross-attention keys / values [slot][layer][pos][K | V], the normalised speaker vector, the last
 // emitted frame and the step counter.  Nothing of this leaves the device between steps; the mel frames of a call are written where
 // b2_tts_tail2(B2_TAIL_APPLY_POSTNET) reads them.
 //
@@ -238,19 +238,38 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
     return r;
 }
 
+// 8 consecutive cache elements (one 16-byte piece of a bf16 row, two of an fp32 row) as floats
+__device__ __forceinline__ void ld_kv8(const float *p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld_kv8(const __nv_bfloat16 *p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4 *>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
 // One query position against a cached sequence, one CTA (128 threads) per (row, head)  (SpeechT5Attention.forward, :872-986; the 1/sqrt(64)
 // scaling is folded into the q projection at pack time).  SELF: the row's new key / value (columns 768.. / 1536.. of qkv) are appended to
 // the slot's cache at its step first, and the sequence is steps 0 .. step; otherwise keys / values are the sentence's cross-attention cache
 // and the sequence is its first enc_len positions (the reference's padding mask).  ctx32 / ctxb: [M][768].
+// Memory-bound (every cached key and value is read once per step): 8 lanes share one position, each owning 8 of the head's 64 dimensions,
+// so a warp reads four whole 128-byte (bf16) rows per load instruction; scores are reduced over the 8 lanes by shuffles, the value sum is
+// kept per lane and folded over positions at the end.
 template <typename KV, bool SELF>
 __global__ void __launch_bounds__(128) k_attend(const float *__restrict__ q, int ldq, const int32_t *__restrict__ slots, const int32_t *__restrict__ rowpos,
                                                const int32_t *__restrict__ enc_len, KV *__restrict__ cache, size_t slot_stride, size_t pos_stride,
                                                size_t layer_off, float *__restrict__ ctx32, __nv_bfloat16 *__restrict__ ctxb) {
-    extern __shared__ float sm[];                      // [T] scores | 64 q | 128 partial | 8 red
+    extern __shared__ float sm[];                      // [T] scores | 64 q | 4 x 64 partial sums | 8 red
     const int m = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, grp = lane >> 3, c8 = (lane & 7) * 8;
     const int sl = slots[m];
     const int T = SELF ? rowpos[m] + 1 : enc_len[sl];
-    float *sc = sm, *qs = sm + ((T + 3) & ~3), *part = qs + HD, *red = part + 128;
+    float *sc = sm, *qs = sm + ((T + 3) & ~3), *part = qs + HD, *red = part + 4 * HD;
     KV *base = cache + (size_t)sl * slot_stride + layer_off + (size_t)h * HD;
     if (tid < HD) {
         qs[tid] = q[(size_t)m * ldq + h * HD + tid];
@@ -261,16 +280,28 @@ __global__ void __launch_bounds__(128) k_attend(const float *__restrict__ q, int
         }
     }
     __syncthreads();
+    float qv[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) qv[e] = qs[c8 + e];
     float mx = -INFINITY;
-    for (int j = tid; j < T; j += 128) {
-        const KV *kr = base + (size_t)j * pos_stride;
+    for (int j0 = warp * 4; j0 < T; j0 += 16) {
+        const int j = j0 + grp;
         float acc = 0.0f;
-#pragma unroll 8
-        for (int d = 0; d < HD; d++) acc = fmaf(qs[d], ld_kv(kr + d), acc);
-        sc[j] = acc;
-        mx = fmaxf(mx, acc);
+        if (j < T) {
+            float kv[8];
+            ld_kv8(base + (size_t)j * pos_stride + c8, kv);
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc = fmaf(qv[e], kv[e], acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (j < T) {
+            if ((lane & 7) == 0) sc[j] = acc;
+            mx = fmaxf(mx, acc);
+        }
     }
-    mx = block_max(mx, red);
+    mx = block_max(mx, red);                            // (its barriers also publish sc[])
     float sum = 0.0f;
     for (int j = tid; j < T; j += 128) {
         const float e = expf(sc[j] - mx);
@@ -278,13 +309,28 @@ __global__ void __launch_bounds__(128) k_attend(const float *__restrict__ q, int
         sum += e;
     }
     sum = block_sum(sum, red);
-    const int d = tid & 63, half = tid >> 6;
-    float acc = 0.0f;
-    for (int j = half; j < T; j += 2) acc = fmaf(sc[j], ld_kv(base + (size_t)j * pos_stride + H + d), acc);
-    part[tid] = acc;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[e] = 0.0f;
+    for (int j = warp * 4 + grp; j < T; j += 16) {
+        float vv[8];
+        ld_kv8(base + (size_t)j * pos_stride + H + c8, vv);
+        const float pj = sc[j];
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[e] = fmaf(pj, vv[e], acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    }
+    if (grp == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) part[warp * HD + c8 + e] = acc[e];
+    }
     __syncthreads();
     if (tid < HD) {
-        const float o = (part[tid] + part[tid + 64]) / sum;
+        const float o = (part[tid] + part[HD + tid] + part[2 * HD + tid] + part[3 * HD + tid]) / sum;
         if (ctx32) ctx32[(size_t)m * H + h * HD + tid] = o;
         if (ctxb) ctxb[(size_t)m * H + h * HD + tid] = __float2bfloat16_rn(o);
     }
@@ -364,15 +410,15 @@ __global__ void __launch_bounds__(256) k_dec_init(const int32_t *__restrict__ sl
 // xkv rows [r0, r0 + rows) of the flattened (session, position) grid -> the slots' cross-attention caches
 template <typename KV>
 __global__ void k_xkv_scatter(const float *__restrict__ xkv, const int32_t *__restrict__ slots, int r0, int rows, int L, KV *__restrict__ xcache,
-                              size_t slot_stride, int max_sessions) {
+                              size_t slot_stride, size_t layer_stride, int max_sessions) {
     const int r = blockIdx.x;
     if (r >= rows) return;
     const int g = r0 + r, m = g / L, j = g - m * L;
     const int sl = slots[m];
     if (sl < 0 || sl >= max_sessions) return;
-    KV *dst = xcache + (size_t)sl * slot_stride + (size_t)j * (NL * 2 * H);
+    KV *dst = xcache + (size_t)sl * slot_stride + (size_t)j * (2 * H);                 // + layer * max_enc * 2H
     const float *src = xkv + (size_t)r * (NL * 2 * H);
-    for (int c = threadIdx.x; c < NL * 2 * H; c += blockDim.x) st_kv(dst + c, src[c]);
+    for (int c = threadIdx.x; c < NL * 2 * H; c += blockDim.x) st_kv(dst + (size_t)(c / (2 * H)) * layer_stride + (c % (2 * H)), src[c]);
 }
 
 __global__ void k_f32_to_bf16(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, size_t n) {
@@ -499,7 +545,7 @@ void fill_linear(std::vector<float> &W, std::vector<float> &B, int Kp, int Np, i
 
 int upload_linear(b2_dec *d, DecLinear &l, int Kp, int Np, const std::vector<float> &W, const std::vector<float> &B) {
     l.K = Kp; l.N = Np;
-    l.nt = (Np % 128 == 0) ? 128 : 64;
+    l.nt = (Np % 128 == 0 && Np >= 2048) ? 128 : 64;        // N = 768 layers: 64-wide tiles double the CTA count (8 x 12 at 1,024 rows)
     if (dalloc(d, &l.bias, (size_t)Np)) return 1;
     B2_CUDA_OK(cudaMemcpy(l.bias, B.data(), (size_t)Np * sizeof(float), cudaMemcpyHostToDevice));
     if (d->mode == B2_MODE_BF16) {
@@ -670,9 +716,9 @@ int steps_impl(b2_dec *d, const int32_t *d_slots, int n, int nsteps, float *d_me
     const bool bf = d->mode == B2_MODE_BF16;
     KV *self_cache = reinterpret_cast<KV *>(d->self_cache), *x_cache = reinterpret_cast<KV *>(d->x_cache);
     const size_t self_slot = (size_t)NL * d->max_steps * 2 * H, self_pos = 2 * H;
-    const size_t x_slot = (size_t)d->max_enc * NL * 2 * H, x_pos = (size_t)NL * 2 * H;
-    const size_t attn_smem_self = ((size_t)((d->max_steps + 3) & ~3) + HD + 128 + 8) * sizeof(float);
-    const size_t attn_smem_x = ((size_t)((d->max_enc + 3) & ~3) + HD + 128 + 8) * sizeof(float);
+    const size_t x_slot = (size_t)NL * d->max_enc * 2 * H, x_pos = 2 * H;            // [slot][layer][pos][K | V], like the self-attention cache
+    const size_t attn_smem_self = ((size_t)((d->max_steps + 3) & ~3) + HD + 4 * HD + 8) * sizeof(float);
+    const size_t attn_smem_x = ((size_t)((d->max_enc + 3) & ~3) + HD + 4 * HD + 8) * sizeof(float);
     if (attn_smem_self > 200 * 1024 || attn_smem_x > 200 * 1024) return set_error("decoder: max_steps / max_enc_len too large for the attention kernel");
     static bool attr_done[64][2] = {};
     if (d->device < 64 && !attr_done[d->device][bf ? 1 : 0]) {
@@ -713,7 +759,7 @@ int steps_impl(b2_dec *d, const int32_t *d_slots, int n, int nsteps, float *d_me
                 B2_LAUNCH_OK("k_add_ln");
                 // cross-attention (:1137-1147)
                 if (linear(d, d->xq[i], d->h, &d->tm_h, M, 0, nullptr, d->qkv32, nullptr, st)) return 1;
-                k_attend<KV, false><<<dim3((unsigned)M, NH), 128, attn_smem_x, st>>>(d->qkv32, H, slots, d->rowpos, d->enc_len, x_cache, x_slot, x_pos, (size_t)i * 2 * H,
+                k_attend<KV, false><<<dim3((unsigned)M, NH), 128, attn_smem_x, st>>>(d->qkv32, H, slots, d->rowpos, d->enc_len, x_cache, x_slot, x_pos, (size_t)i * d->max_enc * 2 * H,
                                                                                        bf ? nullptr : d->ctx, bf ? d->ctxb : nullptr);
                 B2_LAUNCH_OK("k_attend(cross)");
                 if (linear(d, d->xo[i], d->ctx, &d->tm_ctx, M, 0, nullptr, d->tmp, nullptr, st)) return 1;
@@ -737,7 +783,7 @@ template <typename KV>
 int start_impl(b2_dec *d, const int32_t *d_slots, const float *d_enc, int n, int L, cudaStream_t st) {
     const bool bf = d->mode == B2_MODE_BF16;
     KV *x_cache = reinterpret_cast<KV *>(d->x_cache);
-    const size_t x_slot = (size_t)d->max_enc * NL * 2 * H;
+    const size_t x_slot = (size_t)NL * d->max_enc * 2 * H, x_layer = (size_t)d->max_enc * 2 * H;
     const long long rows_total = (long long)n * L;
     for (long long r0 = 0; r0 < rows_total; r0 += d->max_rows) {
         const int rows = (int)std::min<long long>(d->max_rows, rows_total - r0);
@@ -748,7 +794,7 @@ int start_impl(b2_dec *d, const int32_t *d_slots, const float *d_enc, int n, int
             B2_LAUNCH_OK("k_f32_to_bf16");
         }
         if (linear(d, d->xkv, A, &d->tm_enc, rows, 0, nullptr, d->xkv32, nullptr, st)) return 1;
-        k_xkv_scatter<KV><<<rows, 256, 0, st>>>(d->xkv32, d_slots, (int)r0, rows, L, x_cache, x_slot, d->max_sessions);
+        k_xkv_scatter<KV><<<rows, 256, 0, st>>>(d->xkv32, d_slots, (int)r0, rows, L, x_cache, x_slot, x_layer, d->max_sessions);
         B2_LAUNCH_OK("k_xkv_scatter");
     }
     return 0;
