@@ -789,8 +789,10 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     p.dbg = dbg_on ? dbg_buf : nullptr;
     static const int nopf = getenv("B2_RB_NOPF") ? atoi(getenv("B2_RB_NOPF")) : 0;
     p.dbg_flags = nopf ? 1 : 0;
-    // look-ahead prefetch distance in CTAs: one resident set (two CTAs per SM at C = 32, one otherwise); B2_RB_PFDIST=0 switches it off
-    static const int pfd_env = getenv("B2_RB_PFDIST") ? atoi(getenv("B2_RB_PFDIST")) : -1;
+    // look-ahead prefetch distance in CTAs (B2_RB_PFDIST=-1: one resident set, i.e. two CTAs per SM at C = 32, one otherwise).  Measured on the
+    // B200 (profiles/r2f_ab_lookahead_prefetch.json): no gain (nine ResBlock launches 15.67 ms with it, 15.41 ms without) -- the CTA's own
+    // prefetch at its start already hides the HBM latency behind the co-resident CTA.  Off by default.
+    static const int pfd_env = getenv("B2_RB_PFDIST") ? atoi(getenv("B2_RB_PFDIST")) : 0;
     p.pf_dist = pfd_env >= 0 ? pfd_env : sm_count() * (pk.C == 32 ? 2 : 1);
     if (dbg_on) B2_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, dbg_n * 8, st));
     // C = 32: four epilogue warps.  B2_RB32_NEW=8 runs the eight-warp variant (warps 4..7 own the odd sub-tiles, 88 registers per thread so

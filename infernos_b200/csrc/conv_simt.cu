@@ -3,6 +3,7 @@
 //   AmendmentNetwork1.forward (HelloSippyTTSRT/HelloSippyRT.py:219-237)
 //   window builder (HelloSippyTTSRT/HelloSippyRTPipe.py:231-235)
 #include "conv_simt.cuh"
+#include <algorithm>
 
 namespace b2 {
 
@@ -364,6 +365,31 @@ __global__ void __launch_bounds__(192) k_chunker_pre(const float *__restrict__ m
         }
         __syncthreads();
     }
+}
+
+// Operand of the chunker prologue on tensor cores: inb[w][t][ci] = audio[w][12 ci + t] (ci < 256), mel_flat[w][12 (ci - 256) + t] (ci < 336),
+// 0 (ci < 384) -- the two raw `.view` reinterpretations of HelloSippyRT.py:221-224 side by side as one channels-last bf16 tensor [W][12][384].
+__global__ void __launch_bounds__(384) k_chunker_in(const float *__restrict__ mel, const float *__restrict__ audio, __nv_bfloat16 *__restrict__ inb, int W) {
+    const int ci = threadIdx.x;
+    for (int w = blockIdx.x; w < W; w += gridDim.x) {
+        float v[12];
+        const float *src = ci < 256 ? audio + (long long)w * 3072 + 12 * ci : (ci < 336 ? mel + (long long)w * 960 + 12 * (ci - 256) : nullptr);
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const float4 f = src ? __ldg(reinterpret_cast<const float4 *>(src) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+        }
+        __nv_bfloat16 *o = inb + (long long)w * 12 * 384 + ci;
+#pragma unroll
+        for (int t = 0; t < 12; t++) o[t * 384] = __float2bfloat16_rn(v[t]);
+    }
+}
+
+int launch_chunker_in(const float *mel, const float *audio, __nv_bfloat16 *inb, int W, cudaStream_t st) {
+    if (W <= 0) return 0;
+    k_chunker_in<<<(unsigned)std::min<long long>(W, (long long)sm_count() * 8), 384, 0, st>>>(mel, audio, inb, W);
+    B2_LAUNCH_OK("k_chunker_in");
+    return 0;
 }
 
 int launch_chunker_pre(const float *mel, const float *audio, const float *wm, const float *bm, const float *wa, const float *ba,

@@ -48,6 +48,8 @@ int launch_normalise(const float *mel, const float *mean, const float *scale, fl
 // z0 fp32 and/or z0b = bf16(leaky_relu(z0, 0.01)) (operand of the first chunker upsampler on tensor cores)
 int launch_chunker_pre(const float *mel, const float *audio, const float *wm, const float *bm, const float *wa, const float *ba,
                        float *z0, __nv_bfloat16 *z0b, int W, cudaStream_t st);
+// tensor-core form of the prologue: the two `.view`s as ONE bf16 channels-last operand [W][12][384] (audio channels 0..255, mel 256..335, zero pad)
+int launch_chunker_in(const float *mel, const float *audio, __nv_bfloat16 *inb, int W, cudaStream_t st);
 // chunker epilogue (HelloSippyRT.py:235-237): out[w][i] = tanh(audio[w][512+i] * lrelu(post[w][i%8][i/8], 0.01))
 int launch_chunker_final(const float *audio, const float *post, float *out, int W, cudaStream_t st);
 // vocoder-only trim for calls that bypass the chunker: out[w][i] = audio[w][512+i]

@@ -43,6 +43,7 @@ struct Workspace {
     float *z0 = nullptr, *z1 = nullptr, *z2 = nullptr, *zy = nullptr, *z3 = nullptr, *post = nullptr;
     __nv_bfloat16 *win_norm_b = nullptr;               // [F][128] bf16, bins 80..127 zero (BF16 mode)
     __nv_bfloat16 *z0b = nullptr, *z1b = nullptr, *z2b = nullptr, *zyb = nullptr;   // chunker operands (BF16 mode)
+    __nv_bfloat16 *cinb = nullptr, *z3b = nullptr;     // [W][12][384] prologue operand; [W][192][64] bf16(lrelu(z3, 0.01)) = operand of post_conv
     float *audio16k = nullptr;                         // [W][2048]
     // post-net, sized for 12 frames per window like the rest: conv output, ping-pong operands, the post-net's mel
     float *pn_a32 = nullptr, *pn_f0 = nullptr, *pn_f1 = nullptr, *pn_mel = nullptr;    // [F][256] x3, [F][80]
@@ -87,6 +88,12 @@ struct b2_ctx {
     // chunker
     float *cwm = nullptr, *cbm = nullptr, *cwa = nullptr, *cba = nullptr;
     b2::Layer c_up[2], c_res1, c_res2, c_post;
+    // BF16 mode: the prologue (conv_pre_m + conv_pre_a as one block-diagonal 384 -> 256 conv, 192 real outputs) and post_conv (k8 s24 = a
+    // K = 512 GEMM over strided rows of z3) on tensor cores
+    b2::Layer c_pre_tc;
+    __nv_bfloat16 *c_post_wbf = nullptr;               // [256][512] bf16: W[n][j * 64 + ci] = post_conv.weight[n][ci][j]
+    void *c_post_tmA = nullptr, *c_post_tmB = nullptr; // CUtensorMap: A over z3b with a 24-row (1536-element) stride, B over c_post_wbf
+    bool chunker_tc = false;
 
     // SpeechT5 decoder post-net (optional): five k5 convs, batch norm folded in
     bool has_postnet = false;

@@ -21,6 +21,7 @@
 #include "conv_simt.cuh"
 #include "conv_umma.cuh"
 #include "umma_ptx.cuh"
+#include "gemm_tc.cuh"
 #include "../../include/infernos_b200.h"
 
 #include <cuda.h>
@@ -501,17 +502,7 @@ int get_encoder() {
     return 0;
 }
 
-// row-major bf16 [rows][K] -> TMA map with a (64 x box_rows) box, 128-byte swizzle
-int make_map(CUtensorMap *tm, const void *ptr, int rows, int K, int box_rows) {
-    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error("decoder: cuTensorMapEncodeTiled failed with CUresult %d (rows %d K %d)", (int)r, rows, K);
-    return 0;
-}
+int make_map(CUtensorMap *tm, const void *ptr, int rows, int K, int box_rows) { return make_tma_2d_bf16(tm, ptr, rows, K, K, box_rows); }
 
 template <typename T>
 int dalloc(b2_dec *d, T **p, size_t n, bool zero = true) {
@@ -578,27 +569,58 @@ int upload_vec(b2_dec *d, float **dst, const HostTensor &t) {
     return 0;
 }
 
+
+}  // namespace
+
+namespace b2 {
+
+int make_tma_2d_bf16(CUtensorMap *tm, const void *ptr, long long rows, int K, long long row_stride, int box_rows) {
+    if (get_encoder()) return 1;
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)row_stride * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld K %d stride %lld)", (int)r, rows, K, row_stride);
+    return 0;
+}
+
 static bool g_gemm_attr[64][2] = {};
+
+int launch_gemm_tc(const GemmTcArgs &a, cudaStream_t st) {
+    if (a.M <= 0) return 0;
+    if (!a.tmA || !a.tmB || !a.bias || (a.nt != 64 && a.nt != 128) || a.N % a.nt || a.K % 64 || a.K < 64) return set_error("gemm_tc: bad arguments (N %d nt %d K %d)", a.N, a.nt, a.K);
+    GemmParams p;
+    p.bias = a.bias; p.colscale = a.colscale; p.out32 = a.out32; p.outb = a.outb; p.M = a.M; p.N = a.N; p.K = a.K; p.ldo = a.N; p.act = a.act;
+    dim3 grid((unsigned)cdiv(a.M, 128), (unsigned)(a.N / a.nt));
+    const int slot = a.nt == 128 ? 1 : 0;
+    const size_t smem = (size_t)kGemmStages * (128 * 64 * 2 + (size_t)a.nt * 64 * 2) + (2 * kGemmStages + 1) * 8 + 16;
+    int dev = 0;
+    B2_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 64 && !g_gemm_attr[dev][slot]) {
+        if (a.nt == 128) B2_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else B2_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g_gemm_attr[dev][slot] = true;
+    }
+    if (a.nt == 128) k_gemm_tc<128><<<grid, 192, smem, st>>>(*a.tmA, *a.tmB, p);
+    else k_gemm_tc<64><<<grid, 192, smem, st>>>(*a.tmA, *a.tmB, p);
+    B2_LAUNCH_OK("k_gemm_tc");
+    return 0;
+}
+
+}  // namespace b2
+
+namespace {
 
 // C = act(A W^T + bias) * colscale.  fp32 mode: A32 [M][K] through the CUDA-core conv kernel (+ k_act_scale); bf16 mode: tmA over the bf16 A buffer.
 int linear(b2_dec *d, const DecLinear &l, const float *A32, const CUtensorMap *tmA, int M, int act, const float *colscale,
            float *out32, __nv_bfloat16 *outb, cudaStream_t st) {
     if (M <= 0) return 0;
     if (d->mode == B2_MODE_BF16) {
-        GemmParams p;
-        p.bias = l.bias; p.colscale = colscale; p.out32 = out32; p.outb = outb; p.M = M; p.N = l.N; p.K = l.K; p.ldo = l.N; p.act = act;
-        dim3 grid((unsigned)cdiv(M, 128), (unsigned)(l.N / l.nt));
-        const int slot = l.nt == 128 ? 1 : 0;
-        const size_t smem = (size_t)kGemmStages * (128 * 64 * 2 + (size_t)l.nt * 64 * 2) + (2 * kGemmStages + 1) * 8 + 16;
-        if (d->device < 64 && !g_gemm_attr[d->device][slot]) {
-            if (l.nt == 128) B2_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else B2_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            g_gemm_attr[d->device][slot] = true;
-        }
-        if (l.nt == 128) k_gemm_tc<128><<<grid, 192, smem, st>>>(*tmA, l.tmB, p);
-        else k_gemm_tc<64><<<grid, 192, smem, st>>>(*tmA, l.tmB, p);
-        B2_LAUNCH_OK("k_gemm_tc");
-        return 0;
+        GemmTcArgs g;
+        g.tmA = tmA; g.tmB = &l.tmB; g.bias = l.bias; g.colscale = colscale; g.out32 = out32; g.outb = outb; g.M = M; g.N = l.N; g.K = l.K; g.nt = l.nt; g.act = act;
+        return launch_gemm_tc(g, st);
     }
     ConvArgs a;
     a.in = A32; a.wt = l.w32; a.bias = l.bias; a.residual = nullptr; a.out = out32; a.out_bf16 = nullptr;

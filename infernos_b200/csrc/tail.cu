@@ -8,6 +8,7 @@
 #include "ctx.cuh"
 #include "conv_simt.cuh"
 #include "conv_umma.cuh"
+#include "gemm_tc.cuh"
 #include "../../include/infernos_b200.h"
 
 #include <stdarg.h>
@@ -216,8 +217,17 @@ static int finalize(b2_ctx *c) {
         if (!(w = find(c->chk_raw, "conv_pre_a.weight", {160, 256, 3})) || !(b = find(c->chk_raw, "conv_pre_a.bias", {160}))) return 1;
         if (pack_conv(c, tmp, *w, *b, 1, 1, 1, false)) return 1;
         c->cwa = tmp.w32; c->cba = tmp.bias;
+        static const bool chk_tc = !(getenv("B2_CHUNKER_TC") && atoi(getenv("B2_CHUNKER_TC")) == 0);
+        c->chunker_tc = bf && chk_tc;
         if (!(w = find(c->chk_raw, "upsampler.0.weight", {192, 128, 8})) || !(b = find(c->chk_raw, "upsampler.0.bias", {128}))) return 1;
-        if (pack_convT(c, c->c_up[0], *w, *b, bf)) return 1;
+        if (c->chunker_tc) {
+            // the prologue's output is padded from 192 to 256 channels (one N = 256 tile), so the first upsampler takes 256 input channels
+            HostTensor wp;
+            wp.shape = {256, 128, 8};
+            wp.data.assign((size_t)256 * 128 * 8, 0.0f);
+            std::copy(w->data.begin(), w->data.end(), wp.data.begin());
+            if (pack_convT(c, c->c_up[0], wp, *b, bf)) return 1;
+        } else if (pack_convT(c, c->c_up[0], *w, *b, bf)) return 1;
         if (!(w = find(c->chk_raw, "upsampler.1.weight", {128, 64, 8})) || !(b = find(c->chk_raw, "upsampler.1.bias", {64}))) return 1;
         if (pack_convT(c, c->c_up[1], *w, *b, bf)) return 1;
         if (!(w = find(c->chk_raw, "resblock.conv1.weight", {64, 64, 3})) || !(b = find(c->chk_raw, "resblock.conv1.bias", {64}))) return 1;
@@ -226,6 +236,34 @@ static int finalize(b2_ctx *c) {
         if (pack_conv(c, c->c_res2, *w, *b, 3, 3, 1, bf)) return 1;
         if (!(w = find(c->chk_raw, "post_conv.weight", {256, 64, 8})) || !(b = find(c->chk_raw, "post_conv.bias", {256}))) return 1;
         if (pack_conv(c, c->c_post, *w, *b, 1, 0, 24, false)) return 1;
+        if (c->chunker_tc) {
+            // post_conv as a GEMM: row (window, t) of the operand is the 8 x 64 = 512 contiguous bf16 of z3b rows 24t .. 24t+7
+            std::vector<float> q((size_t)256 * 512);
+            for (int n = 0; n < 256; n++)
+                for (int ci = 0; ci < 64; ci++)
+                    for (int j = 0; j < 8; j++) q[(size_t)n * 512 + j * 64 + ci] = w->data[((size_t)n * 64 + ci) * 8 + j];
+            if (upload_bf16(c, &c->c_post_wbf, q)) return 1;
+            // block-diagonal prologue: out 0..31 = conv_pre_m over in-channels 256..335, out 32..191 = conv_pre_a over in-channels 0..255
+            const HostTensor *wm, *bm, *wa, *ba;
+            if (!(wm = find(c->chk_raw, "conv_pre_m.weight", {32, 80, 3})) || !(bm = find(c->chk_raw, "conv_pre_m.bias", {32})) ||
+                !(wa = find(c->chk_raw, "conv_pre_a.weight", {160, 256, 3})) || !(ba = find(c->chk_raw, "conv_pre_a.bias", {160}))) return 1;
+            HostTensor wp, bp;
+            wp.shape = {256, 384, 3};
+            wp.data.assign((size_t)256 * 384 * 3, 0.0f);
+            bp.shape = {256};
+            bp.data.assign(256, 0.0f);
+            for (int co = 0; co < 32; co++) {
+                bp.data[co] = bm->data[co];
+                for (int ci = 0; ci < 80; ci++)
+                    for (int j = 0; j < 3; j++) wp.data[((size_t)co * 384 + 256 + ci) * 3 + j] = wm->data[((size_t)co * 80 + ci) * 3 + j];
+            }
+            for (int co = 0; co < 160; co++) {
+                bp.data[32 + co] = ba->data[co];
+                for (int ci = 0; ci < 256; ci++)
+                    for (int j = 0; j < 3; j++) wp.data[((size_t)(32 + co) * 384 + ci) * 3 + j] = wa->data[((size_t)co * 256 + ci) * 3 + j];
+            }
+            if (pack_conv(c, c->c_pre_tc, wp, bp, 1, 1, 1, true)) return 1;
+        }
     }
     // SpeechT5 decoder post-net (optional): Conv1d(k5, pad 2, no bias) -> BatchNorm1d(eval) [-> tanh], x5
     // (modeling_speecht5.py:700-737).  y = (conv(x) - mean) / sqrt(var + eps) * gamma + beta is folded into the conv:
@@ -268,8 +306,14 @@ static int finalize(b2_ctx *c) {
     if (dev_alloc(c, &ws.h, F * 8192) || dev_alloc(c, &ws.r, F * 8192) || dev_alloc(c, &ws.s0, F * 8192)) return 1;
     if (bf) {
         if (dev_alloc(c, &ws.win_norm_b, F * 128)) return 1;
-        if (!c->chk_raw.empty() && (dev_alloc(c, &ws.z0b, Wn * 12 * 192) || dev_alloc(c, &ws.z1b, Wn * 48 * 128) ||
+        if (!c->chk_raw.empty() && (dev_alloc(c, &ws.z0b, Wn * 12 * 256) || dev_alloc(c, &ws.z1b, Wn * 48 * 128) ||
                                     dev_alloc(c, &ws.z2b, Wn * 192 * 64) || dev_alloc(c, &ws.zyb, Wn * 192 * 64))) return 1;
+        if (c->chunker_tc) {
+            if (dev_alloc(c, &ws.cinb, Wn * 12 * 384) || dev_alloc(c, &ws.z3b, Wn * 192 * 64 + 512)) return 1;
+            CUtensorMap *ta = new CUtensorMap(), *tb = new CUtensorMap();
+            c->c_post_tmA = ta; c->c_post_tmB = tb;
+            if (make_tma_2d_bf16(ta, ws.z3b, (long long)Wn * 8, 512, 24 * 64, 128) || make_tma_2d_bf16(tb, c->c_post_wbf, 256, 512, 512, 128)) return 1;
+        }
         if (dev_alloc(c, &ws.c0b, F * 512) || dev_alloc(c, &ws.hb, F * 8192) || dev_alloc(c, &ws.yb, F * 8192) ||
             dev_alloc(c, &ws.rb, F * 8192) || dev_alloc(c, &ws.sb, F * 4096)) return 1;
     } else {
@@ -455,8 +499,15 @@ static int chunker_fwd(b2_ctx *c, const float *win_raw, const float *audio, int 
     if (!c->cwm) return set_error("chunker weights were not loaded into this context");
     if (c->mode == B2_MODE_BF16) {
         // middle of the chunker on tensor cores (bf16 operands, fp32 accumulate, fp32 residual): 2 upsamplers + the ResBlock
-        PROF(PC_OTHER, launch_chunker_pre(win_raw, audio, c->cwm, c->cbm, c->cwa, c->cba, nullptr, ws.z0b, W, st));
         UmmaConvArgs u;
+        if (c->chunker_tc) {
+            PROF(PC_OTHER, launch_chunker_in(win_raw, audio, ws.cinb, W, st));
+            u.in = ws.cinb; u.layer = &c->c_pre_tc; u.outb = ws.z0b; u.outb_slope = 0.01f; u.W = W; u.T = 12;
+            PROF(PC_CONV_TC, launch_conv_umma(u, st));
+            u = UmmaConvArgs();
+        } else {
+            PROF(PC_OTHER, launch_chunker_pre(win_raw, audio, c->cwm, c->cbm, c->cwa, c->cba, nullptr, ws.z0b, W, st));
+        }
         u.in = ws.z0b; u.layer = &c->c_up[0]; u.outb = ws.z1b; u.outb_slope = 0.01f; u.W = W; u.T = 12;
         PROF(PC_CONV_TC, launch_conv_umma(u, st));
         u = UmmaConvArgs();
@@ -466,8 +517,18 @@ static int chunker_fwd(b2_ctx *c, const float *win_raw, const float *audio, int 
         u.in = ws.z2b; u.layer = &c->c_res1; u.outb = ws.zyb; u.outb_slope = 0.01f; u.W = W; u.T = 192;
         PROF(PC_CONV_TC, launch_conv_umma(u, st));
         u = UmmaConvArgs();
-        u.in = ws.zyb; u.layer = &c->c_res2; u.residual = ws.z2; u.out32 = ws.z3; u.W = W; u.T = 192;
+        u.in = ws.zyb; u.layer = &c->c_res2; u.residual = ws.z2; u.W = W; u.T = 192;
+        if (c->chunker_tc) { u.outb = ws.z3b; u.outb_slope = 0.01f; } else u.out32 = ws.z3;
         PROF(PC_CONV_TC, launch_conv_umma(u, st));
+        if (c->chunker_tc) {
+            // post_conv (64 -> 256, k8, stride 24, no padding; HelloSippyRT.py:233-234) = [W*8][512] x [512][256]
+            GemmTcArgs g;
+            g.tmA = reinterpret_cast<const CUtensorMap *>(c->c_post_tmA); g.tmB = reinterpret_cast<const CUtensorMap *>(c->c_post_tmB);
+            g.bias = c->c_post.bias; g.out32 = ws.post; g.M = W * 8; g.N = 256; g.K = 512; g.nt = 128;
+            PROF(PC_CONV_TC, launch_gemm_tc(g, st));
+            PROF(PC_OTHER, launch_chunker_final(audio, ws.post, out, W, st));
+            return 0;
+        }
     } else {
     PROF(PC_OTHER, launch_chunker_pre(win_raw, audio, c->cwm, c->cbm, c->cwa, c->cba, ws.z0, nullptr, W, st));
     ConvArgs a0 = conv_args(c->c_up[0], ws.z0, ws.z1, W, 12, 12, 0.01f);
@@ -601,7 +662,9 @@ void b2_ctx_destroy(b2_ctx *c) {
         for (int j = 0; j < 3; j++) resblock_free(c->rb[i][j]);
     }
     umma_free_layer(c->conv_pre);
-    umma_free_layer(c->c_up[0]); umma_free_layer(c->c_up[1]); umma_free_layer(c->c_res1); umma_free_layer(c->c_res2);
+    umma_free_layer(c->c_up[0]); umma_free_layer(c->c_up[1]); umma_free_layer(c->c_res1); umma_free_layer(c->c_res2); umma_free_layer(c->c_pre_tc);
+    if (c->c_post_tmA) delete reinterpret_cast<CUtensorMap *>(c->c_post_tmA);
+    if (c->c_post_tmB) delete reinterpret_cast<CUtensorMap *>(c->c_post_tmB);
     for (int i = 0; i < 5; i++) umma_free_layer(c->pn[i]);
     delete c;
 }

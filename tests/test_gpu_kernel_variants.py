@@ -41,6 +41,8 @@ def _run(tmp_path, name, env):
     ("tall_stage0_tiles", {"B2_UMMA_TALL256": "1"}),
     ("separate_conv_post", {"B2_POST_FUSION": "0"}),
     ("cluster_multicast_weights", {"B2_UMMA_MULTICAST": "1"}),
+    ("eight_epilogue_warps_c32", {"B2_RB32_NEW": "8"}),
+    ("lookahead_slab_prefetch", {"B2_RB_PFDIST": "-1"}),
 ])
 def test_variant_matches_default(tmp_path, name, env):
     ref = _run(tmp_path, "default", {})
@@ -54,3 +56,14 @@ def test_variant_matches_default(tmp_path, name, env):
     assert snr > 46.0, (name, snr, err)
     # mu-law codes are ~13-bit: signals 46+ dB apart still disagree on a good fraction of codes, almost always by one step
     assert (got["g711"] != ref["g711"]).mean() < 0.25
+
+
+def test_chunker_prologue_on_cuda_cores_variant(tmp_path):
+    """B2_CHUNKER_TC=0: the chunker's view-prologue (conv_pre_m / conv_pre_a) and post_conv in fp32 on CUDA cores, as in round 1.  The
+    default runs both on tcgen05 with bf16 operands, so the two paths differ by operand rounding (not only by summation order): they
+    must agree far better than either agrees with the fp32 module (>= 40 dB is the bar there, tests/test_gpu_config_sizes.py)."""
+    ref = _run(tmp_path, "default", {})
+    got = _run(tmp_path, "chunker_cuda_cores", {"B2_CHUNKER_TC": "0"})
+    snr = 10 * np.log10((ref["audio"] ** 2).sum() / max(((ref["audio"] - got["audio"]) ** 2).sum(), 1e-30))
+    print(f"chunker prologue/post_conv tcgen05 vs CUDA cores: snr {snr:.1f} dB")
+    assert snr > 43.0
