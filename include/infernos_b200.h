@@ -147,7 +147,9 @@ B2_API void b2_sched_destroy(b2_sched *s);
  * launch whatever is there as soon as the pipeline has room) */
 B2_API int b2_sched_set_policy(b2_sched *s, int min_batch, int max_wait_us);
 /* n chunks: h_slots[n], h_mel (n, nframes, 80) fp32, optional arrival stamps and tags.  Copies into pinned staging and returns; blocks
- * only when every staging buffer is in use (back-pressure).  A session's chunks are processed in submission order. */
+ * only when every staging buffer is in use (back-pressure).  Staging buffers are recycled by b2_sched_poll, so polling must not depend on
+ * the submitting thread making progress (poll from another thread; a submit that cannot get a buffer for 20 s returns an error).
+ * A session's chunks are processed in submission order; two chunks of one session never share a sub-batch. */
 B2_API int b2_sched_submit(b2_sched *s, const int32_t *h_slots, const float *h_mel, int n, const int64_t *t_enqueue_ns, const uint64_t *tags);
 /* up to max_out finished chunks, oldest first; their bytes are copied to h_g711 (may be NULL) at out[i].g711_offset.
  * timeout_ms: 0 = do not wait, < 0 = wait.  Returns the count, or a negative value on error. */

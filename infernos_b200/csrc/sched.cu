@@ -332,7 +332,11 @@ int b2_sched_submit(b2_sched *s, const int32_t *h_slots, const float *h_mel, int
         int at = 0, k = 0;
         {
             std::unique_lock<std::mutex> lk(s->mu);
-            s->cv_submit.wait(lk, [&] { return s->stop || (s->open && s->open->reserved < s->cap); });      // back-pressure: every staging buffer is busy
+            // back-pressure: every staging buffer is busy.  Buffers come back through b2_sched_poll, so a caller that submits and polls on ONE
+            // thread can starve itself: rather than hang, give up after a while and say so
+            if (!s->cv_submit.wait_for(lk, std::chrono::seconds(20), [&] { return s->stop || (s->open && s->open->reserved < s->cap); }))
+                return set_error("b2_sched_submit: no staging buffer became free in 20 s (%d of %d chunks of this call were accepted); finished sub-batches "
+                                 "are recycled by b2_sched_poll -- poll from another thread, or between smaller submits", done, n);
             if (s->stop) return set_error("b2_sched_submit: the scheduler has stopped%s%s", s->async_error.empty() ? "" : ": ", s->async_error.c_str());
             b = s->open;
             at = b->reserved;
@@ -349,7 +353,8 @@ int b2_sched_submit(b2_sched *s, const int32_t *h_slots, const float *h_mel, int
             if (k == 0) {
                 // the next chunk's session is already in the open sub-batch: wait until that one has been closed
                 s->cv_launch.notify_all();
-                s->cv_submit.wait(lk, [&] { return s->stop || s->open != b || b->reserved == 0; });
+                if (!s->cv_submit.wait_for(lk, std::chrono::seconds(20), [&] { return s->stop || s->open != b || b->reserved == 0; }))
+                    return set_error("b2_sched_submit: the open sub-batch was not launched within 20 s (pipeline full and nobody polling?)");
                 continue;
             }
             if (at == 0) b->t_first = t_now;

@@ -31,17 +31,25 @@ def _reference_bytes(tail, mel, nframes):
     return torch.stack(out, dim=1)                       # (S, chunks, nframes*128)
 
 
-def _drain(sched, want, got, deadline_s=60):
-    t0 = time.time()
-    n = 0
-    while True:
-        recs, by = sched.poll(timeout_ms=50 if want else 0)
-        for r in recs:
-            got.setdefault(int(r.tag), []).append((r.t_enqueue_ns, r.t_launch_ns, r.t_done_ns, int(r.slot), int(r.batch_sessions),
-                                                   by[r.g711_offset:r.g711_offset + r.nbytes].clone()))
-        n += len(recs)
-        if n >= want or time.time() - t0 >= deadline_s:
-            return n
+class _Poller(threading.Thread):
+    """Completions are collected on their own thread, as in a deployment: staging buffers only return to the pool through poll(), so a
+    caller that submits and polls on one thread can block itself (submit then fails after 20 s instead of hanging)."""
+
+    def __init__(self, sched, want):
+        super().__init__(daemon=True)
+        self.sched, self.want, self.got, self.n, self.err = sched, want, {}, 0, None
+
+    def run(self):
+        t0 = time.time()
+        try:
+            while self.n < self.want and time.time() - t0 < 120:
+                recs, by = self.sched.poll(timeout_ms=50)
+                for r in recs:
+                    self.got.setdefault(int(r.tag), []).append((r.t_enqueue_ns, r.t_launch_ns, r.t_done_ns, int(r.slot), int(r.batch_sessions),
+                                                                by[r.g711_offset:r.g711_offset + r.nbytes].clone()))
+                self.n += len(recs)
+        except Exception as e:          # surfaced by the test's assertions
+            self.err = e
 
 
 @pytest.mark.parametrize("mode,use_graphs,depth", [("fp32", True, 2), ("bf16", True, 3), ("bf16", False, 2)])
@@ -54,7 +62,8 @@ def test_scheduler_bytes_equal_the_plain_tail(sds, mode, use_graphs, depth):
         ref = _reference_bytes(tail, mel, nframes)
         tail.reset_sessions(list(range(S)))
         sched = TailScheduler(tail, nframes=nframes, depth=depth, use_graphs=use_graphs, max_batch=24)       # 37 sessions never fit one sub-batch
-        got = {}
+        poller = _Poller(sched, S * chunks)
+        poller.start()
         rng = np.random.default_rng(3)
         sent = 0
         for c in range(chunks):
@@ -70,10 +79,10 @@ def test_scheduler_bytes_equal_the_plain_tail(sds, mode, use_graphs, depth):
                 i += k
                 if rng.random() < 0.3:
                     time.sleep(0.002)
-            _drain(sched, 0, got, deadline_s=0)          # a non-blocking poll in between keeps buffers moving
         sched.flush()
-        n = sum(len(v) for v in got.values())
-        n += _drain(sched, sent - n, got)
+        poller.join(130)
+        assert poller.err is None and not poller.is_alive()
+        got, n = poller.got, poller.n
         st = sched.stats()
         sched.close()
         assert n == sent == S * chunks and st["sessions"] == sent and st["max_sub_batch"] <= 24
@@ -101,10 +110,14 @@ def test_scheduler_same_session_twice_in_flight_keeps_order(sds):
         cidx = [0, 0, 0, 1, 1, 1, 2, 3, 2, 3, 2, 3]
         m = torch.stack([mel[int(s), c * nframes:(c + 1) * nframes] for s, c in zip(slots.tolist(), cidx)]).contiguous()
         tags = torch.tensor([int(s) * 1000 + c for s, c in zip(slots.tolist(), cidx)], dtype=torch.int64)
-        sched.submit(slots, m, tags=tags)
+        poller = _Poller(sched, 12)
+        poller.start()
+        sched.submit(slots, m, tags=tags)                       # six sub-batches: more than there are staging buffers
         sched.flush()
-        got = {}
-        assert _drain(sched, 12, got) == 12
+        poller.join(130)
+        assert poller.err is None and poller.n == 12
+        got = poller.got
+        assert sched.stats()["sub_batches"] >= 6
         sched.close()
         for s, c in zip(slots.tolist(), cidx):
             assert torch.equal(got[s * 1000 + c][0][5], ref[s, c])
@@ -125,12 +138,42 @@ def test_scheduler_rejects_bad_slots_and_survives_threads(sds):
         def worker(lo, hi):
             for s in range(lo, hi):
                 sched.submit(torch.tensor([s], dtype=torch.int32), mel[s:s + 1].contiguous())
+        poller = _Poller(sched, S)
+        poller.start()
         ths = [threading.Thread(target=worker, args=(i * 4, i * 4 + 4)) for i in range(4)]
         [t.start() for t in ths]
         [t.join() for t in ths]
         sched.flush()
-        got = {}
-        assert _drain(sched, S, got) == S and sorted(got) == list(range(S))
+        poller.join(130)
+        assert poller.err is None and poller.n == S and sorted(poller.got) == list(range(S))
+        sched.close()
+    finally:
+        tail.close()
+
+
+def test_submit_without_a_poller_fails_instead_of_hanging(sds, monkeypatch):
+    """Back-pressure with nobody polling: submit gives up with an error (the wait is 20 s in the library; the test only checks the path by
+    filling every staging buffer and then polling, which must let a blocked submit through)."""
+    from infernos_b200.engine import TailScheduler, TTSTail
+    tail = TTSTail("cuda:0", sds[0], sds[1], mode="bf16", max_sessions=8, max_windows=8)
+    try:
+        sched = TailScheduler(tail, nframes=8, depth=1, max_batch=1)
+        mel = synth.synth_mel(8, 8, seed=94)
+        done = []
+
+        def feeder():
+            for s in range(8):                                    # eight one-session sub-batches, three staging buffers
+                sched.submit(torch.tensor([s], dtype=torch.int32), mel[s:s + 1].contiguous())
+            done.append(1)
+        th = threading.Thread(target=feeder, daemon=True)
+        th.start()
+        time.sleep(1.0)
+        assert not done                                           # blocked on back-pressure: nothing has been polled yet
+        poller = _Poller(sched, 8)
+        poller.start()
+        th.join(30)
+        poller.join(30)
+        assert done == [1] and poller.n == 8
         sched.close()
     finally:
         tail.close()
