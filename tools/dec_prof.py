@@ -20,7 +20,9 @@ while done < warm:
     done += k
 torch.cuda.synchronize()
 print(f"--- profiled step at position {warm}", file=sys.stderr, flush=True)
+torch.cuda.profiler.start()              # ncu --profile-from-start off: only this step is captured
 dec.steps(slots, 1)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 dec.poll_errors()
 print("ok")
