@@ -47,12 +47,15 @@ def load_peaks():
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/): measured under the
     profiler at a smaller session count, scaled per window; {} when the summary is absent."""
-    p = os.path.join(ROOT, "profiles", "r1_resblock_traffic.json")
-    try:
-        with open(p) as f:
-            return json.load(f)
-    except Exception:
-        return {}
+    for name in ("r2_resblock_traffic.json", "r1_resblock_traffic.json"):          # the newest capture that is committed
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            d["file"] = "profiles/" + name
+            return d
+        except Exception:
+            continue
+    return {}
 
 
 class ClockSampler:
@@ -455,7 +458,7 @@ def main_b200(args, rank, local_rank, world):
                                                  "stages C=128/64/32, 9 launches per sub-batch)",
                     "achieved": round(tf, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(tf / peaks["tf_sustained"], 4),
                     "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
-                    "traffic": traffic.get("k_resblock_bytes_per_launch"), "traffic_note": traffic.get("note"),
+                    "traffic": traffic.get("k_resblock_bytes_per_launch"), "traffic_note": traffic.get("note"), "traffic_file": traffic.get("file"),
                     "flop_per_launch": round(3 * FLOP_PER_WINDOW_RESBLOCK_STAGE * W_step * psteps / rb_n),
                     "launches": rb_n, "avg_launch_ms": round(rb_ms / max(rb_n, 1), 4), "share_of_step": round(rb_ms / step_ms, 4),
                     "note": "M128xN32/N64 MMAs cap at 40 % / 67 % of the tensor peak (operand fetch from shared memory: 32 + N/4 cycles "

@@ -264,7 +264,10 @@ class B200Frontend:
 
     def length_bounds(self, state, minlenratio, maxlenratio):
         n = state._enc_positions
-        return int(n * minlenratio / self.reduction_factor), min(int(n * maxlenratio / self.reduction_factor), self.decoder.max_steps - 1)
+        # a batch keeps stepping until its last sentence has ended, i.e. up to maxlen + 2 steps rounded up to a whole call of 16: the KV cache
+        # (max_steps positions) has to hold that
+        cap = max(1, self.decoder.max_steps - self.steps_per_call - 4)
+        return int(n * minlenratio / self.reduction_factor), min(int(n * maxlenratio / self.reduction_factor), cap)
 
     def call(self, state):
         """One engine call = 16 decoder steps: -> (frames (B, 32, 80) fp32 on the device, BEFORE the post-net; stop probabilities (B, 16, 2) on the host)."""
