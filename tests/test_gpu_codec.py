@@ -189,3 +189,32 @@ def test_empty_inputs(eng):
 def test_cpu_tensor_is_rejected(eng):
     with pytest.raises(RuntimeError):
         eng.g711_encode(torch.zeros(4))
+
+
+def test_smem_staged_resample_kernel_variant_is_bit_identical(tmp_path):
+    """B2_RS_KERNEL=1 (the cp.async / shared-memory variant of the fused 16k -> 8k + G.711 kernel, kept for A/B runs) must produce the
+    same floats and bytes as the default warp-shuffle kernel on ragged row lengths, both laws."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from infernos_b200 import engine
+g = torch.Generator().manual_seed(5)
+outs = {}
+for rows, L in ((1, 16), (3, 48), (257, 320), (64, 8192), (1000, 1600), (5, 16 * 300)):
+    x = ((torch.rand(rows, L, generator=g) * 2 - 1) * 0.95).cuda()
+    for law in (0, 1):
+        outs[f"b_{rows}_{L}_{law}"] = engine.resample_g711_encode(x, law).cpu().numpy()
+    outs[f"f_{rows}_{L}"] = engine.resample_2to1(x).cpu().numpy()
+np.savez(sys.argv[1], **outs)
+""" % root
+    res = {}
+    for k in ("0", "1"):
+        out = str(tmp_path / f"rs{k}.npz")
+        e = dict(os.environ)
+        e["B2_RS_KERNEL"] = k
+        subprocess.run([sys.executable, "-c", script, out], check=True, env=e, timeout=300)
+        res[k] = np.load(out)
+    for name in res["0"].files:
+        assert np.array_equal(res["0"][name], res["1"][name]), name
