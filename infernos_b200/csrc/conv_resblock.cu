@@ -80,6 +80,27 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         : "memory");
 }
 
+// two 32-column TMEM loads in flight, one wait (the pair epilogue: their latencies overlap)
+__device__ __forceinline__ void tmem_ld32x2(uint32_t ta, uint32_t tb, uint32_t (&a)[32], uint32_t (&b)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+          "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
+          "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),
+          "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31]),
+          "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]),
+          "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]),
+          "=r"(b[16]), "=r"(b[17]), "=r"(b[18]), "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]),
+          "=r"(b[24]), "=r"(b[25]), "=r"(b[26]), "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
+        : "r"(ta), "r"(tb));
+}
+
 // 32 consecutive fp32 of one row (128 bytes) -> registers; zeros when the row is not wanted
 __device__ __forceinline__ void ld_row32(const float *src, bool ok, uint32_t (&v)[32]) {
     if (ok) {
@@ -124,6 +145,14 @@ __device__ __forceinline__ void publish_rows(uint32_t bar, int lane) {
     if (lane == 0) mbar_arrive(bar);
 }
 
+// the same for two sub-tiles at once: one pair of fences, two arrivals
+__device__ __forceinline__ void publish_rows2(uint32_t bar_a, uint32_t bar_b, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) { mbar_arrive(bar_a); mbar_arrive(bar_b); }
+}
+
 static constexpr int kRbDbgEvents = 48, kRbDbgCtas = 4096;
 #define RB_DBG(k) do { if (DBG && p.dbg && blockIdx.x < kRbDbgCtas) p.dbg[(size_t)blockIdx.x * kRbDbgEvents + (k)] = clock64(); } while (0)
 
@@ -136,7 +165,11 @@ static constexpr int kRbDbgEvents = 48, kRbDbgCtas = 4096;
 // C = 32 with NEW = 8 ("sub-tile split"): two CTAs still share an SM, and warps 4..7 take the ODD sub-tiles of every phase (slab load,
 // the six conv epilogues, the final epilogue) that warps 0..3 used to do alone: the epilogue chain of a conv, which bounded the C = 32
 // launches (profiles/r1d_resblock_phase_timestamps.txt: ~3k cycles per conv for ~1k cycles of MMA issue), is walked by twice the warps.
-template <int C, int NEW, int NMW, int EPI, bool DBG>
+// PAIR: the conv epilogues take the sub-tiles two at a time -- both TMEM loads in flight before either is consumed, one proxy fence and one
+// barrier hand-shake per pair instead of per sub-tile.  At C = 32 / 64 with short filters the epilogue warps are the busiest resource of
+// the CTA (each conv costs them kS x ~750 cycles, mostly latency: TMEM load, proxy fence, barrier round trip), so this is where a cycle saved
+// is a cycle off the step.
+template <int C, int NEW, int NMW, int EPI, bool DBG, bool PAIR>
 __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? (NEW == 8 ? 88 : 128) : 168) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ RbParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using G = RbGeom<C>;
@@ -347,6 +380,23 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                 const uint32_t dst = e ? a1_u32 : a2_u32;
                 const float *bias = (e ? p.cbias : p.bias1) + i * C + cbase;
                 const uint32_t full0 = e ? X_FULL(0) : T1_FULL(0), ready0 = e ? A1_READY(0) : A2_READY(0);
+                if constexpr (PAIR && !SSPLIT) {
+#pragma unroll 1
+                    for (int s = 0; s < kS; s += 2) {
+                        mbar_wait(full0 + 8u * (uint32_t)s, par);
+                        mbar_wait(full0 + 8u * (uint32_t)(s + 1), par);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (threadIdx.x == 0 && s == 0) RB_DBG(3 + 4 * i + 2 * e);
+#pragma unroll 1
+                        for (int cc = 0; cc < CHW; cc++) {
+                            uint32_t acc0[32], acc1[32];
+                            tmem_ld32x2(src + (uint32_t)(s * C + cbase + cc * 32), src + (uint32_t)((s + 1) * C + cbase + cc * 32), acc0, acc1);
+                            write_operand_row<kRtot>(dst, s * 128 + rq, cbase + cc * 32, acc0, bias + cc * 32, p.slope, inside(s));
+                            write_operand_row<kRtot>(dst, (s + 1) * 128 + rq, cbase + cc * 32, acc1, bias + cc * 32, p.slope, inside(s + 1));
+                        }
+                        publish_rows2(ready0 + 8u * (uint32_t)s, ready0 + 8u * (uint32_t)(s + 1), lane);
+                    }
+                } else {
 #pragma unroll 1
                 for (int s = s0; s < kS; s += SSTEP) {
                     mbar_wait(full0 + 8u * (uint32_t)s, par);
@@ -359,6 +409,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                         write_operand_row<kRtot>(dst, s * 128 + rq, cbase + cc * 32, acc, bias + cc * 32, p.slope, inside(s));
                     }
                     publish_rows(ready0 + 8u * (uint32_t)s, lane);
+                }
                 }
                 if (threadIdx.x == 0) RB_DBG(4 + 4 * i + 2 * e);
             }
@@ -712,20 +763,30 @@ void resblock_free(ResBlockPack &p) {
 }
 
 
-static bool g_rb_attr[64][4][7] = {};
+static bool g_rb_attr[64][4][14] = {};
 
-template <int C, int NEW, int NMW, int EPI, bool DBG>
-static int launch_rb_(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int wslot) {
+template <int C, int NEW, int NMW, int EPI, bool DBG, bool PAIR>
+static int launch_rb__(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int wslot) {
     int dev = 0;
     B2_CUDA_OK(cudaGetDevice(&dev));
-    const int eslot = DBG ? 6 : EPI;
+    const int eslot = (DBG ? 6 : EPI) + (PAIR ? 7 : 0);
     if (dev < 64 && !g_rb_attr[dev][wslot][eslot]) {
-        B2_CUDA_OK(cudaFuncSetAttribute(k_resblock<C, NEW, NMW, EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B2_CUDA_OK(cudaFuncSetAttribute(k_resblock<C, NEW, NMW, EPI, DBG, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         g_rb_attr[dev][wslot][eslot] = true;
     }
-    k_resblock<C, NEW, NMW, EPI, DBG><<<grid, (NEW + 1 + NMW) * 32, smem, st>>>(tm, p);
+    k_resblock<C, NEW, NMW, EPI, DBG, PAIR><<<grid, (NEW + 1 + NMW) * 32, smem, st>>>(tm, p);
     B2_LAUNCH_OK("k_resblock");
     return 0;
+}
+
+// B2_RB_PAIR=0 keeps the one-sub-tile-at-a-time conv epilogue (A/B runs); the timestamped analysis build is always unpaired
+template <int C, int NEW, int NMW, int EPI, bool DBG>
+static int launch_rb_(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int wslot) {
+    static const bool pair_on = !(getenv("B2_RB_PAIR") && atoi(getenv("B2_RB_PAIR")) == 0);
+    if constexpr (!DBG && NEW != 8 || C != 32) {
+        if (pair_on && !DBG) return launch_rb__<C, NEW, NMW, EPI, false, true>(tm, p, grid, smem, st, wslot);
+    }
+    return launch_rb__<C, NEW, NMW, EPI, DBG, false>(tm, p, grid, smem, st, wslot);
 }
 
 // picks the compile-time epilogue that matches the request (the vocoder's three launches per stage are EPI 0, 1 and 2 or 3);
