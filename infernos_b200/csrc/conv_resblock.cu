@@ -779,10 +779,12 @@ static int launch_rb__(const CUtensorMap &tm, const RbParams &p, unsigned grid, 
     return 0;
 }
 
-// B2_RB_PAIR=0 keeps the one-sub-tile-at-a-time conv epilogue (A/B runs); the timestamped analysis build is always unpaired
+// B2_RB_PAIR=1 runs the paired conv epilogue.  Measured on the B200 (profiles/r2i_ab_paired_epilogue.json): bit-identical results, but no
+// faster -- the nine ResBlock launches 15.37 ms paired against 14.77 ms unpaired in the same run: waiting for the second sub-tile's MMAs before
+// touching the first delays the hand-off to the next convolution by more than the shared fence saves.  Off by default.
 template <int C, int NEW, int NMW, int EPI, bool DBG>
 static int launch_rb_(const CUtensorMap &tm, const RbParams &p, unsigned grid, size_t smem, cudaStream_t st, int wslot) {
-    static const bool pair_on = !(getenv("B2_RB_PAIR") && atoi(getenv("B2_RB_PAIR")) == 0);
+    static const bool pair_on = getenv("B2_RB_PAIR") && atoi(getenv("B2_RB_PAIR")) != 0;
     if constexpr (!DBG && NEW != 8 || C != 32) {
         if (pair_on && !DBG) return launch_rb__<C, NEW, NMW, EPI, false, true>(tm, p, grid, smem, st, wslot);
     }

@@ -43,7 +43,7 @@ def _run(tmp_path, name, env):
     ("cluster_multicast_weights", {"B2_UMMA_MULTICAST": "1"}),
     ("eight_epilogue_warps_c32", {"B2_RB32_NEW": "8"}),
     ("lookahead_slab_prefetch", {"B2_RB_PFDIST": "-1"}),
-    ("unpaired_conv_epilogue", {"B2_RB_PAIR": "0"}),
+    ("paired_conv_epilogue", {"B2_RB_PAIR": "1"}),
 ])
 def test_variant_matches_default(tmp_path, name, env):
     ref = _run(tmp_path, "default", {})
