@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int16, c_int32, c_int64, c_size_t, c_uint8, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libinfernos_b200.so")
+SO_PATH = os.environ.get("B2_SO_PATH") or os.path.join(HERE, "libinfernos_b200.so")      # B2_SO_PATH: a variant build for A/B runs
 
 MODE_FP32, MODE_BF16 = 0, 1
 LAW_ULAW, LAW_ALAW, LAW_NONE = 0, 1, -1

@@ -29,14 +29,15 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), so_out: str = SO, tag: str = "") -> str:
+    """extra_flags / out / tag: variant builds for A/B runs (e.g. -DB2_MBAR_NO_HINT into libinfernos_b200_nohint.so; load with B2_SO_PATH)."""
+    if not force and not extra_flags and not needs_build():
         return SO
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(CSRC, s.replace(".cu", ".o"))
-        cmd = [nvcc(), *FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        o = os.path.join(CSRC, s.replace(".cu", tag + ".o"))
+        cmd = [nvcc(), *FLAGS, *extra_flags, "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -49,9 +50,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc(), "-shared", "-o", SO, *objs])
-    return SO
+    subprocess.check_call([nvcc(), "-shared", "-o", so_out, *objs])
+    return so_out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:          # python -m infernos_b200.build --variant nohint -DB2_MBAR_NO_HINT
+        i = sys.argv.index("--variant")
+        name, flags = sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")]
+        print(build(force=True, extra_flags=flags, so_out=os.path.join(HERE, f"libinfernos_b200_{name}.so"), tag="_" + name))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

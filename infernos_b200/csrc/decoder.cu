@@ -215,8 +215,6 @@ __global__ void k_pos_cat(const float *__restrict__ fin, const float *__restrict
     }
 }
 
-__device__ __forceinline__ float ld_kv(const float *p) { return *p; }
-__device__ __forceinline__ float ld_kv(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void st_kv(float *p, float v) { *p = v; }
 __device__ __forceinline__ void st_kv(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 

@@ -12,7 +12,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// try_wait carries a suspend-time hint: without one the hardware's default time limit is a few tens of cycles, and the waiting warps (TMA producer,
+// MMA issuers, epilogue warps between sub-tiles) re-issue the try_wait + branch pair all the time -- in k_resblock<32> a quarter of all executed
+// warp instructions were this polling (ncu source page, round 2), on the same schedulers the epilogue math needs.  With the hint the warp is parked
+// until the phase completes (or the limit passes).  -DB2_MBAR_NO_HINT builds the old loop for A/B runs.
+#ifndef B2_MBAR_HINT_NS
+#define B2_MBAR_HINT_NS 0x989680
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef B2_MBAR_NO_HINT
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
         "WAIT_%=:\n\t"
@@ -20,6 +28,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "@P1 bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+#else
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"((uint32_t)B2_MBAR_HINT_NS) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
