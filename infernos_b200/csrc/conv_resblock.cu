@@ -117,20 +117,44 @@ __device__ __forceinline__ void ld_row32(const float *src, bool ok, uint32_t (&v
 
 // 32 consecutive channels [c0, c0+32) of buffer row r -> bf16(lrelu(v + bias)) (zeros when !keep) in the interleaved operand
 // layout (RT rows per 8-channel chunk).  slope is in (0, 1), so leaky_relu(v) == max(v, slope * v).
+// The bias add and the slope multiply run on packed pairs (add.rn.f32x2 / mul.rn.f32x2: the same IEEE results, half the instructions), and the
+// zeroing select is skipped when every lane's row lies inside the window (warp-uniform): the conv epilogues were ~4.4 instructions per element and
+// about half issue-bound with two CTAs per SM (ncu source page, round 2).
+__device__ __forceinline__ unsigned long long rb_pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
 template <int RT>
 __device__ __forceinline__ void write_operand_row(uint32_t sA_u32, int r, int c0, const uint32_t (&v)[32], const float *bias, float slope, bool keep) {
+    const unsigned long long slope2 = rb_pack2(slope, slope);
+    const bool all_keep = __all_sync(0xffffffffu, keep);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const int c = 8 * i + 2 * e;
+#ifdef B2_RB_SCALAR_EPI          // the round-1 scalar form (variant build for A/B runs; same results)
             float v0 = __uint_as_float(v[c]), v1 = __uint_as_float(v[c + 1]);
             if (bias) { v0 += bias[c]; v1 += bias[c + 1]; }
-            v0 = fmaxf(v0, v0 * slope);
-            v1 = fmaxf(v1, v1 * slope);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-            pk[e] = keep ? *reinterpret_cast<uint32_t *>(&h2) : 0u;
+            const float m0 = v0 * slope, m1 = v1 * slope;
+            (void)slope2;
+#else
+            unsigned long long x2 = rb_pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1]));
+            if (bias) asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x2) : "l"(x2), "l"(rb_pack2(bias[c], bias[c + 1])));
+            unsigned long long m2;
+            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(m2) : "l"(x2), "l"(slope2));
+            float v0, v1, m0, m1;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(x2));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(m0), "=f"(m1) : "l"(m2));
+#endif
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(v0, m0), fmaxf(v1, m1));
+            pk[e] = *reinterpret_cast<uint32_t *>(&h2);
+        }
+        if (!all_keep) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) pk[e] = keep ? pk[e] : 0u;
         }
         const uint32_t dst = sA_u32 + (uint32_t)(((((c0 >> 3) + i) * RT) + kGuard + r) * 16);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
