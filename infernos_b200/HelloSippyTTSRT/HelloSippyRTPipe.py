@@ -20,9 +20,13 @@ What differs, by design:
     the GPU pass.  InfernTTSWorker(continuous=True) drives it.
   * the decoder post-net (:230) runs on the GPU inside the same tail call when its weights are given
     (`postnet_state_dict`, or automatically when the engine loads a SpeechT5 model itself); `frontend.postnet` is then not called.
-  * the autoregressive front half (SpeechT5 encoder/decoder, :111-118, :195-229) is out of this project's
-    scope: it is reached through a small `frontend` object.  SpeechT5Frontend wraps a transformers model and
-    issues the same calls the reference does; tests and benchmarks script it.
+  * the autoregressive front half is reached through a small `frontend` object.  B200Frontend runs the decoder loop of
+    :195-229 -- prenet, six decoder layers with a slot KV cache, feat_out / prob_out, 16 steps per engine call -- inside the CUDA library
+    (engine.TTSDecoder, b2_dec_*) and hands the frames to the tail without leaving the device; the tokenizer and the text encoder (:111-116,
+    once per sentence) are two callables.  SpeechT5Frontend issues the reference's own torch calls on a transformers model; ScriptedFrontend
+    replays a fixed mel plan (tests, benchmarks of the tail alone).
+  * requests may ask for pre-encoded dispatch (`pre_encoded=True`): `dispatch` then receives G711AudioChunk objects (samples + the G.711 bytes
+    made on the GPU in the same pass), which the payload-aware OutputMuxer carries to the RTP packetiser un-re-encoded (f1).
 """
 from __future__ import annotations
 

@@ -24,19 +24,6 @@ struct UmmaConvArgs {
 
 int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st);
 
-// One fused ResBlock pair  out = residual + conv2(lrelu(conv1(in), mid_slope))  (conv_pair.cu); epilogue options as above.
-struct PairArgs {
-    const __nv_bfloat16 *in = nullptr;     // bf16(lrelu(x)), channels-last [W][T][C]
-    const float *residual = nullptr;       // x, fp32
-    const Layer *conv1 = nullptr, *conv2 = nullptr;
-    const float *acc_src = nullptr;
-    float *out32 = nullptr;
-    __nv_bfloat16 *outb = nullptr;
-    float outb_slope = 1.0f, mid_slope = 0.1f, div = 1.0f;
-    int W = 0, T = 0;
-};
-bool pair_supported(const Layer &conv1, const Layer &conv2, int T);
-int launch_resblock_pair(const PairArgs &a, cudaStream_t st);
 // One whole ResBlock (three conv pairs, dilations d0..d2) in a single launch (conv_resblock.cu).
 //   result = x3, where x_{n+1} = x_n + conv2_n(lrelu(conv1_n(lrelu(x_n, slope)), slope));
 //   v = result; v = acc_src + v; v /= div; out32 = v; outb = bf16(lrelu(v, outb_slope))

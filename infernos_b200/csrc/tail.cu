@@ -463,17 +463,6 @@ static int vocoder_bf16(b2_ctx *c, const float *xn, int W, int T, float *audio, 
                         else o32 = ws.s0;           // fp32 input of conv_post
                     }
                 }
-                if (pair_supported(c->res1[i][j][d], c->res2[i][j][d], Tc)) {
-                    // the fused kernel reads its operand with a halo while other CTAs write theirs, so the bf16 operand
-                    // ping-pongs between rb and yb (yb is otherwise unused when pairs are fused); fp32 x is row-local, in place
-                    PairArgs pa;
-                    const __nv_bfloat16 *pin = (d == 0) ? ws.hb : (d == 1 ? ws.rb : ws.yb);
-                    if (!last) ob = (d == 0) ? ws.rb : ws.yb;
-                    pa.in = pin; pa.residual = x; pa.conv1 = &c->res1[i][j][d]; pa.conv2 = &c->res2[i][j][d];
-                    pa.acc_src = accs; pa.out32 = o32; pa.outb = ob; pa.outb_slope = 0.1f; pa.mid_slope = 0.1f; pa.div = dv; pa.W = W; pa.T = Tc;
-                    PROF(PC_CONV_TC, launch_resblock_pair(pa, st));
-                    continue;
-                }
                 UmmaConvArgs u1;
                 u1.in = xb; u1.layer = &c->res1[i][j][d]; u1.outb = ws.yb; u1.outb_slope = 0.1f; u1.W = W; u1.T = Tc;
                 PROF(PC_CONV_TC, launch_conv_umma(u1, st));

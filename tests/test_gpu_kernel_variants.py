@@ -35,7 +35,6 @@ def _run(tmp_path, name, env):
 @pytest.mark.parametrize("name,env", [
     ("one_tile_kernel_everywhere", {"B2_UMMA_V1": "1"}),
     ("persistent_kernel_everywhere", {"B2_UMMA_V2": "1"}),
-    ("fused_resblock_pairs", {"B2_PAIR_FUSION": "1", "B2_RESBLOCK_FUSION": "0"}),
     ("single_subtile", {"B2_UMMA_MT": "1", "B2_RESBLOCK_FUSION": "0"}),
     ("conv_by_conv_resblocks", {"B2_RESBLOCK_FUSION": "0"}),
     ("tall_stage0_tiles", {"B2_UMMA_TALL256": "1"}),
