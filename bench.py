@@ -546,11 +546,27 @@ def main_b200(args, rank, local_rank, world):
         except Exception as e:
             front = {"error": repr(e)[:300]}
 
+    # ---- the reference's own load-test shape (HelloSippyRTPipeTest.py:180-236) through the plugin API: per-session TTFF / TTLF / rtr -------------
+    session_test = None
+    if rank == 0 and world == 1 and not args.no_sessions and args.mode == "bf16":
+        tail.close()
+        tail = None
+        torch.cuda.empty_cache()
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import session_bench
+            session_test = [session_bench.run(n, 96, args.mode, device=f"cuda:{local_rank}") for n in args.session_counts]
+            for r in session_test:
+                r.pop("what", None)
+        except Exception as e:
+            session_test = {"error": repr(e)[:300]}
+
     # ---- north_star's joint target: p99 chunk latency at >= 5,000 concurrent real-time streams ---------------------------------------
     latency = None
     if rank == 0 and world == 1 and not args.no_latency:
-        tail.close()
-        tail = None
+        if tail is not None:
+            tail.close()
+            tail = None
         torch.cuda.empty_cache()
         latency = []
         for nsess in args.latency_sessions:
@@ -584,7 +600,7 @@ def main_b200(args, rank, local_rank, world):
             "roofline": roofline, "roofline_conv_family": family_roof, "roofline_codec": codec_roof,
             "kernel_ms_per_step": {k: round(v / psteps, 3) for k, v in ms_cls.items()},
             "cpu_baseline": cpu,
-            "latency": latency, "strong": strong, "front_half": front,
+            "latency": latency, "strong": strong, "front_half": front, "session_test": session_test,
             "per_gpu_stats": [{"sessions": int(s["sessions"]), "steps": int(s["steps"]), "g711_bytes": int(s["g711_bytes"]),
                                "device_ms": round(s["device_ms"], 3)} for s in allstats],
             "hbm_bytes_ctx": ctx_bytes,
@@ -615,6 +631,8 @@ def main():
     ap.add_argument("--no-latency", action="store_true", help="skip the p99 chunk-latency legs (5,000 / 20,000 staggered real-time sessions)")
     ap.add_argument("--latency-sessions", type=int, nargs="*", default=[5000, 20000])
     ap.add_argument("--latency-seconds", type=float, default=3.0)
+    ap.add_argument("--no-sessions", action="store_true", help="skip the reference-style session test (TTFF / TTLF / rtr through InfernTTSWorker + GPU front half)")
+    ap.add_argument("--session-counts", type=int, nargs="*", default=[50, 1000])
     ap.add_argument("--no-front", action="store_true", help="skip the AR-decoder + tail leg (SURVEY 8 f3)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (BASELINE config 3 as written)")
     ap.add_argument("--strong-total", type=int, default=1024)

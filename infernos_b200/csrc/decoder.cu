@@ -26,6 +26,8 @@
 
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
+#include <utility>
 #include <string.h>
 #include <algorithm>
 #include <map>
@@ -52,6 +54,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, uint
                  ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+// Programmatic dependent launch (PDL): a decoder step is a chain of ~74 short kernels on one stream.  Launched with the programmatic-serialization
+// attribute, kernel N+1 may become resident while kernel N is still running: it announces itself early (launch_dependents), does the work that
+// depends on nothing (barrier init, TMEM allocation, descriptor prefetch), and only then waits for kernel N to complete and flush (wait).
+// Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 constexpr int kGemmStages = 4;
@@ -71,6 +80,7 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kGemmStages + 1);
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * NT;
     const int nkb = p.K / 64;
+    pdl_trigger();
 
     if (warp == 5) {
         if (lane == 0) {
@@ -91,6 +101,7 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();                                   // everything above overlapped the previous kernel; its results are read from here on
 
     if (warp == 4) {
         if (lane == 0) {
@@ -174,6 +185,8 @@ template <bool BF>
 __global__ void k_dec_gather(const int32_t *__restrict__ slots, const float *__restrict__ last, const int32_t *__restrict__ step, int M,
                              float *__restrict__ x0, __nv_bfloat16 *__restrict__ x0b, int32_t *__restrict__ rowpos, int32_t *__restrict__ rowslot,
                              int max_sessions, int max_steps, int *__restrict__ err) {
+    pdl_trigger();
+    pdl_wait();
     const int m = blockIdx.x, c = threadIdx.x;            // 128 threads
     if (m >= M) return;
     int sl = slots[m];
@@ -190,6 +203,8 @@ __global__ void k_dec_gather(const int32_t *__restrict__ slots, const float *__r
 
 // fp32 mode: x = act(x) * colscale[col], in place (the bf16 GEMM does this in its epilogue)
 __global__ void k_act_scale(float *__restrict__ x, const float *__restrict__ colscale, size_t n, int N, int act) {
+    pdl_trigger();
+    pdl_wait();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float v = x[i];
@@ -204,6 +219,8 @@ __global__ void k_act_scale(float *__restrict__ x, const float *__restrict__ col
 template <bool BF>
 __global__ void k_pos_cat(const float *__restrict__ fin, const float *__restrict__ pe, const float *__restrict__ alpha, const int32_t *__restrict__ rowpos,
                           const int32_t *__restrict__ slots, const float *__restrict__ spk, int M, float *__restrict__ cat, __nv_bfloat16 *__restrict__ catb) {
+    pdl_trigger();
+    pdl_wait();
     const int m = blockIdx.x;
     if (m >= M) return;
     const int pos = rowpos[m], sl = slots[m];
@@ -263,6 +280,8 @@ template <typename KV, bool SELF>
 __global__ void __launch_bounds__(128) k_attend(const float *__restrict__ q, int ldq, const int32_t *__restrict__ slots, const int32_t *__restrict__ rowpos,
                                                const int32_t *__restrict__ enc_len, KV *__restrict__ cache, size_t slot_stride, size_t pos_stride,
                                                size_t layer_off, float *__restrict__ ctx32, __nv_bfloat16 *__restrict__ ctxb) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];                      // [T] scores | 64 q | 4 x 64 partial sums | 8 red
     const int m = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31, grp = lane >> 3, c8 = (lane & 7) * 8;
@@ -338,6 +357,8 @@ __global__ void __launch_bounds__(128) k_attend(const float *__restrict__ q, int
 // h = LayerNorm(h + o) * w + b over 768 columns, eps 1e-5, biased variance (torch.nn.LayerNorm); 256 threads per row
 __global__ void __launch_bounds__(256) k_add_ln(float *__restrict__ h, const float *__restrict__ o, const float *__restrict__ w, const float *__restrict__ b,
                                                __nv_bfloat16 *__restrict__ hb, int M) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[8];
     const int m = blockIdx.x, tid = threadIdx.x;
     if (m >= M) return;
@@ -361,6 +382,8 @@ __global__ void __launch_bounds__(256) k_add_ln(float *__restrict__ h, const flo
 
 // after the speaker projection: h = relu(x) as fp32 residual stream + bf16 operand
 __global__ void k_relu_dual(const float *__restrict__ x, float *__restrict__ h, __nv_bfloat16 *__restrict__ hb, size_t n) {
+    pdl_trigger();
+    pdl_wait();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float v = fmaxf(x[i], 0.0f);
@@ -372,6 +395,8 @@ __global__ void k_relu_dual(const float *__restrict__ x, float *__restrict__ h, 
 // out[m] = feat (2 x 80) | prob logits (2) -> the call's mel [M][2*nsteps][80], the stop probabilities [M][nsteps][2], the slot's last frame and step
 __global__ void k_dec_finish(const float *__restrict__ out, const int32_t *__restrict__ slots, int M, int s, int nsteps,
                              float *__restrict__ mel, float *__restrict__ prob, float *__restrict__ last, int32_t *__restrict__ step, int max_sessions) {
+    pdl_trigger();
+    pdl_wait();
     const int m = blockIdx.x, c = threadIdx.x;           // 192 threads
     if (m >= M) return;
     const int sl = slots[m];
@@ -475,6 +500,7 @@ struct b2_dec {
     int *err_h = nullptr, *err_d = nullptr;
     unsigned long long calls = 0;
     // one CUDA graph per (padded batch size, steps per call): a call is ~74 launches per step, 16 steps (b2_dec_steps)
+    bool use_pdl = true;                        // programmatic dependent launch between the kernels of a step (B2_DEC_PDL=0 switches it off)
     bool use_graphs = true;
     std::map<unsigned long long, std::pair<cudaGraphExec_t, int>> graphs;    // key -> (exec, kernel nodes); exec == nullptr: seen once, run eagerly
     cudaStream_t g_stream = nullptr;           // captures run here: the caller's stream may be the legacy default stream, which cannot capture
@@ -586,6 +612,18 @@ int make_tma_2d_bf16(CUtensorMap *tm, const void *ptr, long long rows, int K, lo
 
 static bool g_gemm_attr[64][2] = {};
 
+// <<<>>> with the programmatic-stream-serialization attribute when pdl is set (see pdl_trigger / pdl_wait)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 int launch_gemm_tc(const GemmTcArgs &a, cudaStream_t st) {
     if (a.M <= 0) return 0;
     if (!a.tmA || !a.tmB || !a.bias || (a.nt != 64 && a.nt != 128) || a.N % a.nt || a.K % 64 || a.K < 64) return set_error("gemm_tc: bad arguments (N %d nt %d K %d)", a.N, a.nt, a.K);
@@ -601,8 +639,8 @@ int launch_gemm_tc(const GemmTcArgs &a, cudaStream_t st) {
         else B2_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g_gemm_attr[dev][slot] = true;
     }
-    if (a.nt == 128) k_gemm_tc<128><<<grid, 192, smem, st>>>(*a.tmA, *a.tmB, p);
-    else k_gemm_tc<64><<<grid, 192, smem, st>>>(*a.tmA, *a.tmB, p);
+    if (a.nt == 128) B2_CUDA_OK(launch_k(k_gemm_tc<128>, grid, dim3(192), smem, st, a.pdl, *a.tmA, *a.tmB, (const GemmParams)p));
+    else B2_CUDA_OK(launch_k(k_gemm_tc<64>, grid, dim3(192), smem, st, a.pdl, *a.tmA, *a.tmB, (const GemmParams)p));
     B2_LAUNCH_OK("k_gemm_tc");
     return 0;
 }
@@ -617,7 +655,7 @@ int linear(b2_dec *d, const DecLinear &l, const float *A32, const CUtensorMap *t
     if (M <= 0) return 0;
     if (d->mode == B2_MODE_BF16) {
         GemmTcArgs g;
-        g.tmA = tmA; g.tmB = &l.tmB; g.bias = l.bias; g.colscale = colscale; g.out32 = out32; g.outb = outb; g.M = M; g.N = l.N; g.K = l.K; g.nt = l.nt; g.act = act;
+        g.tmA = tmA; g.tmB = &l.tmB; g.bias = l.bias; g.colscale = colscale; g.out32 = out32; g.outb = outb; g.M = M; g.N = l.N; g.K = l.K; g.nt = l.nt; g.act = act; g.pdl = d->use_pdl;
         return launch_gemm_tc(g, st);
     }
     ConvArgs a;
@@ -627,7 +665,7 @@ int linear(b2_dec *d, const DecLinear &l, const float *A32, const CUtensorMap *t
     if (launch_conv_simt(a, st)) return 1;
     if (act || colscale) {
         const size_t n = (size_t)M * l.N;
-        k_act_scale<<<(unsigned)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 8), 256, 0, st>>>(out32, colscale, n, l.N, act);
+        B2_CUDA_OK(launch_k(k_act_scale, dim3((unsigned)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 8)), dim3(256), 0, st, d->use_pdl, out32, colscale, n, l.N, act));
         B2_LAUNCH_OK("k_act_scale");
     }
     return 0;
@@ -752,47 +790,51 @@ int steps_impl(b2_dec *d, const int32_t *d_slots, int n, int nsteps, float *d_me
         float *mel = d_mel + (size_t)r0 * 2 * nsteps * NMEL, *prob = d_prob + (size_t)r0 * nsteps * 2;
         for (int s = 0; s < nsteps; s++) {
             const float *sc0 = d->scales + (size_t)(s * 2) * PRE, *sc1 = sc0 + PRE;
-            if (bf) k_dec_gather<true><<<M, 128, 0, st>>>(d_slots + r0, d->last, d->step, M, nullptr, d->x0b, d->rowpos, d->rowslot, d->max_sessions, d->max_steps, d->err_d);
-            else k_dec_gather<false><<<M, 128, 0, st>>>(d_slots + r0, d->last, d->step, M, d->x0, nullptr, d->rowpos, d->rowslot, d->max_sessions, d->max_steps, d->err_d);
+            const bool pdl = d->use_pdl;
+            const dim3 gM((unsigned)M);
+            if (bf) B2_CUDA_OK(launch_k(k_dec_gather<true>, gM, dim3(128), 0, st, pdl, d_slots + r0, (const float *)d->last, (const int32_t *)d->step, M, (float *)nullptr, d->x0b, d->rowpos, d->rowslot, d->max_sessions, d->max_steps, d->err_d));
+            else B2_CUDA_OK(launch_k(k_dec_gather<false>, gM, dim3(128), 0, st, pdl, d_slots + r0, (const float *)d->last, (const int32_t *)d->step, M, d->x0, (__nv_bfloat16 *)nullptr, d->rowpos, d->rowslot, d->max_sessions, d->max_steps, d->err_d));
             B2_LAUNCH_OK("k_dec_gather");
             // prenet (:689-692)
             if (linear(d, d->pre0, d->x0, &d->tm_x0, M, 1, sc0, bf ? nullptr : d->p1, bf ? d->p1b : nullptr, st)) return 1;
             if (linear(d, d->pre1, d->p1, &d->tm_p1, M, 1, sc1, bf ? nullptr : d->p2, bf ? d->p2b : nullptr, st)) return 1;
             if (linear(d, d->fin, d->p2, &d->tm_p2, M, 0, nullptr, d->fin32, nullptr, st)) return 1;
-            if (bf) k_pos_cat<true><<<M, 256, 0, st>>>(d->fin32, d->pe, d->alpha, d->rowpos, slots, d->spk, M, nullptr, d->catb);
-            else k_pos_cat<false><<<M, 256, 0, st>>>(d->fin32, d->pe, d->alpha, d->rowpos, slots, d->spk, M, d->cat, nullptr);
+            if (bf) B2_CUDA_OK(launch_k(k_pos_cat<true>, gM, dim3(256), 0, st, pdl, (const float *)d->fin32, (const float *)d->pe, (const float *)d->alpha, (const int32_t *)d->rowpos, slots, (const float *)d->spk, M, (float *)nullptr, d->catb));
+            else B2_CUDA_OK(launch_k(k_pos_cat<false>, gM, dim3(256), 0, st, pdl, (const float *)d->fin32, (const float *)d->pe, (const float *)d->alpha, (const int32_t *)d->rowpos, slots, (const float *)d->spk, M, d->cat, (__nv_bfloat16 *)nullptr));
             B2_LAUNCH_OK("k_pos_cat");
             if (linear(d, d->spkl, d->cat, &d->tm_cat, M, 0, nullptr, d->tmp, nullptr, st)) return 1;
             {
                 const size_t ne = (size_t)M * H;
-                k_relu_dual<<<(unsigned)std::min<size_t>((ne + 255) / 256, (size_t)sm_count() * 8), 256, 0, st>>>(d->tmp, d->h, bf ? d->hb : nullptr, ne);
+                B2_CUDA_OK(launch_k(k_relu_dual, dim3((unsigned)std::min<size_t>((ne + 255) / 256, (size_t)sm_count() * 8)), dim3(256), 0, st, pdl, (const float *)d->tmp, d->h, bf ? d->hb : (__nv_bfloat16 *)nullptr, ne));
                 B2_LAUNCH_OK("k_relu_dual");
             }
             for (int i = 0; i < NL; i++) {
                 // self-attention (:1125-1134)
                 if (linear(d, d->qkv[i], d->h, &d->tm_h, M, 0, nullptr, d->qkv32, nullptr, st)) return 1;
-                k_attend<KV, true><<<dim3((unsigned)M, NH), 128, attn_smem_self, st>>>(d->qkv32, 3 * H, slots, d->rowpos, d->enc_len, self_cache, self_slot, self_pos,
-                                                                                         (size_t)i * d->max_steps * 2 * H, bf ? nullptr : d->ctx, bf ? d->ctxb : nullptr);
+                B2_CUDA_OK(launch_k(k_attend<KV, true>, dim3((unsigned)M, NH), dim3(128), attn_smem_self, st, pdl, (const float *)d->qkv32, 3 * H, slots, (const int32_t *)d->rowpos,
+                                    (const int32_t *)d->enc_len, self_cache, self_slot, self_pos, (size_t)i * d->max_steps * 2 * H, bf ? (float *)nullptr : d->ctx,
+                                    bf ? d->ctxb : (__nv_bfloat16 *)nullptr));
                 B2_LAUNCH_OK("k_attend(self)");
                 if (linear(d, d->so[i], d->ctx, &d->tm_ctx, M, 0, nullptr, d->tmp, nullptr, st)) return 1;
-                k_add_ln<<<M, 256, 0, st>>>(d->h, d->tmp, d->ln_w[i][0], d->ln_b[i][0], bf ? d->hb : nullptr, M);
+                B2_CUDA_OK(launch_k(k_add_ln, gM, dim3(256), 0, st, pdl, d->h, (const float *)d->tmp, (const float *)d->ln_w[i][0], (const float *)d->ln_b[i][0], bf ? d->hb : (__nv_bfloat16 *)nullptr, M));
                 B2_LAUNCH_OK("k_add_ln");
                 // cross-attention (:1137-1147)
                 if (linear(d, d->xq[i], d->h, &d->tm_h, M, 0, nullptr, d->qkv32, nullptr, st)) return 1;
-                k_attend<KV, false><<<dim3((unsigned)M, NH), 128, attn_smem_x, st>>>(d->qkv32, H, slots, d->rowpos, d->enc_len, x_cache, x_slot, x_pos, (size_t)i * d->max_enc * 2 * H,
-                                                                                       bf ? nullptr : d->ctx, bf ? d->ctxb : nullptr);
+                B2_CUDA_OK(launch_k(k_attend<KV, false>, dim3((unsigned)M, NH), dim3(128), attn_smem_x, st, pdl, (const float *)d->qkv32, H, slots, (const int32_t *)d->rowpos,
+                                    (const int32_t *)d->enc_len, x_cache, x_slot, x_pos, (size_t)i * d->max_enc * 2 * H, bf ? (float *)nullptr : d->ctx,
+                                    bf ? d->ctxb : (__nv_bfloat16 *)nullptr));
                 B2_LAUNCH_OK("k_attend(cross)");
                 if (linear(d, d->xo[i], d->ctx, &d->tm_ctx, M, 0, nullptr, d->tmp, nullptr, st)) return 1;
-                k_add_ln<<<M, 256, 0, st>>>(d->h, d->tmp, d->ln_w[i][1], d->ln_b[i][1], bf ? d->hb : nullptr, M);
+                B2_CUDA_OK(launch_k(k_add_ln, gM, dim3(256), 0, st, pdl, d->h, (const float *)d->tmp, (const float *)d->ln_w[i][1], (const float *)d->ln_b[i][1], bf ? d->hb : (__nv_bfloat16 *)nullptr, M));
                 B2_LAUNCH_OK("k_add_ln");
                 // feed-forward (:1150-1151)
                 if (linear(d, d->ff1[i], d->h, &d->tm_h, M, 2, nullptr, bf ? nullptr : d->f1, bf ? d->f1b : nullptr, st)) return 1;
                 if (linear(d, d->ff2[i], d->f1, &d->tm_f1, M, 0, nullptr, d->tmp, nullptr, st)) return 1;
-                k_add_ln<<<M, 256, 0, st>>>(d->h, d->tmp, d->ln_w[i][2], d->ln_b[i][2], bf ? d->hb : nullptr, M);
+                B2_CUDA_OK(launch_k(k_add_ln, gM, dim3(256), 0, st, pdl, d->h, (const float *)d->tmp, (const float *)d->ln_w[i][2], (const float *)d->ln_b[i][2], bf ? d->hb : (__nv_bfloat16 *)nullptr, M));
                 B2_LAUNCH_OK("k_add_ln");
             }
             if (linear(d, d->outl, d->h, &d->tm_h, M, 0, nullptr, d->out, nullptr, st)) return 1;
-            k_dec_finish<<<M, OUTP, 0, st>>>(d->out, slots, M, s, nsteps, mel, prob, d->last, d->step, d->max_sessions);
+            B2_CUDA_OK(launch_k(k_dec_finish, gM, dim3(OUTP), 0, st, pdl, (const float *)d->out, slots, M, s, nsteps, mel, prob, d->last, d->step, d->max_sessions));
             B2_LAUNCH_OK("k_dec_finish");
         }
     }
@@ -843,6 +885,7 @@ b2_dec *b2_dec_create(int device, int mode, int max_sessions, int max_rows, int 
     if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); return nullptr; }
     b2_dec *d = new b2_dec();
     d->device = device; d->mode = mode; d->max_sessions = max_sessions; d->max_rows = max_rows; d->max_steps = max_steps; d->max_enc = max_enc_len;
+    d->use_pdl = !(getenv("B2_DEC_PDL") && atoi(getenv("B2_DEC_PDL")) == 0);
     return d;
 }
 

@@ -13,6 +13,7 @@ struct GemmTcArgs {
     float *out32 = nullptr;             // optional [M][N]
     __nv_bfloat16 *outb = nullptr;      // optional [M][N]
     int M = 0, N = 0, K = 0, nt = 128, act = 0;   // N % nt == 0, K % 64 == 0; act: 0 none, 1 relu, 2 gelu (erf)
+    bool pdl = false;                   // launch with the programmatic-stream-serialization attribute (the decoder's kernel chain)
 };
 int launch_gemm_tc(const GemmTcArgs &a, cudaStream_t st);
 // TMA map over row-major bf16 [rows][K] with `row_stride` ELEMENTS between rows (>= K), box 64 x box_rows, 128-byte swizzle
