@@ -63,11 +63,11 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-constexpr int kGemmStages = 4;
 
 // C[m][n] = act(sum_k A[m][k] * W[n][k] + bias[n]) * colscale[n];  one 128 x NT tile per CTA.
 // warps 0..3 epilogue (TMEM lane quadrant = warp), warp 4 TMA producer, warp 5 TMEM allocation + MMA issue.
-template <int NT>
+// kGemmStages ring stages: with the decoder's K = 768 (12 K blocks) an 8-deep ring has two thirds of the tile's operands in flight at once
+template <int NT, int kGemmStages>
 __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr uint32_t kABytes = 128 * 64 * 2, kBBytes = NT * 64 * 2, kStage = kABytes + kBBytes;
@@ -610,7 +610,7 @@ int make_tma_2d_bf16(CUtensorMap *tm, const void *ptr, long long rows, int K, lo
     return 0;
 }
 
-static bool g_gemm_attr[64][2] = {};
+static bool g_gemm_attr[64][4] = {};
 
 // <<<>>> with the programmatic-stream-serialization attribute when pdl is set (see pdl_trigger / pdl_wait)
 template <typename... KArgs, typename... Args>
@@ -630,17 +630,29 @@ int launch_gemm_tc(const GemmTcArgs &a, cudaStream_t st) {
     GemmParams p;
     p.bias = a.bias; p.colscale = a.colscale; p.out32 = a.out32; p.outb = a.outb; p.M = a.M; p.N = a.N; p.K = a.K; p.ldo = a.N; p.act = a.act;
     dim3 grid((unsigned)cdiv(a.M, 128), (unsigned)(a.N / a.nt));
-    const int slot = a.nt == 128 ? 1 : 0;
-    const size_t smem = (size_t)kGemmStages * (128 * 64 * 2 + (size_t)a.nt * 64 * 2) + (2 * kGemmStages + 1) * 8 + 16;
+    // ring depth: deep (8 x 24 KB / 6 x 32 KB) when the K loop is long enough to use it, 4 otherwise (B2_GEMM_DEEP=0: always 4)
+    static const bool deep_on = !(getenv("B2_GEMM_DEEP") && atoi(getenv("B2_GEMM_DEEP")) == 0);
+    const bool deep = deep_on && a.K >= 512;
+    const int stages = deep ? (a.nt == 128 ? 6 : 8) : 4;
+    const int slot = (a.nt == 128 ? 1 : 0) + (deep ? 2 : 0);
+    const size_t smem = (size_t)stages * (128 * 64 * 2 + (size_t)a.nt * 64 * 2) + (2 * stages + 1) * 8 + 16;
     int dev = 0;
     B2_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 64 && !g_gemm_attr[dev][slot]) {
-        if (a.nt == 128) B2_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else B2_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (a.nt == 128) B2_CUDA_OK(deep ? cudaFuncSetAttribute(k_gemm_tc<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                         : cudaFuncSetAttribute(k_gemm_tc<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else B2_CUDA_OK(deep ? cudaFuncSetAttribute(k_gemm_tc<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                             : cudaFuncSetAttribute(k_gemm_tc<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g_gemm_attr[dev][slot] = true;
     }
-    if (a.nt == 128) B2_CUDA_OK(launch_k(k_gemm_tc<128>, grid, dim3(192), smem, st, a.pdl, *a.tmA, *a.tmB, (const GemmParams)p));
-    else B2_CUDA_OK(launch_k(k_gemm_tc<64>, grid, dim3(192), smem, st, a.pdl, *a.tmA, *a.tmB, (const GemmParams)p));
+    const GemmParams cp = p;
+    if (a.nt == 128) {
+        if (deep) B2_CUDA_OK(launch_k(k_gemm_tc<128, 6>, grid, dim3(192), smem, st, a.pdl, *a.tmA, *a.tmB, cp));
+        else B2_CUDA_OK(launch_k(k_gemm_tc<128, 4>, grid, dim3(192), smem, st, a.pdl, *a.tmA, *a.tmB, cp));
+    } else {
+        if (deep) B2_CUDA_OK(launch_k(k_gemm_tc<64, 8>, grid, dim3(192), smem, st, a.pdl, *a.tmA, *a.tmB, cp));
+        else B2_CUDA_OK(launch_k(k_gemm_tc<64, 4>, grid, dim3(192), smem, st, a.pdl, *a.tmA, *a.tmB, cp));
+    }
     B2_LAUNCH_OK("k_gemm_tc");
     return 0;
 }
