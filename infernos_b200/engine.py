@@ -82,6 +82,8 @@ class TTSTail:
             _lib.check(fn(self.ctx, k.encode(), ctypes.c_void_p(t.data_ptr()), shape, t.dim()), f"load {k}")
 
     def close(self):
+        for sch in list(getattr(self, "_schedulers", ())):      # a serving loop's threads use this context: stop them first
+            sch.close()
         if getattr(self, "ctx", None):
             self.lib.b2_ctx_destroy(self.ctx)
             self.ctx = None
@@ -263,6 +265,9 @@ class TailScheduler:
                                               1 if use_graphs else 0)
         if not self.h:
             raise RuntimeError("b2_sched_create: " + self.lib.b2_last_error(None).decode())
+        if not hasattr(tail, "_schedulers"):
+            tail._schedulers = []
+        tail._schedulers.append(self)
         self._cap = int(poll_capacity)
         self._recs = (_Completion * self._cap)()
         self._bytes = torch.empty(self._cap * self.nframes * 128, dtype=torch.uint8)
@@ -271,6 +276,8 @@ class TailScheduler:
         if getattr(self, "h", None):
             self.lib.b2_sched_destroy(self.h)
             self.h = None
+            if self in getattr(self.tail, "_schedulers", []):
+                self.tail._schedulers.remove(self)
 
     def __del__(self):
         try:
