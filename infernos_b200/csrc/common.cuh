@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string>
 #include <atomic>
+#include <utility>
 
 namespace b2 {
 
@@ -32,6 +33,27 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Programmatic dependent launch (PDL).  The tail is a chain of ~42 kernels on one stream (a decoder step: ~74): launched with the
+// programmatic-stream-serialization attribute, kernel N+1 may become resident while kernel N is still running; it announces itself
+// (pdl_trigger) and must not touch anything kernel N produces -- or still reads -- before pdl_wait returns (kernel N complete and flushed).
+// Without the attribute both instructions are no-ops, so every kernel can carry them.  B2_PDL=0 launches everything the plain way.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 int sm_count();   // SMs of the current device (cached)
 

@@ -196,6 +196,7 @@ static constexpr int kRbDbgEvents = 48, kRbDbgCtas = 4096;
 template <int C, int NEW, int NMW, int EPI, bool DBG, bool PAIR>
 __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? (NEW == 8 ? 88 : 128) : 168) k_resblock(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ RbParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    pdl_trigger();
     using G = RbGeom<C>;
     constexpr int kS = G::kS, kRows = G::kRows, kRtot = G::kRtot, KB = G::KB, NKB = G::NKB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -303,6 +304,9 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
     const uint32_t tmem_X = *tmem_slot;
     const uint32_t tmem_T1 = tmem_X + (uint32_t)(kS * C);
     if (threadIdx.x == 0) RB_DBG(1);
+    // PDL: barrier setup, TMEM allocation, guard rows and the L2 prefetches above ran while the previous kernel drained; its output (x, the MRF
+    // partial sum) is only touched by the epilogue warps, from here on.  The weight ring (warp NEW) reads nothing a kernel writes.
+    if (warp < NEW) pdl_wait();
 
     if (warp < NEW) {
         // ======================================================================================= slab load + epilogues
@@ -798,7 +802,7 @@ static int launch_rb__(const CUtensorMap &tm, const RbParams &p, unsigned grid, 
         B2_CUDA_OK(cudaFuncSetAttribute(k_resblock<C, NEW, NMW, EPI, DBG, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         g_rb_attr[dev][wslot][eslot] = true;
     }
-    k_resblock<C, NEW, NMW, EPI, DBG, PAIR><<<grid, (NEW + 1 + NMW) * 32, smem, st>>>(tm, p);
+    B2_CUDA_OK(launch_k(k_resblock<C, NEW, NMW, EPI, DBG, PAIR>, dim3(grid), dim3((NEW + 1 + NMW) * 32), smem, st, pdl_enabled(), tm, p));
     B2_LAUNCH_OK("k_resblock");
     return 0;
 }

@@ -229,6 +229,8 @@ __global__ void __launch_bounds__(256) k_build_windows(const int32_t *__restrict
                                                       float *__restrict__ win_raw, float *__restrict__ win_norm, __nv_bfloat16 *__restrict__ win_norm_b,
                                                       int B, int nframes, int max_sessions, unsigned *__restrict__ claim, unsigned epoch,
                                                       int *__restrict__ err_flag) {
+    pdl_trigger();
+    pdl_wait();
     const int nwin = nframes / 8;
     __shared__ int s_ok;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -269,7 +271,7 @@ int launch_build_windows(const int32_t *slots, const float *mel, float *pre_pool
                          float *win_raw, float *win_norm, __nv_bfloat16 *win_norm_b, int B, int nframes,
                          int max_sessions, unsigned *claim, unsigned epoch, int *err_flag, cudaStream_t st) {
     if (B <= 0) return 0;
-    k_build_windows<<<B, 256, 0, st>>>(slots, mel, pre_pool, mean, scale, win_raw, win_norm, win_norm_b, B, nframes, max_sessions, claim, epoch, err_flag);
+    B2_CUDA_OK(launch_k(k_build_windows, dim3(B), dim3(256), 0, st, pdl_enabled(), slots, mel, pre_pool, mean, scale, win_raw, win_norm, win_norm_b, B, nframes, max_sessions, claim, epoch, err_flag));
     B2_LAUNCH_OK("k_build_windows");
     return 0;
 }
@@ -370,6 +372,8 @@ __global__ void __launch_bounds__(192) k_chunker_pre(const float *__restrict__ m
 // Operand of the chunker prologue on tensor cores: inb[w][t][ci] = audio[w][12 ci + t] (ci < 256), mel_flat[w][12 (ci - 256) + t] (ci < 336),
 // 0 (ci < 384) -- the two raw `.view` reinterpretations of HelloSippyRT.py:221-224 side by side as one channels-last bf16 tensor [W][12][384].
 __global__ void __launch_bounds__(384) k_chunker_in(const float *__restrict__ mel, const float *__restrict__ audio, __nv_bfloat16 *__restrict__ inb, int W) {
+    pdl_trigger();
+    pdl_wait();
     const int ci = threadIdx.x;
     for (int w = blockIdx.x; w < W; w += gridDim.x) {
         float v[12];
@@ -387,7 +391,7 @@ __global__ void __launch_bounds__(384) k_chunker_in(const float *__restrict__ me
 
 int launch_chunker_in(const float *mel, const float *audio, __nv_bfloat16 *inb, int W, cudaStream_t st) {
     if (W <= 0) return 0;
-    k_chunker_in<<<(unsigned)std::min<long long>(W, (long long)sm_count() * 8), 384, 0, st>>>(mel, audio, inb, W);
+    B2_CUDA_OK(launch_k(k_chunker_in, dim3((unsigned)std::min<long long>(W, (long long)sm_count() * 8)), dim3(384), 0, st, pdl_enabled(), mel, audio, inb, W));
     B2_LAUNCH_OK("k_chunker_in");
     return 0;
 }
@@ -412,6 +416,8 @@ int launch_chunker_pre(const float *mel, const float *audio, const float *wm, co
 }
 
 __global__ void __launch_bounds__(256) k_chunker_final(const float *__restrict__ audio, const float *__restrict__ post, float *__restrict__ out, long long n) {
+    pdl_trigger();
+    pdl_wait();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         const long long w = e >> 11;
@@ -425,7 +431,7 @@ int launch_chunker_final(const float *audio, const float *post, float *out, int 
     const long long n = (long long)W * 2048;
     if (n <= 0) return 0;
     long long blocks = (n + 255) / 256, cap = (long long)sm_count() * 16;
-    k_chunker_final<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(audio, post, out, n);
+    B2_CUDA_OK(launch_k(k_chunker_final, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(256), 0, st, pdl_enabled(), audio, post, out, n));
     B2_LAUNCH_OK("k_chunker_final");
     return 0;
 }

@@ -58,6 +58,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #define DBG(k) do { if (p.dbg && blockIdx.x < 8192 && blockIdx.y == 0) p.dbg[(size_t)blockIdx.x * 8 + (k)] = gtime(); } while (0)
 template <int N_TILE>
 __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128) ? 2 : 1)) k_conv_umma(const __grid_constant__ CUtensorMap tmap_w, const UmmaParams p) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = p.KB;
@@ -129,7 +130,10 @@ __global__ void __launch_bounds__(kThreads, (N_TILE <= 64) ? 4 : ((N_TILE <= 128
             cp_async16(sA_u32 + (uint32_t)(((kb * cpr + c) * p.R + r) * 16), src, (ok && !(p.flags & 8)) ? 16u : 0u);
         }
     };
-    if (warp < 4) load_a_block(0);
+    if (warp < 4) {
+        pdl_wait();                 // the activations are the previous kernel's output (the weight ring above overlapped its tail)
+        load_a_block(0);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -336,6 +340,7 @@ template <int N_TILE, int MINB>
 __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
                                                                   const UmmaParams2 pp) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    pdl_trigger();
     const UmmaParams &p = pp.b;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = p.KB;
@@ -375,6 +380,8 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t crank = pp.mc ? cluster_ctarank() : 0u;
+    // everything above overlapped the previous kernel (PDL); the weight producer (warp 4) reads nothing a kernel writes and goes straight on
+    if (warp != 4) pdl_wait();
 
     auto tile_coords = [&](int tile, int &w0, int &t0, int &n0) {
         const int mt = (pp.ntiles > 1) ? fdiv(tile, p.m_ntiles) : tile;
@@ -732,7 +739,7 @@ static int launch_nt(const CUtensorMap &tm, const UmmaParams &p, dim3 grid, size
         B2_CUDA_OK(cudaFuncSetAttribute(k_conv_umma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         g_attr_set[dev][slot] = true;
     }
-    k_conv_umma<NT><<<grid, kThreads, smem, st>>>(tm, p);
+    B2_CUDA_OK(launch_k(k_conv_umma<NT>, dim3(grid), dim3(kThreads), smem, st, pdl_enabled(), tm, p));
     B2_LAUNCH_OK("k_conv_umma");
     return 0;
 }
@@ -870,7 +877,7 @@ static int launch_nt2(const CUtensorMap &tm, const CUtensorMap *tm_half, UmmaPar
         p.b.dbg = pdbg_buf;
     }
     if (!p.mc) {
-        k_conv_umma_p<NT, MINB><<<grid, kThreads2, smem, st>>>(tm, tm, p);
+        B2_CUDA_OK(launch_k(k_conv_umma_p<NT, MINB>, dim3(grid), dim3(kThreads2), smem, st, pdl_enabled(), tm, tm, p));
         B2_LAUNCH_OK("k_conv_umma_p");
         if (pdbg_on) {
             cudaStreamSynchronize(st);

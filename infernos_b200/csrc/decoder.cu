@@ -54,13 +54,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, uint
                  ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
-// Programmatic dependent launch (PDL): a decoder step is a chain of ~74 short kernels on one stream.  Launched with the programmatic-serialization
-// attribute, kernel N+1 may become resident while kernel N is still running: it announces itself early (launch_dependents), does the work that
-// depends on nothing (barrier init, TMEM allocation, descriptor prefetch), and only then waits for kernel N to complete and flush (wait).
-// Without the attribute both instructions are no-ops.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 
@@ -612,18 +605,6 @@ int make_tma_2d_bf16(CUtensorMap *tm, const void *ptr, long long rows, int K, lo
 
 static bool g_gemm_attr[64][4] = {};
 
-// <<<>>> with the programmatic-stream-serialization attribute when pdl is set (see pdl_trigger / pdl_wait)
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args &&...args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
-}
-
 int launch_gemm_tc(const GemmTcArgs &a, cudaStream_t st) {
     if (a.M <= 0) return 0;
     if (!a.tmA || !a.tmB || !a.bias || (a.nt != 64 && a.nt != 128) || a.N % a.nt || a.K % 64 || a.K < 64) return set_error("gemm_tc: bad arguments (N %d nt %d K %d)", a.N, a.nt, a.K);
@@ -897,7 +878,7 @@ b2_dec *b2_dec_create(int device, int mode, int max_sessions, int max_rows, int 
     if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); return nullptr; }
     b2_dec *d = new b2_dec();
     d->device = device; d->mode = mode; d->max_sessions = max_sessions; d->max_rows = max_rows; d->max_steps = max_steps; d->max_enc = max_enc_len;
-    d->use_pdl = !(getenv("B2_DEC_PDL") && atoi(getenv("B2_DEC_PDL")) == 0);
+    d->use_pdl = pdl_enabled() && !(getenv("B2_DEC_PDL") && atoi(getenv("B2_DEC_PDL")) == 0);
     return d;
 }
 

@@ -31,6 +31,11 @@ int set_error(const char *fmt, ...) {
     return 1;
 }
 
+bool pdl_enabled() {
+    static const bool on = !(getenv("B2_PDL") && atoi(getenv("B2_PDL")) == 0);
+    return on;
+}
+
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -513,7 +518,7 @@ static int chunker_fwd(b2_ctx *c, const float *win_raw, const float *audio, int 
             // post_conv (64 -> 256, k8, stride 24, no padding; HelloSippyRT.py:233-234) = [W*8][512] x [512][256]
             GemmTcArgs g;
             g.tmA = reinterpret_cast<const CUtensorMap *>(c->c_post_tmA); g.tmB = reinterpret_cast<const CUtensorMap *>(c->c_post_tmB);
-            g.bias = c->c_post.bias; g.out32 = ws.post; g.M = W * 8; g.N = 256; g.K = 512; g.nt = 128;
+            g.bias = c->c_post.bias; g.out32 = ws.post; g.M = W * 8; g.N = 256; g.K = 512; g.nt = 128; g.pdl = pdl_enabled();
             PROF(PC_CONV_TC, launch_gemm_tc(g, st));
             PROF(PC_OTHER, launch_chunker_final(audio, ws.post, out, W, st));
             return 0;
