@@ -204,3 +204,16 @@ def test_engine_end_to_end_with_the_gpu_front_half(sd):
     for i in range(2):
         a, r = torch.cat(got[i]), torch.cat(ref[i])
         assert a.shape == r.shape and float((a - r).abs().max()) <= 1e-3
+
+
+def test_worker_with_gpu_front_half_reference_load_test_shape():
+    """The reference's own load test (HelloSippyRTPipeTest.py:180-236) in miniature: requests queued at once on InfernTTSWorker(continuous=True)
+    with the GPU front half and pre-encoded dispatch; every session ends, gets (ends_at - 1) * 256 samples (A.5) with as many payload bytes."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import session_bench
+    r = session_bench.run(6, 24, "bf16")
+    assert r["sessions"] == 6 and r["payload_bytes_equal_samples"] and r["all_faster_than_real_time"]
+    # maxlen = 24 decoder steps -> ends_at = 26 -> (26 - 1) * 256 samples at 8 kHz
+    assert abs(r["audio_s_per_session"] - 25 * 256 / 8000.0) < 1e-9
+    assert r["time_to_first_frame_s"]["p99"] <= r["time_to_last_frame_s"]["p50"]
