@@ -46,10 +46,15 @@ class InfernTTSWorker(InfernBatchedWorker):
     output_sr: int
 
     continuous: bool = False
+    async_dispatch: bool = False
 
-    def __init__(self, lang, output_sr, device=None, continuous: bool = False, **engine_kwa):
+    def __init__(self, lang, output_sr, device=None, continuous: bool = False, async_dispatch: bool = False, **engine_kwa):
+        """async_dispatch (continuous mode): the dispatch callbacks of a call run on a second thread, in order, while this thread already
+        drives the next engine call -- the reference overlaps generation and dispatch the same way in its load test
+        (HelloSippyTTSRT/HelloSippyRTPipeTest.py:126-161: separate executors); the GPU no longer idles while Python slices and hands out audio."""
         super().__init__()
         self.continuous = continuous
+        self.async_dispatch = async_dispatch and continuous
         if device is None:
             device = get_torch_hw()
         kwa = dict(lang2model[lang])
@@ -93,6 +98,31 @@ class InfernTTSWorker(InfernBatchedWorker):
             return super().run()
         self.thread_started()
         cohorts: List[HelloSippyPipeStateBatched] = []
+        dq, dthread = None, None
+        if self.async_dispatch:
+            import queue
+            import threading
+            dq = queue.Queue()
+
+            def dispatcher():
+                while True:
+                    job = dq.get()
+                    if job is None:
+                        return
+                    try:
+                        job()
+                    except Exception as e:          # a listener's callback must not take the worker down
+                        print(f"InfernTTSWorker: dispatch callback failed: {e!r}")
+            dthread = threading.Thread(target=dispatcher, daemon=True)
+            dthread.start()
+        try:
+            self._run_continuous(cohorts, dq)
+        finally:
+            if dq is not None:
+                dq.put(None)
+                dthread.join()
+
+    def _run_continuous(self, cohorts, dq):
         while self.get_state() == RTPWrkTRun:
             in_flight = sum(len(c.dispatch) for c in cohorts)
             room = self.max_batch_size - in_flight
@@ -117,7 +147,12 @@ class InfernTTSWorker(InfernBatchedWorker):
                 raise
             alive = []
             for c in cohorts:
-                if self.tts_engine.unbatch_and_dispatch(c):
+                if dq is None:
+                    more = self.tts_engine.unbatch_and_dispatch(c)
+                else:
+                    deliver, more = self.tts_engine.unbatch_prepare(c)
+                    dq.put(deliver)
+                if more:
                     alive.append(c)
                 else:
                     c.release()                       # its pre_frames slots go back to the pool at once

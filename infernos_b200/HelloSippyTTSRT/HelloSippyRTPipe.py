@@ -468,10 +468,14 @@ class HelloSippyRTPipe:
         state.audio = self.resampler(audio) if self.resampler else audio
         state.g711 = None
 
-    def unbatch_and_dispatch(self, state: HelloSippyPipeStateBatched) -> bool:
+    def unbatch_prepare(self, state: HelloSippyPipeStateBatched):
+        """The bookkeeping half of unbatch_and_dispatch (:242-259): ONE device->host copy for the whole batch, the slice arithmetic, and the
+        end-of-sentence marking (`state.dispatch[i] = None`).  -> (deliver, more): `deliver()` makes the callbacks, in the reference's
+        order, and may run on another thread (InfernTTSWorker(async_dispatch=True)); `more` is the method's return value."""
         sr_rr = self.model_sr // self.output_sr
         end_idx = state.idx - 1
         stepsize = 256 * 2 // sr_rr
+        actions = []
         with self.cuda_lock:
             audio = state.audio.cpu()                       # one D2H for the whole batch
             pre_enc = getattr(state, "pre_encoded", None) or [False] * len(state.dispatch)
@@ -480,26 +484,40 @@ class HelloSippyRTPipe:
             ename = "PCMA" if self.law == LAW_ALAW else "PCMU"
             asize = audio.size(1)
             starts, ends = state.starts_at.tolist(), state.ends_at.tolist()
+            idx = state.idx
             for i, dispatch in enumerate(state.dispatch):
                 if dispatch is None:
                     continue
-                startoff = max(0, asize - (state.idx - starts[i]) * stepsize)
-                endoff = min(asize, asize - ((state.idx - ends[i]) * stepsize if ends[i] >= 0 else 0))
+                startoff = max(0, asize - (idx - starts[i]) * stepsize)
+                endoff = min(asize, asize - ((idx - ends[i]) * stepsize if ends[i] >= 0 else 0))
                 assert startoff <= endoff
-                if startoff != endoff:
-                    if g711 is not None and pre_enc[i]:
-                        dispatch(G711AudioChunk(audio[i][startoff:endoff], self.output_sr, g711[i, startoff:endoff].tobytes(), ename))
-                    else:
-                        dispatch(audio[i][startoff:endoff])
-                    if g711 is not None and state.dispatch_g711[i] is not None:
-                        state.dispatch_g711[i](g711[i, startoff:endoff].tobytes())
-                if 0 <= ends[i] <= end_idx:
-                    dispatch(None)
+                ended = 0 <= ends[i] <= end_idx
+                if startoff != endoff or ended:
+                    cb711 = state.dispatch_g711[i] if g711 is not None else None
+                    actions.append((dispatch, i, startoff, endoff, ended, g711 is not None and pre_enc[i], cb711))
+                if ended:
                     state.dispatch[i] = None
             alive = (state.ends_at < 0) | (state.ends_at > end_idx)
-            if not bool(alive.any()):
-                return False
-        return True
+            more = bool(alive.any())
+        out_sr = self.output_sr
+
+        def deliver():
+            for dispatch, i, startoff, endoff, ended, as_chunk, cb711 in actions:
+                if startoff != endoff:
+                    if as_chunk:
+                        dispatch(G711AudioChunk(audio[i][startoff:endoff], out_sr, g711[i, startoff:endoff].tobytes(), ename))
+                    else:
+                        dispatch(audio[i][startoff:endoff])
+                    if cb711 is not None:
+                        cb711(g711[i, startoff:endoff].tobytes())
+                if ended:
+                    dispatch(None)
+        return deliver, more
+
+    def unbatch_and_dispatch(self, state: HelloSippyPipeStateBatched) -> bool:
+        deliver, more = self.unbatch_prepare(state)
+        deliver()
+        return more
 
     def get_rand_voice_id(self) -> int:
         return torch.randint(0, len(self.speaker_embeddings), (1,)).item()

@@ -195,6 +195,43 @@ def test_worker_admits_requests_while_a_sentence_is_in_flight_cpu():
     assert sorted(w.tts_engine._free) == list(range(8))
 
 
+def _run_worker(async_dispatch):
+    from infernos_b200.Cluster.InfernTTSWorker import InfernTTSWorker
+    w = InfernTTSWorker.__new__(InfernTTSWorker)
+    InfernBatchedWorker.__init__(w)
+    w.continuous, w.async_dispatch, w.output_sr, w.max_batch_size = True, async_dispatch, 8000, 4
+    w.tts_engine = cpu_pipe(ScriptedFrontend(plans(), maxlen=100))
+    got, order, lock, done = {}, [], threading.Lock(), threading.Event()
+
+    def cb(name):
+        def f(chunk):
+            with lock:
+                order.append((name, threading.current_thread().name))
+                got.setdefault(name, []).append(None if chunk is None else chunk.clone())
+                if sum(1 for v in got.values() if v[-1] is None) == 3:
+                    done.set()
+        return f
+    for t in ("long", "short", "medium"):
+        w.infer(HelloSippyPlayRequest(uuid.uuid4(), t, w.get_voice(0), cb(t)))
+    w.start()
+    assert done.wait(20)
+    w.stop()
+    assert sorted(w.tts_engine._free) == list(range(8))
+    return got, order
+
+
+def test_async_dispatch_delivers_the_same_chunks_in_the_same_order_cpu():
+    """InfernTTSWorker(async_dispatch=True): callbacks run on the dispatcher thread while the worker drives the next call (the reference's
+    load test overlaps the two on separate executors, HelloSippyRTPipeTest.py:126-161); per session the chunks and their order must not change."""
+    sync, _ = _run_worker(False)
+    asyn, order = _run_worker(True)
+    assert set(sync) == set(asyn)
+    for t in sync:
+        assert len(sync[t]) == len(asyn[t]) and asyn[t][-1] is None and all(c is not None for c in asyn[t][:-1]), t
+        assert torch.equal(torch.cat(sync[t][:-1]), torch.cat(asyn[t][:-1])), t
+    assert len({th for _, th in order}) == 1                              # every callback came from the one dispatcher thread, in queue order
+
+
 @pytest.mark.gpu
 def test_continuous_batching_is_session_independent_on_the_gpu():
     from infernos_b200 import synth
