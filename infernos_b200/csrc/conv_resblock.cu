@@ -427,16 +427,34 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                 } else {
 #pragma unroll 1
                 for (int s = s0; s < kS; s += SSTEP) {
+                    const bool probe = DBG && threadIdx.x == 0 && i == 1 && e == 0 && s == 1;     // micro-phases of ONE sub-tile's epilogue (analysis build)
+                    if (probe) RB_DBG(15);
                     mbar_wait(full0 + 8u * (uint32_t)s, par);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (threadIdx.x == 0 && s == 0) RB_DBG(3 + 4 * i + 2 * e);
+                    if (probe) RB_DBG(29);
 #pragma unroll 1
                     for (int cc = 0; cc < CHW; cc++) {
                         uint32_t acc[32];
                         tmem_ld32(src + (uint32_t)(s * C + cbase + cc * 32), acc);
+                        if (probe && cc == 0) RB_DBG(30);
+#ifdef B2_RB_EXP_NOBIAS          // timing experiment only (wrong results): what the conv epilogue costs without the bias add
+                        write_operand_row<kRtot>(dst, s * 128 + rq, cbase + cc * 32, acc, nullptr, p.slope, inside(s));
+#else
                         write_operand_row<kRtot>(dst, s * 128 + rq, cbase + cc * 32, acc, bias + cc * 32, p.slope, inside(s));
+#endif
                     }
-                    publish_rows(ready0 + 8u * (uint32_t)s, lane);
+                    if (probe) RB_DBG(31);
+                    if constexpr (DBG) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        if (probe) RB_DBG(41);
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(ready0 + 8u * (uint32_t)s);
+                        if (probe) RB_DBG(42);
+                    } else {
+                        publish_rows(ready0 + 8u * (uint32_t)s, lane);
+                    }
                 }
                 }
                 if (threadIdx.x == 0) RB_DBG(4 + 4 * i + 2 * e);
@@ -783,11 +801,12 @@ int resblock_pack(const Layer *const conv1[3], const Layer *const conv2[3], ResB
                                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete tm; return set_error("resblock: cuTensorMapEncodeTiled failed with CUresult %d (C %d k %d)", (int)r, C, k); }
     out.tmap = tm;
-    return 0;
+    return resblock_t_pack(out, allocs, bytes);          // C = 32: the stacked-output kernel's copy of the weights (no-op otherwise)
 }
 
 void resblock_free(ResBlockPack &p) {
     if (p.tmap) { delete reinterpret_cast<CUtensorMap *>(p.tmap); p.tmap = nullptr; }
+    resblock_t_free(p);
 }
 
 
@@ -842,6 +861,9 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     if (post && (pk.C != 32 || !a.post_w || !a.post_b || !a.acc_src)) return set_error("resblock: the conv_post epilogue needs C = 32, weights and the MRF partial sum");
     if (!a.x || (!a.out32 && !a.outb && !post)) return set_error("resblock: null input or no output");
     if (a.W <= 0 || a.T <= 0) return 0;
+    // C = 32: the stacked-output kernel (conv_resblock_t.cu).  B2_RB_T=0 keeps this file's time-as-M kernel for A/B runs and the variant tests.
+    static const bool rbt_on = !(getenv("B2_RB_T") && atoi(getenv("B2_RB_T")) == 0);
+    if (rbt_on && pk.tmap_t) return launch_resblock_t(a, st);
     RbParams p;
     p.x = a.x; p.acc_src = a.acc_src; p.out32 = a.out32; p.outb = a.outb;
     p.post_w = a.post_w; p.post_b = a.post_b; p.audio = a.audio;
@@ -914,6 +936,8 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
             fprintf(stderr, "[rb dbg] C=%d k=%d T=%d ctas=%lld (avg of %d) cycles since CTA start: setup %.0f | load done %.0f | end %.0f\n", pk.C, pk.taps, a.T, nct, cnt, ev[1], ev[2], ev[28]);
             fprintf(stderr, "[rb dbg]   load done per sub-tile %.0f %.0f %.0f %.0f | acc parked %.0f | final: ready/done per sub-tile %.0f/%.0f %.0f/%.0f %.0f/%.0f %.0f/%.0f\n",
                     ev[44], ev[45], ev[46], ev[47], ev[40], ev[32], ev[36], ev[33], ev[37], ev[34], ev[38], ev[35], ev[39]);
+            fprintf(stderr, "[rb dbg]   conv-epilogue micro-phases (warp 0, pair 1 epilogue 1, sub-tile 1): barrier wait %.0f | TMEM load %.0f | math + st.shared %.0f | proxy fence %.0f | arrive %.0f\n",
+                    ev[29] - ev[15], ev[30] - ev[29], ev[31] - ev[30], ev[41] - ev[31], ev[42] - ev[41]);
             for (int i = 0; i < 3; i++)
                 fprintf(stderr, "[rb dbg]   pair %d: conv1 issue %.0f..%.0f (%.0f) | epi1 first-ready %.0f done %.0f | conv2 issue %.0f..%.0f (%.0f) | epi2 first-ready %.0f done %.0f\n", i,
                         ev[16 + 4 * i], ev[17 + 4 * i], ev[17 + 4 * i] - ev[16 + 4 * i], ev[3 + 4 * i], ev[4 + 4 * i],

@@ -29,6 +29,9 @@ struct ResBlockPack {
     std::vector<float> h_bias1;      // [3][C] conv1 biases (host: passed as kernel parameters)
     std::vector<float> h_cbias;      // [3][C] running sums of the conv2 biases
     void *tmap = nullptr;            // host copy of the CUtensorMap over w
+    // stacked-output kernel (conv_resblock_t.cu, C = 32): the same weights with every conv's taps in reverse order, one tap per TMA box
+    __nv_bfloat16 *wt = nullptr;     // [6*taps][C][C] bf16: wt[c*taps + q] = tap taps-1-q of conv c
+    void *tmap_t = nullptr;
 };
 
 struct Workspace {

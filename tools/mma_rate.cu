@@ -22,6 +22,8 @@ struct Cfg {
     int distinct;   // how many different A start rows are cycled through (1 = same operand every time)
     int a_step;     // rows between consecutive A starts (tap shift)
     int commit_every; // 0: one commit at the end; n: a tcgen05.commit (to a second barrier) after every n MMAs
+    int smem_kb;      // dynamic shared memory of the launch (100: two CTAs share an SM)
+    int alt_k;        // 1: alternate between the two K16 halves of a 32-channel operand (A + 2 chunks, B + 32 bytes), as the C = 32 kernels do
 };
 
 __global__ void __launch_bounds__(128) k_rate(Cfg c, unsigned long long *out) {
@@ -30,7 +32,7 @@ __global__ void __launch_bounds__(128) k_rate(Cfg c, unsigned long long *out) {
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5;
     // zero operands (timing does not depend on the values)
-    for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < c.smem_kb * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(128) k_rate(Cfg c, unsigned long long *out) {
     if (warp == 1) {
         const bool leader = elect_one();
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(c.N >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 96 * 1024;
+        const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + (uint32_t)(c.smem_kb - 32) * 1024;
         const int R = 701;
         uint64_t adesc0;
         if (c.a_mode == 0) adesc0 = smem_desc(sA, R * 16, 128u, 0u);
@@ -60,7 +62,8 @@ __global__ void __launch_bounds__(128) k_rate(Cfg c, unsigned long long *out) {
             int d = 0;
             for (int i = 0; i < c.iters; i++) {
                 const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)(d * c.a_step) * row_units);
-                if (leader) umma_f16(tmem, adesc, bdesc0, idesc, 1u);
+                const bool hi = c.alt_k && (i & 1);
+                if (leader) umma_f16(tmem, adesc + (hi ? (uint64_t)(2 * R) : 0ull), bdesc0 + (hi ? 2ull : 0ull), idesc, 1u);
                 if (++d == c.distinct) d = 0;
                 if (c.commit_every && ((i + 1) % c.commit_every) == 0 && leader) umma_commit(smem_u32(&bar2));
             }
@@ -89,7 +92,7 @@ int main() {
                 Cfg c;
                 c.N = Ns[ni]; c.a_mode = a_mode; c.iters = 2048;
                 c.b_mode = (variant == 2) ? 0 : ((c.N == 32) ? 4 : 2);
-                c.commit_every = 0;
+                c.commit_every = 0; c.smem_kb = 160; c.alt_k = 0;
                 c.distinct = (variant == 0) ? 1 : 11; c.a_step = (variant == 0) ? 0 : ((a_mode == 1) ? 8 : 5);
                 if (a_mode == 1 && variant == 2) continue;
                 for (int grid : {1, 148}) {
@@ -107,7 +110,7 @@ int main() {
     for (int ni = 0; ni < 4; ni++)
         for (int ce : {0, 32, 8, 4, 2, 1}) {
             Cfg c;
-            c.N = Ns[ni]; c.a_mode = 0; c.iters = 2048; c.b_mode = (c.N == 32) ? 4 : 2; c.distinct = 11; c.a_step = 5; c.commit_every = ce;
+            c.N = Ns[ni]; c.a_mode = 0; c.iters = 2048; c.b_mode = (c.N == 32) ? 4 : 2; c.distinct = 11; c.a_step = 5; c.commit_every = ce; c.smem_kb = 160; c.alt_k = 0;
             k_rate<<<148, 128, 160 * 1024>>>(c, d_out);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
@@ -116,5 +119,20 @@ int main() {
             std::sort(h.begin(), h.end());
             printf("N=%3d commit_every=%2d : %6.1f cycles/MMA\n", c.N, ce, (double)h[74] / c.iters);
         }
+    printf("# 64B-swizzled B (rows of 32 bf16) at every N, alternating K16 halves; one and two CTAs per SM (round 2, conv_resblock_t.cu's operands)\n");
+    for (int N : {32, 64, 96, 128})
+        for (int bm : {4, 2})
+            for (int two : {0, 1}) {
+                Cfg c;
+                c.N = N; c.a_mode = 0; c.iters = 2048; c.b_mode = bm; c.distinct = 11; c.a_step = 5; c.commit_every = 0; c.smem_kb = two ? 100 : 160; c.alt_k = 1;
+                const int grid = two ? 296 : 148;
+                k_rate<<<grid, 128, c.smem_kb * 1024>>>(c, d_out);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+                std::vector<unsigned long long> h(grid);
+                cudaMemcpy(h.data(), d_out, grid * 8, cudaMemcpyDeviceToHost);
+                std::sort(h.begin(), h.end());
+                printf("N=%3d b_mode=%d ctas_per_sm=%d : %6.1f cycles/MMA per CTA\n", N, bm, two + 1, (double)h[grid / 2] / c.iters);
+            }
     return 0;
 }
