@@ -571,12 +571,12 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                 if (has_acc && PF) ld_acc(0, accA);
                 if (threadIdx.x == 0) RB_DBG(40);
                 const float rcp = p.rdiv, nd = -p.div;
-                // (one copy of this body: the next piece's partial sums are fetched into accB and moved over, which is cheaper
-                // than a second, ping-pong copy of the code -- the kernel has to stay small)
-#pragma unroll 1
-                for (int q = 0; q < NCHW; q++) {
-                    float4 (&acur)[8] = accA;
-                    float4 (&anx)[8] = accB;
+                // One 32x32 piece.  `cur` holds its partial sums; the next piece's are requested into `nxt` while this one is worked on, and the two
+                // buffers swap roles from piece to piece (moving one into the other made every piece wait for its loads).  The row loop is
+                // branch-free: four staged rows are read back at a time and the stores are predicated -- with `if (row is an output) { load; add;
+                // store; }` the compiler emitted a divergent branch and a load -> store round trip per row, one after the other (round 2: ~1.4k
+                // cycles per piece in the stacked-output kernel, whose final epilogue had the same shape).
+                auto piece = [&](int q, float4 (&cur)[8], float4 (&nxt)[8]) {
                     const int s = s0 + (q / CHW) * SSTEP, c0 = cbase + (q % CHW) * 32;
                     if ((q % CHW) == 0) {
                         mbar_wait(X_FULL(s), par);
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                         if (threadIdx.x == 0 && s == 0) RB_DBG(5 + 4 * i);
                         if (threadIdx.x == 0) RB_DBG(32 + s);
                     }
-                    if (has_acc && !PF) ld_acc(q, accA);
+                    if (has_acc && !PF) ld_acc(q, cur);
                     {
                         uint32_t a32[32];
                         tmem_ld32(tmem_X + tm_lane + (uint32_t)(s * C + c0), a32);
@@ -596,35 +596,46 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                             *reinterpret_cast<uint4 *>(stg + lane * kRbStageLd + j * 4) = make_uint4(a32[4 * j], a32[4 * j + 1], a32[4 * j + 2], a32[4 * j + 3]);
                     }
                     __syncwarp();
-                    if (has_acc && PF && q + 1 < NCHW) ld_acc(q + 1, anx);
+                    if (has_acc && PF && q + 1 < NCHW) ld_acc(q + 1, nxt);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        if (!((out_t[j] >> s) & 1u)) continue;
-                        float4 v = *reinterpret_cast<const float4 *>(stg + (j * 4 + sub_r) * kRbStageLd + c4 * 4);
-                        if (has_acc) { v.x = acur[j].x + v.x; v.y = acur[j].y + v.y; v.z = acur[j].z + v.z; v.w = acur[j].w + v.w; }
-                        if (has_div) {
-                            // v / div as a reciprocal multiply plus one Newton correction (correctly rounded away from denormals;
-                            // __fdiv_rn was 9 % of this kernel's stall samples)
-                            float q0;
-                            q0 = v.x * rcp; v.x = fmaf(fmaf(nd, q0, v.x), rcp, q0);
-                            q0 = v.y * rcp; v.y = fmaf(fmaf(nd, q0, v.y), rcp, q0);
-                            q0 = v.z * rcp; v.z = fmaf(fmaf(nd, q0, v.z), rcp, q0);
-                            q0 = v.w * rcp; v.w = fmaf(fmaf(nd, q0, v.w), rcp, q0);
-                        }
-                        const size_t o = (row0 + (size_t)s * 128 + j * 4) * C + (size_t)(c0 + c4 * 4);
-                        if (has_o32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
-                        if (has_ob) {
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
-                            __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
-                            *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                    for (int jh = 0; jh < 8; jh += 4) {
+                        float4 v[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; jj++) v[jj] = *reinterpret_cast<const float4 *>(stg + ((jh + jj) * 4 + sub_r) * kRbStageLd + c4 * 4);
+#pragma unroll
+                        for (int jj = 0; jj < 4; jj++) {
+                            const int j = jh + jj;
+                            if (has_acc) { v[jj].x = cur[j].x + v[jj].x; v[jj].y = cur[j].y + v[jj].y; v[jj].z = cur[j].z + v[jj].z; v[jj].w = cur[j].w + v[jj].w; }
+                            if (has_div) {
+                                // v / div as a reciprocal multiply plus one Newton correction (correctly rounded away from denormals;
+                                // __fdiv_rn was 9 % of this kernel's stall samples)
+                                float q0;
+                                q0 = v[jj].x * rcp; v[jj].x = fmaf(fmaf(nd, q0, v[jj].x), rcp, q0);
+                                q0 = v[jj].y * rcp; v[jj].y = fmaf(fmaf(nd, q0, v[jj].y), rcp, q0);
+                                q0 = v[jj].z * rcp; v[jj].z = fmaf(fmaf(nd, q0, v[jj].z), rcp, q0);
+                                q0 = v[jj].w * rcp; v[jj].w = fmaf(fmaf(nd, q0, v[jj].w), rcp, q0);
+                            }
+                            const bool out = ((out_t[j] >> s) & 1u) != 0u;
+                            const size_t o = out ? (row0 + (size_t)s * 128 + j * 4) * C + (size_t)(c0 + c4 * 4) : 0;
+                            if (has_o32)
+                                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                                             ::"l"(p.out32 + o), "f"(v[jj].x), "f"(v[jj].y), "f"(v[jj].z), "f"(v[jj].w), "r"((int)out) : "memory");
+                            if (has_ob) {
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v[jj].x, p.outb_slope), lrelu_f(v[jj].y, p.outb_slope));
+                                __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v[jj].z, p.outb_slope), lrelu_f(v[jj].w, p.outb_slope));
+                                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.b32 [%0], {%1, %2};\n\t}"
+                                             ::"l"(p.outb + o), "r"(*reinterpret_cast<uint32_t *>(&h0)), "r"(*reinterpret_cast<uint32_t *>(&h1)), "r"((int)out) : "memory");
+                            }
                         }
                     }
                     __syncwarp();
-                    if (has_acc && PF) {
-#pragma unroll
-                        for (int j = 0; j < 8; j++) accA[j] = accB[j];
-                    }
                     if ((q % CHW) == CHW - 1 && threadIdx.x == 0) RB_DBG(36 + s);
+                };
+                static_assert(NCHW % 2 == 0, "the final epilogue walks the pieces in pairs");
+#pragma unroll 1
+                for (int q = 0; q < NCHW; q += 2) {
+                    piece(q, accA, accB);
+                    piece(q + 1, accB, accA);
                 }
                 }
                 if (threadIdx.x == 0) RB_DBG(6 + 4 * i);

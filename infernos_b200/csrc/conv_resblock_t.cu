@@ -134,6 +134,19 @@ __device__ __forceinline__ void rbt_operand_row(uint32_t a_u32, int row16, const
     }
 }
 
+// predicated 16-byte stores: the row loops of the final epilogues stay branch-free (with `if (row is an output) { load; ...; store; }` the
+// compiler emitted a divergent branch and a load -> store round trip per row, one after the other: ~1.4k cycles per 32-row piece, measured)
+__device__ __forceinline__ void rbt_stg_v4(float *ptr, const float4 &v, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void rbt_stg_v2(void *ptr, uint32_t a, uint32_t b, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.b32 [%0], {%1, %2};\n\t}" ::"l"(ptr), "r"(a), "r"(b), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void rbt_sts_v4(uint32_t addr, float a, float b, float c, float d, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"((int)pred));
+}
+
 // this warp's operand rows (and TMEM accesses) of the phase are done: publish them to the MMA thread (one arrival per warp)
 __device__ __forceinline__ void rbt_publish(uint32_t bar, int lane) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> UMMA (async proxy) reads
@@ -200,7 +213,7 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
     const int S = p.S;
     if (threadIdx.x == 0) RBT_DBG(0);
 
-    // the slab's x rows (and the MRF partial sum's output rows) start their way from HBM into L2 before anything else: one 128-byte line per row
+    // the slab's x rows start their way from HBM into L2 before anything else: one 128-byte line per row
     if (warp < 4) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -208,7 +221,6 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
             if (r < S && t >= 0 && t < p.T) {
                 const size_t off = ((size_t)w * p.T + t) * C;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + off));
-                if (p.acc_src && r >= p.H && r < p.H + p.V) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc_src + off));
             }
         }
     }
@@ -317,6 +329,17 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
 #pragma unroll 1
         for (int i = 0; i < 3; i++) {
             const uint32_t par = (uint32_t)(i & 1);
+            if (i == 2 && p.acc_src) {
+                // the MRF partial sum of the output rows: into L2 NOW, two convs (~5k cycles) before the final epilogue reads it.  Requested at CTA
+                // start (30-45k cycles ahead) the lines were gone again by the time they were needed -- the final epilogue ran at HBM latency with
+                // 16 KB in flight per CTA, 6-9k cycles for 56 KB (phase timestamps, profiles/).
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int r = 4 * m + q, t = t_base + r;
+                    if (r + 3 >= p.H && r < p.H + p.V + 3 && r < S && t >= 0 && t < p.T)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc_src + ((size_t)w * p.T + t) * C));
+                }
+            }
             {
                 // ---- epilogue 1: T1 (conv1 + b1, in the mapping of dil[i]) -> lrelu -> A2 in conv2's mapping (dilation 1); T1 <- conv1's bias of the next pair
                 const int d = p.dil[i], off = p.off[i], lim = p.lim[i];
@@ -371,7 +394,7 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
             // ring and the operand buffers (rows of 128 bytes, 16-byte pieces XOR-ed with row & 7), the conv_post weights behind it.
             const uint32_t v_u32 = smem_u32(smem);
             float *wp = reinterpret_cast<float *>(smem + 65536);
-            // the MRF partial sum of the rows conv_post reads, 8 lanes per row, 8 rows per thread and batch; the first batch is requested before
+            // the MRF partial sum of the rows conv_post reads, 8 lanes per row, kPB rows per thread and batch; the first batch is requested before
             // the last conv2 has finished (it does not depend on it)
             const int r_lo = max(0, p.H - 3), r_hi = min(S, p.H + p.V + 3);
             const float *aq = p.acc_src + ((size_t)w * p.T + t_base) * C + c4 * 4;
@@ -379,10 +402,11 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
                 const int t = t_base + r;
                 return (r < r_hi && t >= 0 && t < p.T) ? *reinterpret_cast<const float4 *>(aq + (ptrdiff_t)r * C) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
-            float4 pa[8];
+            constexpr int kPB = 13;                      // rows per thread and batch: two batches cover the 390 rows of a k = 11 slab
+            float4 pa[kPB];
             const int rb0 = r_lo + ((int)threadIdx.x >> 3);
 #pragma unroll
-            for (int u = 0; u < 8; u++) pa[u] = ld_row(rb0 + 16 * u);
+            for (int u = 0; u < kPB; u++) pa[u] = ld_row(rb0 + 16 * u);
             mbar_wait(X_FULL, 0u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (threadIdx.x == 0) RBT_DBG(13);
@@ -411,65 +435,67 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
             {
                 const float rcp = p.rdiv, nd = -p.div;
 #pragma unroll 1
-                for (int rb = rb0; rb < r_hi; rb += 128) {
+                for (int rb = rb0; rb < r_hi; rb += 16 * kPB) {
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
+                    for (int u = 0; u < kPB; u++) {
                         const int r = rb + 16 * u, t = t_base + r;
                         const float4 a4 = pa[u];
-                        pa[u] = ld_row(r + 128);
-                        if (r < r_hi) {
-                            const bool in = t >= 0 && t < p.T;
-                            const uint32_t a = v_u32 + (uint32_t)(r * 128 + ((c4 ^ ((r >> 2) & 7)) << 4));
-                            float4 v;
-                            // (no memory clobber on the accesses of V in passes B and C: rows are independent, a row's store depends on its load
-                            // through the data, and volatile asm statements keep their order against the named barriers around the passes)
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-                            float o[4] = {a4.x + v.x, a4.y + v.y, a4.z + v.z, a4.w + v.w};
+                        pa[u] = ld_row(r + 16 * kPB);
+                        // (no memory clobber on the accesses of V in passes B and C: rows are independent, a row's store depends on its load
+                        // through the data, and volatile asm statements keep their order against the named barriers around the passes.  Rows
+                        // past r_hi are read (inside the CTA's shared memory) but not written.)
+                        const bool in = t >= 0 && t < p.T;
+                        const uint32_t a = v_u32 + (uint32_t)(r * 128 + ((c4 ^ ((r >> 2) & 7)) << 4));
+                        float4 v;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+                        float o[4] = {a4.x + v.x, a4.y + v.y, a4.z + v.z, a4.w + v.w};
 #pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const float q0 = o[e] * rcp;
-                                const float mm = fmaf(fmaf(nd, q0, o[e]), rcp, q0);       // (acc + r) / 3: reciprocal multiply + one Newton correction
-                                o[e] = in ? fmaxf(mm, 0.01f * mm) : 0.0f;
-                            }
-                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]));
+                        for (int e = 0; e < 4; e++) {
+                            const float q0 = o[e] * rcp;
+                            const float mm = fmaf(fmaf(nd, q0, o[e]), rcp, q0);       // (acc + r) / 3: reciprocal multiply + one Newton correction
+                            o[e] = in ? fmaxf(mm, 0.01f * mm) : 0.0f;
                         }
+                        rbt_sts_v4(a, o[0], o[1], o[2], o[3], r < r_hi);
                     }
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (threadIdx.x == 0) RBT_DBG(29);
-            // pass C (one output sample per thread and trip, up to four trips): 7 taps x 32 channels.  Tap-major: a tap's 32 weights are read once
-            // into registers and serve every trip, and the trips' accumulators are independent FMA chains.  Lane l of a warp takes row
-            // 4 * (l & 7) + (l >> 3) of the warp's 32: the eight lanes of a shared-memory phase then read rows four apart, which the (row >> 2)
-            // swizzle of V spreads over all banks (V is written by lanes that own rows 4m + q, hence that swizzle).
+            // pass C: FOUR consecutive output samples per thread (V <= 512 - 2H: at most 128 threads' worth), channel-chunk-major.  The four
+            // outputs share their input rows: 10 row reads per 4 outputs instead of 28 -- shared-memory bandwidth is what the co-resident CTA's
+            // MMAs live on.  Lanes read rows four apart, which the (row >> 2) swizzle of V spreads over all banks.
             {
                 const float pb = __ldg(p.post_b);
-                const int idx = p.H + warp * 32 + 4 * (lane & 7) + (lane >> 3);
-                float acc[4] = {pb, pb, pb, pb};
+                const int r0 = p.H + 4 * (int)threadIdx.x;
+                if (r0 < p.H + p.V) {
+                    float acc[4] = {pb, pb, pb, pb};
 #pragma unroll 1
-                for (int j = 0; j < 7; j++) {
-                    float4 wv[8];
+                    for (int ch = 0; ch < 8; ch++) {
+                        float4 wv[7];
 #pragma unroll
-                    for (int ch = 0; ch < 8; ch++) wv[ch] = *reinterpret_cast<const float4 *>(wp + j * 32 + ch * 4);
+                        for (int j = 0; j < 7; j++) wv[j] = *reinterpret_cast<const float4 *>(wp + j * 32 + ch * 4);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int rr = idx + 128 * u - 3 + j;
-                        if (128 * u < p.V && (unsigned)rr < (unsigned)S) {             // outside the slab == outside the window here
-#pragma unroll
-                            for (int ch = 0; ch < 8; ch++) {
-                                float4 x;
+                        for (int ri = 0; ri < 10; ri++) {
+                            const int rr = r0 - 3 + ri;
+                            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if ((unsigned)rr < (unsigned)S)                              // outside the slab == outside the window here
                                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
                                              : "r"(v_u32 + (uint32_t)(rr * 128 + ((ch ^ ((rr >> 2) & 7)) << 4))));
-                                acc[u] = fmaf(wv[ch].x, x.x, acc[u]); acc[u] = fmaf(wv[ch].y, x.y, acc[u]);
-                                acc[u] = fmaf(wv[ch].z, x.z, acc[u]); acc[u] = fmaf(wv[ch].w, x.w, acc[u]);
+#pragma unroll
+                            for (int o = 0; o < 4; o++) {
+                                const int j = ri - o;
+                                if (j >= 0 && j < 7) {
+                                    acc[o] = fmaf(wv[j].x, x.x, acc[o]); acc[o] = fmaf(wv[j].y, x.y, acc[o]);
+                                    acc[o] = fmaf(wv[j].z, x.z, acc[o]); acc[o] = fmaf(wv[j].w, x.w, acc[o]);
+                                }
                             }
                         }
                     }
-                }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int r = idx + 128 * u, t = t_base + r;
-                    if (r < p.H + p.V && t < p.T) p.audio[(size_t)w * p.T + t] = tanhf(acc[u]);
+                    for (int o = 0; o < 4; o++) {
+                        const int r = r0 + o, t = t_base + r;
+                        if (r < p.H + p.V && t < p.T) p.audio[(size_t)w * p.T + t] = tanhf(acc[o]);
+                    }
                 }
             }
         } else {
@@ -514,25 +540,27 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
                 }
                 __syncwarp();
                 if (has_acc && q + 1 < 4) ld_acc(q + 1, nxt);
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = *reinterpret_cast<const float4 *>(stg + (j * 4 + sub_r) * kTStageLd + c4 * 4);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    if (!is_out(q, j)) continue;
-                    float4 v = *reinterpret_cast<const float4 *>(stg + (j * 4 + sub_r) * kTStageLd + c4 * 4);
-                    if (has_acc) { v.x = cur[j].x + v.x; v.y = cur[j].y + v.y; v.z = cur[j].z + v.z; v.w = cur[j].w + v.w; }
+                    if (has_acc) { v[j].x = cur[j].x + v[j].x; v[j].y = cur[j].y + v[j].y; v[j].z = cur[j].z + v[j].z; v[j].w = cur[j].w + v[j].w; }
                     if (has_div) {
                         float q0;
-                        q0 = v.x * rcp; v.x = fmaf(fmaf(nd, q0, v.x), rcp, q0);
-                        q0 = v.y * rcp; v.y = fmaf(fmaf(nd, q0, v.y), rcp, q0);
-                        q0 = v.z * rcp; v.z = fmaf(fmaf(nd, q0, v.z), rcp, q0);
-                        q0 = v.w * rcp; v.w = fmaf(fmaf(nd, q0, v.w), rcp, q0);
+                        q0 = v[j].x * rcp; v[j].x = fmaf(fmaf(nd, q0, v[j].x), rcp, q0);
+                        q0 = v[j].y * rcp; v[j].y = fmaf(fmaf(nd, q0, v[j].y), rcp, q0);
+                        q0 = v[j].z * rcp; v[j].z = fmaf(fmaf(nd, q0, v[j].z), rcp, q0);
+                        q0 = v[j].w * rcp; v[j].w = fmaf(fmaf(nd, q0, v[j].w), rcp, q0);
                     }
                     const int r = 4 * (warp * 32 + j * 4 + sub_r) + q;
-                    const size_t o = (row0 + r) * C + (size_t)(c4 * 4);
-                    if (has_o32) *reinterpret_cast<float4 *>(p.out32 + o) = v;
+                    const bool out = is_out(q, j);
+                    const size_t o = out ? (row0 + r) * C + (size_t)(c4 * 4) : 0;
+                    if (has_o32) rbt_stg_v4(p.out32 + o, v[j], out);
                     if (has_ob) {
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v.x, p.outb_slope), lrelu_f(v.y, p.outb_slope));
-                        __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v.z, p.outb_slope), lrelu_f(v.w, p.outb_slope));
-                        *reinterpret_cast<uint2 *>(p.outb + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(lrelu_f(v[j].x, p.outb_slope), lrelu_f(v[j].y, p.outb_slope));
+                        __nv_bfloat162 h1 = __floats2bfloat162_rn(lrelu_f(v[j].z, p.outb_slope), lrelu_f(v[j].w, p.outb_slope));
+                        rbt_stg_v2(p.outb + o, *reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1), out);
                     }
                 }
                 __syncwarp();
@@ -703,7 +731,11 @@ static int launch_rbt_(const CUtensorMap &tm, const RbtParams &p, unsigned grid,
         B2_CUDA_OK(cudaFuncSetAttribute(k_resblock_t<EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTSmemBytes));
         g_rbt_attr[dev][slot] = true;
     }
-    B2_CUDA_OK(launch_k(k_resblock_t<EPI, DBG>, dim3(grid), dim3(192), (size_t)kTSmemBytes, st, pdl_enabled(), tm, p, g_rbt_dbg));
+    // B2_RBT_ONE_CTA=1 (analysis runs): ask for more shared memory than two CTAs can share, so that a CTA has the SM to itself
+    static const bool one_cta = getenv("B2_RBT_ONE_CTA") && atoi(getenv("B2_RBT_ONE_CTA")) != 0;
+    const size_t smem = one_cta ? (size_t)120 * 1024 : (size_t)kTSmemBytes;
+    if (one_cta) B2_CUDA_OK(cudaFuncSetAttribute(k_resblock_t<EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CUDA_OK(launch_k(k_resblock_t<EPI, DBG>, dim3(grid), dim3(192), smem, st, pdl_enabled(), tm, p, g_rbt_dbg));
     B2_LAUNCH_OK("k_resblock_t");
     return 0;
 }
