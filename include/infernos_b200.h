@@ -157,6 +157,11 @@ B2_API int b2_sched_poll(b2_sched *s, b2_completion *out, int max_out, uint8_t *
 /* returns when everything submitted so far has completed (its completions may still be waiting for b2_sched_poll) */
 B2_API int b2_sched_flush(b2_sched *s, int timeout_ms);
 B2_API int b2_sched_get_stats(b2_sched *s, b2_sched_stats *out);
+/* Captures and instantiates, ahead of time, the CUDA graph of every sub-batch bucket up to `max_sessions` sessions (<= 0: up to max_batch) for
+ * every staging buffer, so that no graph is ever built on the serving path: a backlog after a host hiccup makes sub-batches of sizes that were
+ * never seen before, and building their graphs right then (a few ms each) turns one hiccup into a latency tail.  Call while the scheduler is
+ * idle (before the first submit, or after b2_sched_flush); nothing is launched. */
+B2_API int b2_sched_prebuild(b2_sched *s, int max_sessions);
 
 /* ---- the step before the path: the autoregressive SpeechT5 speech decoder, HelloSippyRTPipe.py:195-229 ----------------------
  * prenet -> wrapped_decoder (six layers, KV cache) -> feat_out / prob_out, batched over sessions whose state (self-attention KV cache,
@@ -230,6 +235,16 @@ B2_API int b2_conv1d_f32(const float *d_in, const float *h_weight, const float *
  * d_acc optional fp32 [W][T][C]; d_out32 fp32 / d_outb bf16(lrelu(v, outb_slope)) [W][T][C], either may be NULL.  C in {32, 64, 128}. */
 B2_API int b2_resblock_tc(const float *d_x, const float *h_weights, const float *h_biases, int W, int T, int C, int k, int d0, int d1, int d2,
                           const float *d_acc, float *d_out32, void *d_outb, float slope, float outb_slope, float div, void *stream);
+
+/* Slab geometry of the stacked-output C = 32 ResBlock kernel (csrc/conv_resblock_t.cu) for a window of T time steps, k taps, dilations
+ * d0..d2 (`post` != 0: conv_post fused, three more halo rows).  Host arithmetic only -- no device is touched; exported so that the CPU tests
+ * can run the index-exact numpy model of the kernel (tools/resblock_t_model.py) on the library's own plan.
+ * out[10] = {S rows per slab, H halo, V output rows per tile, tiles per window, off[0..2], lim[0..2]}: conv1 of pair i reads slab rows
+ * [off[i], off[i] + lim[i]) through the operand mapping of dilation d_i.  Returns non-zero (b2_last_error) when the kernel does not cover the shape. */
+B2_API int b2_resblock_t_plan(int k, int d0, int d1, int d2, int T, int post, int *out);
+/* Test hook: C = 32 ResBlocks with at least k taps run the stacked-output kernel (default 5, B2_RB_T_MINK; measured: three-tap blocks are
+ * faster on the time-as-M kernel).  k <= 0 restores the default.  Process-wide; not for concurrent use with running launches. */
+B2_API int b2_debug_set_stacked_min_taps(int k);
 
 /* ---- bookkeeping the benchmark reports ------------------------------------------------------------- */
 /* number of kernels this library has launched in this process since load (all contexts) */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "b2_sched_poll": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int]),
     "b2_sched_flush": (c_int, [c_void_p, c_int]),
     "b2_sched_get_stats": (c_int, [c_void_p, c_void_p]),
+    "b2_sched_prebuild": (c_int, [c_void_p, c_int]),
     "b2_dec_create": (c_void_p, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "b2_dec_destroy": (None, [c_void_p]),
     "b2_dec_device_bytes": (c_size_t, [c_void_p]),
@@ -73,6 +74,8 @@ SIGNATURES = {
     "b2_conv1d_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p]),
     "b2_resblock_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_float, c_float, c_float, c_void_p]),
+    "b2_resblock_t_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int)]),
+    "b2_debug_set_stacked_min_taps": (c_int, [c_int]),
     "b2_kernel_launch_count": (c_uint64, []),
     "b2_profile_begin": (c_int, [c_void_p]),
     "b2_profile_end": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint64)]),

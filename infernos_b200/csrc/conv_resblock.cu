@@ -865,6 +865,8 @@ static int launch_rb(const CUtensorMap &tm, const RbParams &p, unsigned grid, si
     return launch_rb_<C, NEW, NMW, 4, false>(tm, p, grid, smem, st, wslot);
 }
 
+int g_rbt_min_taps = 0;
+
 int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     const ResBlockPack &pk = *a.pack;
     if (!pk.tmap || !pk.w) return set_error("resblock: weights were not packed");
@@ -872,9 +874,14 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     if (post && (pk.C != 32 || !a.post_w || !a.post_b || !a.acc_src)) return set_error("resblock: the conv_post epilogue needs C = 32, weights and the MRF partial sum");
     if (!a.x || (!a.out32 && !a.outb && !post)) return set_error("resblock: null input or no output");
     if (a.W <= 0 || a.T <= 0) return 0;
-    // C = 32: the stacked-output kernel (conv_resblock_t.cu).  B2_RB_T=0 keeps this file's time-as-M kernel for A/B runs and the variant tests.
+    // C = 32, five taps and more: the stacked-output kernel (conv_resblock_t.cu).  B2_RB_T=0 keeps this file's time-as-M kernel for A/B runs and
+    // the variant tests; B2_RB_T_MINK sets the smallest tap count that goes to the stacked kernel.  Measured (ncu, 4,096 windows, same run):
+    // k = 11 2.73 vs 3.57 ms, k = 7 1.85 vs 2.01 ms, but k = 3 1.44 vs 1.34 ms -- with three taps half of the stacked MMAs' N range is
+    // structural zeros and the conv epilogues, not the MMAs, set the pace in both kernels.
     static const bool rbt_on = !(getenv("B2_RB_T") && atoi(getenv("B2_RB_T")) == 0);
-    if (rbt_on && pk.tmap_t) return launch_resblock_t(a, st);
+    static const int rbt_mink_env = getenv("B2_RB_T_MINK") ? atoi(getenv("B2_RB_T_MINK")) : 5;
+    const int rbt_mink = g_rbt_min_taps > 0 ? g_rbt_min_taps : rbt_mink_env;          // b2_debug_set_stacked_min_taps (tests) wins over the environment
+    if (rbt_on && pk.tmap_t && pk.taps >= rbt_mink) return launch_resblock_t(a, st);
     RbParams p;
     p.x = a.x; p.acc_src = a.acc_src; p.out32 = a.out32; p.outb = a.outb;
     p.post_w = a.post_w; p.post_b = a.post_b; p.audio = a.audio;

@@ -237,13 +237,18 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // The operand buffers are NOT cleared: every row a valid output reads is written by an epilogue first (rows outside the window as zeros);
+    // guard rows and rows the current mapping does not hold are only ever read on behalf of outputs the halo has already invalidated, and
+    // whatever they contain (NaN bit patterns included) stays in those rows -- an accumulator row depends on its own operand rows only.
+    // tests/test_resblock_t_model.py runs the index-exact model with NaN-filled buffers to pin this.  (-DB2_RBT_ZERO_INIT clears them.)
+#ifdef B2_RBT_ZERO_INIT
     {
-        // both operand buffers start as zeros: guard rows, rows a mapping does not hold, rows outside the window
         const uint32_t a1 = smem_u32(sA1);
         for (uint32_t q = threadIdx.x; q < 2u * kTABytes / 16u; q += 192u)
             asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a1 + q * 16u), "r"(0u) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -316,9 +321,6 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
                 rbt_tmem_st32(tmem_X + tm_lane + (uint32_t)(q * 32), v);
                 rbt_operand_row<false>(a1_u32, rbt_map(4 * m + q, d0, md0, off0, lim0), v, nob, p.slope, ((inside_mask >> q) & 1u) != 0u);
             }
-            // the staging area lay over A2: zero it again (only this warp wrote there)
-            for (uint32_t q = lane; q < 8192u / 16u; q += 32u)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(stg_u32 + q * 16u), "r"(0u) : "memory");
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             rbt_publish(A1_READY, lane);
         }

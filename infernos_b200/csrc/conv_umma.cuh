@@ -50,6 +50,7 @@ int resblock_t_pack(ResBlockPack &out, std::vector<void *> &allocs, size_t &byte
 void resblock_t_free(ResBlockPack &p);
 int resblock_t_plan(int k, const int dil[3], int T, bool post, int &S, int &H, int &V, int &tiles, int off[3], int lim[3]);
 int launch_resblock_t(const ResBlockArgs &a, cudaStream_t st);
+extern int g_rbt_min_taps;          // > 0: smallest tap count launch_resblock hands to the stacked-output kernel (b2_debug_set_stacked_min_taps)
 // builds the TMA descriptor of a layer's bf16 weights; called once from b2_weights_finalize
 int umma_prepare_layer(Layer &l);
 void umma_free_layer(Layer &l);

@@ -98,6 +98,28 @@ int sched_fail(b2_sched *s, const char *what) {
     return 1;
 }
 
+// captures the tail over `b`'s device staging buffers at a padded sub-batch size `nb` and instantiates it (nothing is launched)
+int build_graph(b2_sched *s, Batch *b, int nb) {
+    b2_ctx *c = s->ctx;
+    const bool pn = (s->flags & B2_TAIL_APPLY_POSTNET) != 0;
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    const uint64_t l0 = g_launches.load();
+    B2_CUDA_OK(cudaStreamBeginCapture(s->s_c, cudaStreamCaptureModeRelaxed)      /* relaxed: a kernel's first launch may set its function attributes */);
+    const int rc = tail_device(c, b->d_slots, b->d_mel, nb, s->nframes, s->law, pn, b->d_out, nullptr, s->s_c, false, true);
+    cudaError_t e = cudaStreamEndCapture(s->s_c, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+    if (e != cudaSuccess) return set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    const int nk = (int)(g_launches.load() - l0);          // kernel nodes: counted by the launch wrappers while capturing
+    g_launches.fetch_sub((uint64_t)nk);                    // ... and only charged when the graph actually runs
+    b->graphs.emplace(nb, std::make_pair(ge, nk));
+    s->n_graphs++;
+    return 0;
+}
+
 int enqueue_batch(b2_sched *s, Batch *b) {
     b2_ctx *c = s->ctx;
     const int n = b->n;
@@ -112,21 +134,8 @@ int enqueue_batch(b2_sched *s, Batch *b) {
     if (s->use_graphs && !c->prof.on) {
         auto it = b->graphs.find(nb);
         if (it == b->graphs.end()) {
-            cudaGraph_t g = nullptr;
-            cudaGraphExec_t ge = nullptr;
-            const uint64_t l0 = g_launches.load();
-            B2_CUDA_OK(cudaStreamBeginCapture(s->s_c, cudaStreamCaptureModeRelaxed)      /* relaxed: a kernel's first launch may set its function attributes */);
-            const int rc = tail_device(c, b->d_slots, b->d_mel, nb, s->nframes, s->law, pn, b->d_out, nullptr, s->s_c, false, true);
-            cudaError_t e = cudaStreamEndCapture(s->s_c, &g);
-            if (rc) { if (g) cudaGraphDestroy(g); return 1; }
-            if (e != cudaSuccess) return set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e));
-            e = cudaGraphInstantiate(&ge, g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) return set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
-            const int nk = (int)(g_launches.load() - l0);          // kernel nodes: counted by the launch wrappers while capturing
-            g_launches.fetch_sub((uint64_t)nk);                    // ... and only charged when the graph actually runs
-            it = b->graphs.emplace(nb, std::make_pair(ge, nk)).first;
-            s->n_graphs++;
+            if (build_graph(s, b, nb)) return 1;
+            it = b->graphs.find(nb);
         }
         B2_CUDA_OK(cudaGraphLaunch(it->second.first, s->s_c));
         count_launch(it->second.second);
@@ -419,6 +428,24 @@ int b2_sched_flush(b2_sched *s, int timeout_ms) {
         if (s->cv_poll.wait_until(lk, deadline) == std::cv_status::timeout && !idle()) return set_error("b2_sched_flush: timed out");
     }
     if (!s->async_error.empty()) return set_error("b2_sched_flush: %s", s->async_error.c_str());
+    return 0;
+}
+
+int b2_sched_prebuild(b2_sched *s, int max_sessions) {
+    if (!s) return set_error("null scheduler");
+    if (!s->use_graphs || s->ctx->prof.on) return 0;
+    std::unique_lock<std::mutex> lk(s->mu);
+    if (!((!s->open || s->open->reserved == 0) && s->inflight.empty())) return set_error("b2_sched_prebuild: the scheduler is not idle");
+    if (cudaSetDevice(s->ctx->device) != cudaSuccess) return set_error("b2_sched_prebuild: cudaSetDevice failed");
+    const int top = bucket_of(std::max(1, std::min(max_sessions <= 0 ? s->cap : max_sessions, s->cap)), s->cap);
+    // every staging buffer has its own graphs (they bake the buffer's device pointers in)
+    for (Batch *b : s->pool)
+        for (int n = 1; n <= top;) {
+            const int nb = bucket_of(n, s->cap);
+            if (!b->graphs.count(nb) && build_graph(s, b, nb)) return 1;
+            n = nb + 1;
+        }
+    if (cudaStreamSynchronize(s->s_c) != cudaSuccess) return set_error("b2_sched_prebuild: %s", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
 

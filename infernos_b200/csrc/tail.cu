@@ -942,6 +942,22 @@ int b2_resblock_tc(const float *d_x, const float *h_weights, const float *h_bias
     return rc;
 }
 
+int b2_debug_set_stacked_min_taps(int k) {
+    g_rbt_min_taps = k > 0 ? k : 0;
+    return 0;
+}
+
+int b2_resblock_t_plan(int k, int d0, int d1, int d2, int T, int post, int *out) {
+    if (!out || T < 1) return set_error("b2_resblock_t_plan: bad arguments");
+    const int dil[3] = {d0, d1, d2};
+    if (!resblock_t_supported(32, k, dil)) return set_error("b2_resblock_t_plan: k=%d dilations %d,%d,%d are not covered by the stacked-output kernel", k, d0, d1, d2);
+    int S, H, V, tiles, off[3], lim[3];
+    if (resblock_t_plan(k, dil, T, post != 0, S, H, V, tiles, off, lim)) return 1;
+    out[0] = S; out[1] = H; out[2] = V; out[3] = tiles;
+    for (int i = 0; i < 3; i++) { out[4 + i] = off[i]; out[7 + i] = lim[i]; }
+    return 0;
+}
+
 int b2_session_reset(b2_ctx *c, const int32_t *h_slots, int n, void *stream) {
     CTX_GUARD(c);
     if (!c->finalized) return set_error("b2_weights_finalize has not been called");

@@ -313,6 +313,11 @@ class TailScheduler:
     def flush(self, timeout_ms: int = 60000) -> None:
         _lib.check(self.lib.b2_sched_flush(self.h, int(timeout_ms)), "sched_flush")
 
+    def prebuild(self, max_sessions: int = 0) -> None:
+        """Build the CUDA graphs of every sub-batch bucket up to `max_sessions` (0: up to max_batch) now, while the scheduler is idle, instead of
+        on the serving path the first time a sub-batch of that size turns up."""
+        _lib.check(self.lib.b2_sched_prebuild(self.h, int(max_sessions)), "sched_prebuild")
+
     def stats(self) -> dict:
         st = _SchedStats()
         _lib.check(self.lib.b2_sched_get_stats(self.h, ctypes.byref(st)), "sched_get_stats")

@@ -58,8 +58,21 @@ SHAPES = [
     (3, 3072, 32, 11), (2, 3072, 32, 7), (2, 3072, 32, 3),
     (2, 768, 64, 11), (3, 768, 64, 7), (2, 768, 64, 3),
     (3, 100, 32, 7), (2, 700, 64, 11), (1, 393, 32, 11), (5, 1, 32, 3), (2, 513, 64, 3),
+    (2, 900, 32, 5), (2, 700, 32, 9), (1, 3072, 32, 9),       # tap counts that take the stacked-output kernel's table-driven MMA loop
     (3, 192, 128, 3), (2, 192, 128, 7), (3, 192, 128, 11), (2, 600, 128, 7), (1, 257, 128, 3), (2, 40, 128, 11),
 ]
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _stacked_kernel_for_every_tap_count():
+    """C = 32 shapes go to the stacked-output kernel (conv_resblock_t.cu) from five taps up by default; in this module also the three-tap
+    shapes do, so that both of its MMA issue paths (unrolled k = 3 / 7 / 11, table-driven otherwise) are checked against torch.  The
+    time-as-M kernel's C = 32 path is covered by test_time_as_m_kernel_c32 below and by tests/test_gpu_kernel_variants.py."""
+    from infernos_b200 import _lib
+    lib = _lib.load()
+    lib.b2_debug_set_stacked_min_taps(3)
+    yield
+    lib.b2_debug_set_stacked_min_taps(0)
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -81,6 +94,24 @@ def test_fused_resblock_matches_torch(shape):
     ref_exact = _ref(x, ws, bs, k, dils, 0.1, acc, 3.0, round_ops=False)
     snr_exact = 10 * torch.log10((ref_exact ** 2).sum() / ((out.double() - ref_exact) ** 2).sum()).item()
     assert snr_exact > 40.0, snr_exact
+
+
+@pytest.mark.parametrize("shape", [(2, 3072, 32, 3), (2, 1000, 32, 7), (1, 3072, 32, 11)])
+def test_time_as_m_kernel_c32(shape):
+    """the same check with every C = 32 block on the time-as-M kernel (conv_resblock.cu), which the product keeps for three-tap blocks"""
+    from infernos_b200 import _lib
+    lib = _lib.load()
+    lib.b2_debug_set_stacked_min_taps(99)
+    try:
+        W, T, C, k = shape
+        x, ws, bs, acc = _make(W, T, C, k, seed=sum(shape))
+        out, _ = _run(x, ws, bs, k, (1, 3, 5), 0.1, acc, 3.0)
+        ref = _ref(x, ws, bs, k, (1, 3, 5), 0.1, acc, 3.0)
+        err = (out.double() - ref).abs()
+        snr = 10 * torch.log10((ref ** 2).sum() / (err ** 2).sum().clamp_min(1e-30)).item()
+        assert snr > 60.0 and err.max().item() < 2e-2, (snr, err.max().item())
+    finally:
+        lib.b2_debug_set_stacked_min_taps(3)
 
 
 def test_fused_resblock_output_options():

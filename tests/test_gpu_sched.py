@@ -125,6 +125,40 @@ def test_scheduler_same_session_twice_in_flight_keeps_order(sds):
         tail.close()
 
 
+def test_prebuild_leaves_no_graph_to_build_on_the_serving_path(sds):
+    """b2_sched_prebuild captures every bucket up front: afterwards sub-batches of sizes never seen before launch existing graphs, and the
+    bytes are the plain tail's."""
+    from infernos_b200.engine import TailScheduler, TTSTail
+    S, nframes = 40, 8
+    mel = synth.synth_mel(S, nframes * 2, seed=93)
+    tail = TTSTail("cuda:0", sds[0], sds[1], mode="bf16", max_sessions=S, max_windows=64)
+    try:
+        ref = _reference_bytes(tail, mel, nframes)
+        tail.reset_sessions(list(range(S)))
+        sched = TailScheduler(tail, nframes=nframes, depth=2, max_batch=48)
+        sched.prebuild(0)
+        built = sched.stats()["graphs_built"]
+        assert built >= 6 * 2                                    # buckets 8, 16, .., 48 for at least two staging buffers
+        tail.reset_sessions(list(range(S)))
+        for c, sizes in ((0, (5, 17, 18)), (1, (33, 7))):        # sub-batch sizes in different buckets
+            i = 0
+            for n in sizes:
+                poller = _Poller(sched, n)
+                poller.start()
+                sl = torch.arange(i, i + n, dtype=torch.int32)
+                sched.submit(sl, mel[i:i + n, c * nframes:(c + 1) * nframes].contiguous(), tags=sl.to(torch.int64) * 1000 + c)
+                sched.flush()
+                poller.join(60)
+                assert poller.err is None and poller.n == n
+                for s_ in range(i, i + n):
+                    assert torch.equal(poller.got[s_ * 1000 + c][0][5], ref[s_, c])
+                i += n
+        assert sched.stats()["graphs_built"] == built            # nothing was captured while serving
+        sched.close()
+    finally:
+        tail.close()
+
+
 def test_scheduler_rejects_bad_slots_and_survives_threads(sds):
     from infernos_b200.engine import TailScheduler, TTSTail
     S, nframes = 16, 8
