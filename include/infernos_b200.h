@@ -237,7 +237,8 @@ B2_API int b2_resblock_tc(const float *d_x, const float *h_weights, const float 
                           const float *d_acc, float *d_out32, void *d_outb, float slope, float outb_slope, float div, void *stream);
 
 /* Slab geometry of the stacked-output C = 32 ResBlock kernel (csrc/conv_resblock_t.cu) for a window of T time steps, k taps, dilations
- * d0..d2 (`post` != 0: conv_post fused, three more halo rows).  Host arithmetic only -- no device is touched; exported so that the CPU tests
+ * d0..d2 (`post` bit 0: conv_post fused, three more halo rows; bit 1: the stage's upsampler fused, tiles start on a multiple of four rows).
+ * Host arithmetic only -- no device is touched; exported so that the CPU tests
  * can run the index-exact numpy model of the kernel (tools/resblock_t_model.py) on the library's own plan.
  * out[10] = {S rows per slab, H halo, V output rows per tile, tiles per window, off[0..2], lim[0..2]}: conv1 of pair i reads slab rows
  * [off[i], off[i] + lim[i]) through the operand mapping of dilation d_i.  Returns non-zero (b2_last_error) when the kernel does not cover the shape. */

@@ -867,18 +867,27 @@ static int launch_rb(const CUtensorMap &tm, const RbParams &p, unsigned grid, si
 
 int g_rbt_min_taps = 0;
 
+bool resblock_t_enabled() {
+    static const bool on = !(getenv("B2_RB_T") && atoi(getenv("B2_RB_T")) == 0);
+    return on;
+}
+
 int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     const ResBlockPack &pk = *a.pack;
     if (!pk.tmap || !pk.w) return set_error("resblock: weights were not packed");
     const bool post = a.audio != nullptr;
     if (post && (pk.C != 32 || !a.post_w || !a.post_b || !a.acc_src)) return set_error("resblock: the conv_post epilogue needs C = 32, weights and the MRF partial sum");
-    if (!a.x || (!a.out32 && !a.outb && !post)) return set_error("resblock: null input or no output");
+    if ((!a.x && !a.up_in) || (!a.out32 && !a.outb && !post)) return set_error("resblock: null input or no output");
     if (a.W <= 0 || a.T <= 0) return 0;
+    if (a.up_in) {                  // x = upsampler(up_in) computed in the kernel: the stacked-output kernel only
+        if (!pk.tmap_t) return set_error("resblock: the fused upsampler needs the stacked-output kernel (C = 32)");
+        return launch_resblock_t(a, st);
+    }
     // C = 32, five taps and more: the stacked-output kernel (conv_resblock_t.cu).  B2_RB_T=0 keeps this file's time-as-M kernel for A/B runs and
     // the variant tests; B2_RB_T_MINK sets the smallest tap count that goes to the stacked kernel.  Measured (ncu, 4,096 windows, same run):
     // k = 11 2.73 vs 3.57 ms, k = 7 1.85 vs 2.01 ms, but k = 3 1.44 vs 1.34 ms -- with three taps half of the stacked MMAs' N range is
     // structural zeros and the conv epilogues, not the MMAs, set the pace in both kernels.
-    static const bool rbt_on = !(getenv("B2_RB_T") && atoi(getenv("B2_RB_T")) == 0);
+    const bool rbt_on = resblock_t_enabled();
     static const int rbt_mink_env = getenv("B2_RB_T_MINK") ? atoi(getenv("B2_RB_T_MINK")) : 5;
     const int rbt_mink = g_rbt_min_taps > 0 ? g_rbt_min_taps : rbt_mink_env;          // b2_debug_set_stacked_min_taps (tests) wins over the environment
     if (rbt_on && pk.tmap_t && pk.taps >= rbt_mink) return launch_resblock_t(a, st);

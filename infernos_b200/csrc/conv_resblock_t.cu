@@ -69,6 +69,11 @@ struct RbtParams {
     //   z: accumulator column of the N sub-range | (group to wait for + 1) << 8 | (group to hand back + 1) << 12      w: instruction descriptor
     int nsteps, ngroups;
     uint4 st[6][kTMaxTaps + 4];
+    // UP: the stage's upsampler computed in place of the slab load (x never goes through HBM): its bf16 input [W][up_T][64] (already
+    // leaky-ReLU'd by its producer), up_T = T / 4, and its bias per output channel
+    const __nv_bfloat16 *up_in;
+    int up_T;
+    float up_bias[32];
     float bias1[96];                  // conv1 biases
     float cbias[96];                  // running sums of the conv2 biases
 };
@@ -187,8 +192,13 @@ static constexpr int kRbtDbgEvents = 32, kRbtDbgCtas = 4096;
 
 // EPI: 0 out32 = r;  1 out32 = acc + r;  2 outb = bf16(lrelu((acc + r) / div));  3 out32 = (acc + r) / div;  4 decided at run time;
 // 5 the vocoder's last step fused in: audio = tanh(conv_post(lrelu((acc + r) / div, 0.01))), nothing else written.
-template <int EPI, bool DBG>
-__global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ RbtParams p, unsigned long long *dbg) {
+// UP: x = upsampler(up_in) is computed by this kernel (ConvTranspose1d k8 s4 p2, 64 -> 32 channels, restated as a 3-tap conv with 4 x 32
+// outputs per input time step, tail.cu:pack_convT): output times 4t..4t+3 of input step t are exactly accumulator row m = t - t_base/4 in X's
+// layout, so the upsampler is twelve more MMAs into X (pre-loaded with its bias) on a 17 KB operand instead of a 64 KB fp32 slab load, and
+// the separate upsampler launch with its 1.6 GB round trip through HBM disappears.  Needs t_base = 0 (mod 4): the plan rounds H and V.
+template <int EPI, bool DBG, bool UP>
+__global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_up,
+                                                       const __grid_constant__ RbtParams p, unsigned long long *dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     pdl_trigger();
     constexpr int C = 32;
@@ -214,7 +224,7 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
     if (threadIdx.x == 0) RBT_DBG(0);
 
     // the slab's x rows start their way from HBM into L2 before anything else: one 128-byte line per row
-    if (warp < 4) {
+    if (!UP && warp < 4) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int r = 4 * (int)threadIdx.x + q, t = t_base + r;
@@ -229,6 +239,7 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
         if (lane == 0) {
             if (smem_u32(smem) & 1023u) __trap();
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+            if (UP) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_up) : "memory");
             for (int g = 0; g < kTMaxGrp; g++) { mbar_init(W_FULL(g), 1); mbar_init(W_EMPTY(g), 1); }
             mbar_init(A1_READY, 4); mbar_init(T1_FULL, 1); mbar_init(A2_READY, 4); mbar_init(X_FULL, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -271,64 +282,108 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
         }
         const int sub_r = lane >> 3, c4 = lane & 7;
 
-        // ---- x -> X (TMEM), conv1's bias -> T1, lrelu(x) -> A1 in the first conv's mapping.  Global memory is read coalesced (8 lanes per 128
-        // contiguous bytes of a row, one 32x32 piece ahead) and turned into the lane-owns-a-row order by a per-warp transpose through shared
-        // memory (A2 is free until the first epilogue).  Piece q = rows 4m + q of this warp's 32 accumulator rows.
-        {
-            const uint32_t stg_u32 = a2_u32 + (uint32_t)warp * 8192u;
-            const float *xw = p.x + ((size_t)w * p.T + t_base) * C + c4 * 4;      // row 0 of the slab (may lie before the window: only dereferenced when ok)
-            auto issue_piece = [&](int q) {
-                const uint32_t dst0 = stg_u32 + (uint32_t)((q & 1) * 4096);
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int row = j * 4 + sub_r;                                // staged row == lane that will own it
-                    const int r = 4 * (warp * 32 + row) + q, t = t_base + r;
-                    const bool ok = r < S && t >= 0 && t < p.T;
-                    const float *src = ok ? xw + (ptrdiff_t)r * C : p.x;
-                    cp_async16(dst0 + (uint32_t)(row * 128 + ((c4 ^ (row & 7)) << 4)), src, ok ? 16u : 0u);     // zero-fill outside the window
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            };
-            issue_piece(0);
-            {
-                uint32_t b1[32];
-#pragma unroll
-                for (int c = 0; c < 32; c++) b1[c] = __float_as_uint(p.bias1[c]);
-#pragma unroll
-                for (int q = 0; q < 4; q++) rbt_tmem_st32(tmem_T1 + tm_lane + (uint32_t)(q * 32), b1);
+        if constexpr (UP) {
+            // ---- the upsampler's operand: input steps [t_base/4 - 1, t_base/4 + 129) x 64 channels, [ci/8][row][8 ch] in A2 (rows 16 bytes
+            // apart: its three taps are row offsets 0 / 1 / 2); steps outside the window are the transposed conv's zero padding
+            const int t0 = t_base >> 2;                            // t_base is a multiple of 4 (possibly negative)
+            for (int idx = (int)threadIdx.x; idx < 130 * 8; idx += 128) {
+                const int row = idx >> 3, ch = idx & 7, tin = t0 - 1 + row;
+                const bool ok = tin >= 0 && tin < p.up_T;
+                const __nv_bfloat16 *src = ok ? p.up_in + ((size_t)w * p.up_T + tin) * 64 + ch * 8 : p.up_in;
+                cp_async16(a2_u32 + (uint32_t)((ch * 130 + row) * 16), src, ok ? 16u : 0u);
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            {
+                // X <- the upsampler's bias, T1 <- conv1's bias: both accumulators are pre-loaded, every MMA accumulates
+#pragma unroll 1
+                for (int which = 0; which < 2; which++) {
+                    const float *bsrc = which ? p.bias1 : p.up_bias;
+                    const uint32_t dstc = which ? tmem_T1 : tmem_X;
+                    uint32_t bv[32];
+#pragma unroll
+                    for (int c = 0; c < 32; c++) bv[c] = __float_as_uint(bsrc[c]);
+#pragma unroll 1
+                    for (int q = 0; q < 4; q++) rbt_tmem_st32(dstc + tm_lane + (uint32_t)(q * 32), bv);
+                }
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            rbt_publish(A2_READY, lane);
+            // ---- x (X, after the upsampler's MMAs) -> lrelu -> A1 in the first conv's mapping
             const int d0 = p.dil[0], off0 = p.off[0], lim0 = p.lim[0];
             const unsigned md0 = p.mdiv[0];
             const float nob[32] = {};
+            mbar_wait(X_FULL, 0u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int q = 0; q < 4; q++) {
-                if (q + 1 < 4) {
-                    issue_piece(q + 1);
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");
-                } else {
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                }
-                __syncwarp();
-                uint32_t v[32];
-                {
-                    const uint32_t src0 = stg_u32 + (uint32_t)((q & 1) * 4096) + (uint32_t)(lane * 128);
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
-                                     : "r"(src0 + (uint32_t)((j ^ (lane & 7)) << 4)) : "memory");
-                }
-                __syncwarp();                  // the buffer is refilled two pieces later
-                rbt_tmem_st32(tmem_X + tm_lane + (uint32_t)(q * 32), v);
-                rbt_operand_row<false>(a1_u32, rbt_map(4 * m + q, d0, md0, off0, lim0), v, nob, p.slope, ((inside_mask >> q) & 1u) != 0u);
+                uint32_t acc[32];
+                tmem_ld32(tmem_X + tm_lane + (uint32_t)(q * 32), acc);
+                rbt_operand_row<false>(a1_u32, rbt_map(4 * m + q, d0, md0, off0, lim0), acc, nob, p.slope, ((inside_mask >> q) & 1u) != 0u);
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             rbt_publish(A1_READY, lane);
+        } else {
+        // ---- x -> X (TMEM), conv1's bias -> T1, lrelu(x) -> A1 in the first conv's mapping.  Global memory is read coalesced (8 lanes per 128
+            // contiguous bytes of a row, one 32x32 piece ahead) and turned into the lane-owns-a-row order by a per-warp transpose through shared
+            // memory (A2 is free until the first epilogue).  Piece q = rows 4m + q of this warp's 32 accumulator rows.
+            {
+                const uint32_t stg_u32 = a2_u32 + (uint32_t)warp * 8192u;
+                const float *xw = p.x + ((size_t)w * p.T + t_base) * C + c4 * 4;      // row 0 of the slab (may lie before the window: only dereferenced when ok)
+                auto issue_piece = [&](int q) {
+                    const uint32_t dst0 = stg_u32 + (uint32_t)((q & 1) * 4096);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int row = j * 4 + sub_r;                                // staged row == lane that will own it
+                        const int r = 4 * (warp * 32 + row) + q, t = t_base + r;
+                        const bool ok = r < S && t >= 0 && t < p.T;
+                        const float *src = ok ? xw + (ptrdiff_t)r * C : p.x;
+                        cp_async16(dst0 + (uint32_t)(row * 128 + ((c4 ^ (row & 7)) << 4)), src, ok ? 16u : 0u);     // zero-fill outside the window
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                issue_piece(0);
+                {
+                    uint32_t b1[32];
+#pragma unroll
+                    for (int c = 0; c < 32; c++) b1[c] = __float_as_uint(p.bias1[c]);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) rbt_tmem_st32(tmem_T1 + tm_lane + (uint32_t)(q * 32), b1);
+                }
+                const int d0 = p.dil[0], off0 = p.off[0], lim0 = p.lim[0];
+                const unsigned md0 = p.mdiv[0];
+                const float nob[32] = {};
+#pragma unroll 1
+                for (int q = 0; q < 4; q++) {
+                    if (q + 1 < 4) {
+                        issue_piece(q + 1);
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    } else {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    }
+                    __syncwarp();
+                    uint32_t v[32];
+                    {
+                        const uint32_t src0 = stg_u32 + (uint32_t)((q & 1) * 4096) + (uint32_t)(lane * 128);
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
+                                         : "r"(src0 + (uint32_t)((j ^ (lane & 7)) << 4)) : "memory");
+                    }
+                    __syncwarp();                  // the buffer is refilled two pieces later
+                    rbt_tmem_st32(tmem_X + tm_lane + (uint32_t)(q * 32), v);
+                    rbt_operand_row<false>(a1_u32, rbt_map(4 * m + q, d0, md0, off0, lim0), v, nob, p.slope, ((inside_mask >> q) & 1u) != 0u);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                rbt_publish(A1_READY, lane);
+            }
+            // every warp's staging area lies in rows of A2 that OTHER warps write in epilogue 1: nobody starts it before all are done
+            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        // every warp's staging area lies in rows of A2 that OTHER warps write in epilogue 1: nobody starts it before all are done
-        asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 0) RBT_DBG(2);
 
 #pragma unroll 1
+        // (UP: A2_READY and X_FULL have completed once more -- the upsampler's operand and its MMAs -- so their parities are flipped)
+        constexpr uint32_t xph = UP ? 1u : 0u;
         for (int i = 0; i < 3; i++) {
             const uint32_t par = (uint32_t)(i & 1);
             if (i == 2 && p.acc_src) {
@@ -376,7 +431,7 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
                 float cb[32];
 #pragma unroll
                 for (int c = 0; c < 32; c++) cb[c] = p.cbias[i * 32 + c];
-                mbar_wait(X_FULL, par);
+                mbar_wait(X_FULL, par ^ xph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (threadIdx.x == 0) RBT_DBG(5 + 4 * i);
 #pragma unroll 1
@@ -409,7 +464,7 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
             const int rb0 = r_lo + ((int)threadIdx.x >> 3);
 #pragma unroll
             for (int u = 0; u < kPB; u++) pa[u] = ld_row(rb0 + 16 * u);
-            mbar_wait(X_FULL, 0u);
+            mbar_wait(X_FULL, xph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (threadIdx.x == 0) RBT_DBG(13);
             for (int q = threadIdx.x; q < 7 * 32; q += 128) wp[q] = __ldg(p.post_w + q);
@@ -522,7 +577,7 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
             };
             float4 accA[8], accB[8];
             if (has_acc) ld_acc(0, accA);                 // requested before the last conv2 has finished
-            mbar_wait(X_FULL, 0u);
+            mbar_wait(X_FULL, xph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (threadIdx.x == 0) RBT_DBG(13);
             const float rcp = p.rdiv, nd = -p.div;
@@ -579,6 +634,16 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
         // four slots per box and barrier pair; a conv walks the ring exactly once, so the producer runs up to one conv ahead of the MMA thread
         if (lane == 0) {
             const int k = p.taps, ng = p.ngroups;
+            if constexpr (UP) {
+                // the upsampler's weights first: 3 taps x 2 halves of its 64 input channels, [128 (phase, co)][32 ci] = 8 KB each, two passes over
+                // the three ring groups (an even number of passes: the conv passes keep their parities)
+                for (int b = 0; b < 6; b++) {
+                    const int g = b % kTMaxGrp;
+                    mbar_wait(W_EMPTY(g), (uint32_t)(((b / kTMaxGrp) & 1) ^ 1));
+                    mbar_expect_tx(W_FULL(g), kTGrp * kTTapBytes);
+                    tma_load_3d(smem_u32(sW + (size_t)g * kTGrp * kTTapBytes), &tmap_up, W_FULL(g), (b & 1) * 32, 0, b >> 1);
+                }
+            }
             for (int c = 0; c < 6; c++)
                 for (int g = 0; g < ng; g++) {
                     mbar_wait(W_EMPTY(g), (uint32_t)((c & 1) ^ 1));
@@ -595,6 +660,27 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
             const uint64_t adesc_2 = smem_desc(smem_u32(sA2), (uint32_t)kTChunk16 * 16u, 128u, 0u);
             const uint64_t bdesc0 = smem_desc(smem_u32(sW), 0u, 512u, 4u);        // SWIZZLE_64B: a weight row is 32 bf16
             const int nsteps = p.nsteps, k = p.taps;
+            if constexpr (UP) {
+                // x = upsampler(up_in) into X: tap j of input step t = accumulator row m reads operand row m + j; tap 0 only feeds output phases
+                // 0-1 (columns 0..63), tap 2 phases 2-3 (columns 64..127): N = 64 MMAs there (tail.cu:pack_convT)
+                const uint64_t adesc_u = smem_desc(smem_u32(sA2), 130u * 16u, 128u, 0u);
+                const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+                mbar_wait(A2_READY, 0u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int b = 0; b < 6; b++) {
+                    const int tap = b >> 1, h = b & 1, g = b % kTMaxGrp;
+                    mbar_wait(W_FULL(g), (uint32_t)((b / kTMaxGrp) & 1));
+                    const int col = (tap == 2) ? 64 : 0, nn = (tap == 1) ? 128 : 64;
+                    const uint32_t idesc = idesc0 | ((uint32_t)(nn >> 3) << 17);
+                    const uint64_t bd = bdesc0 + (uint64_t)(uint32_t)(g * (int)((kTGrp * kTTapBytes) >> 4) + col * 4);      // 64 bytes per weight row
+                    const uint64_t ad = adesc_u + (uint64_t)(uint32_t)(4 * h * 130 + tap);
+                    umma_f16(tX + (uint32_t)col, ad, bd, idesc, 1u);
+                    umma_f16(tX + (uint32_t)col, ad + (uint64_t)(uint32_t)(2 * 130), bd + 2ull, idesc, 1u);
+                    umma_commit(W_EMPTY(g));
+                }
+                umma_commit(X_FULL);
+            }
 #pragma unroll 1
             for (int cidx = 0; cidx < 6; cidx++) {
                 const int i = cidx >> 1, cv = cidx & 1;
@@ -602,7 +688,7 @@ __global__ void __launch_bounds__(192, 2) k_resblock_t(const __grid_constant__ C
                 const uint64_t adesc_c = cv ? adesc_2 : adesc_1;
                 const uint32_t acc_base = cv ? tX : tX + 128u;
                 const uint32_t wpar = (uint32_t)cv;                          // conv index 2i + cv: its parity
-                mbar_wait(cv ? A2_READY : A1_READY, (uint32_t)(i & 1));
+                mbar_wait(cv ? A2_READY : A1_READY, (uint32_t)(i & 1) ^ ((UP && cv) ? 1u : 0u));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 RBT_DBG(16 + 2 * cidx);
                 if (k == 11) rbt_issue_conv<11>(adesc_c, bdesc0, acc_base, d, wpar, W_FULL(0), W_EMPTY(0));
@@ -694,7 +780,7 @@ void resblock_t_free(ResBlockPack &p) {
 }
 
 // slab geometry: S rows per slab, halo H, V output rows per tile, and for every pair the row range its conv1 mapping holds
-int resblock_t_plan(int k, const int dil[3], int T, bool post, int &S, int &H, int &V, int &tiles, int off[3], int lim[3]) {
+int resblock_t_plan(int k, const int dil[3], int T, bool post, int &S, int &H, int &V, int &tiles, int off[3], int lim[3], bool align4) {
     const int half = (k - 1) / 2;
     int cap[3], dsum = 0;
     for (int i = 0; i < 3; i++) {
@@ -714,30 +800,32 @@ int resblock_t_plan(int k, const int dil[3], int T, bool post, int &S, int &H, i
         lim[i] = std::min(cap[i], S - off[i]);
         if (off[i] > g[i] || S - off[i] - lim[i] > g[i]) return set_error("resblock_t: no slab geometry for k=%d dil=%d", k, dil[i]);
     }
-    const int vmax = S - 2 * H;
+    if (align4) H = (H + 3) & ~3;          // fused upsampler: a tile starts on an input step (t_base = tile * V - H = 0 mod 4)
+    const int vmax = align4 ? ((S - 2 * H) & ~3) : S - 2 * H;
     if (vmax < 64) return set_error("resblock_t: halo %d leaves no room in a %d-row slab", H, S);
     tiles = cdiv(T, vmax);
     V = cdiv(T, tiles);
+    if (align4) V = (V + 3) & ~3;
     return 0;
 }
 
-static bool g_rbt_attr[64][16] = {};
+static bool g_rbt_attr[64][32] = {};
 static unsigned long long *g_rbt_dbg = nullptr;
 
-template <int EPI, bool DBG>
-static int launch_rbt_(const CUtensorMap &tm, const RbtParams &p, unsigned grid, cudaStream_t st) {
+template <int EPI, bool DBG, bool UP = false>
+static int launch_rbt_(const CUtensorMap &tm, const RbtParams &p, unsigned grid, cudaStream_t st, const CUtensorMap *tm_up = nullptr) {
     int dev = 0;
     B2_CUDA_OK(cudaGetDevice(&dev));
-    const int slot = EPI + (DBG ? 8 : 0);
+    const int slot = EPI + (DBG ? 8 : 0) + (UP ? 16 : 0);
     if (dev < 64 && !g_rbt_attr[dev][slot]) {
-        B2_CUDA_OK(cudaFuncSetAttribute(k_resblock_t<EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTSmemBytes));
+        B2_CUDA_OK(cudaFuncSetAttribute(k_resblock_t<EPI, DBG, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTSmemBytes));
         g_rbt_attr[dev][slot] = true;
     }
     // B2_RBT_ONE_CTA=1 (analysis runs): ask for more shared memory than two CTAs can share, so that a CTA has the SM to itself
     static const bool one_cta = getenv("B2_RBT_ONE_CTA") && atoi(getenv("B2_RBT_ONE_CTA")) != 0;
     const size_t smem = one_cta ? (size_t)120 * 1024 : (size_t)kTSmemBytes;
-    if (one_cta) B2_CUDA_OK(cudaFuncSetAttribute(k_resblock_t<EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2_CUDA_OK(launch_k(k_resblock_t<EPI, DBG>, dim3(grid), dim3(192), smem, st, pdl_enabled(), tm, p, g_rbt_dbg));
+    if (one_cta) B2_CUDA_OK(cudaFuncSetAttribute(k_resblock_t<EPI, DBG, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CUDA_OK(launch_k(k_resblock_t<EPI, DBG, UP>, dim3(grid), dim3(192), smem, st, pdl_enabled(), tm, tm_up ? *tm_up : tm, p, g_rbt_dbg));
     B2_LAUNCH_OK("k_resblock_t");
     return 0;
 }
@@ -753,7 +841,19 @@ int launch_resblock_t(const ResBlockArgs &a, cudaStream_t st) {
     p.W = a.W; p.T = a.T; p.taps = pk.taps;
     for (int i = 0; i < 96; i++) { p.bias1[i] = pk.h_bias1[i]; p.cbias[i] = pk.h_cbias[i]; }
     for (int i = 0; i < 3; i++) { p.dil[i] = pk.dil[i]; p.mdiv[i] = (unsigned)(((1u << 20) + (unsigned)pk.dil[i] - 1u) / (unsigned)pk.dil[i]); }
-    if (resblock_t_plan(pk.taps, pk.dil, a.T, post, p.S, p.H, p.V, p.tiles_per_win, p.off, p.lim)) return 1;
+    const bool up = a.up_in != nullptr;
+    const CUtensorMap *tm_up = nullptr;
+    p.up_in = a.up_in; p.up_T = a.T / 4;
+    for (int i = 0; i < 32; i++) p.up_bias[i] = 0.0f;
+    if (up) {
+        const Layer *ul = a.up_layer;
+        if (!ul || !ul->tmap_q || ul->Cin != 64 || ul->Cout != 128 || ul->taps != 3 || ul->h_bias.size() < 32 || (a.T & 3))
+            return set_error("resblock_t: the fused upsampler needs a packed 64 -> 4 x 32 transposed conv and T = 0 (mod 4)");
+        if (a.x) return set_error("resblock_t: x and up_in are exclusive");
+        tm_up = reinterpret_cast<const CUtensorMap *>(ul->tmap_q);
+        for (int i = 0; i < 32; i++) p.up_bias[i] = ul->h_bias[i];
+    }
+    if (resblock_t_plan(pk.taps, pk.dil, a.T, post, p.S, p.H, p.V, p.tiles_per_win, p.off, p.lim, up)) return 1;
     p.m_tpw = ((1ull << 40) + (unsigned long long)p.tiles_per_win - 1) / (unsigned long long)p.tiles_per_win;
     {
         // extended taps j' = k+2 .. 0: stacked outputs r' in [rlo, rhi] use tap j' - r' = slot k-1-j'+r' (taps are stored in reverse order), so
@@ -790,7 +890,8 @@ int launch_resblock_t(const ResBlockArgs &a, cudaStream_t st) {
     if (dbg_on) {
         if (!g_rbt_dbg) B2_CUDA_OK(cudaMalloc(&g_rbt_dbg, dbg_n * 8));
         B2_CUDA_OK(cudaMemsetAsync(g_rbt_dbg, 0, dbg_n * 8, st));
-        int rc = post ? launch_rbt_<5, true>(tm, p, (unsigned)nct, st) : launch_rbt_<4, true>(tm, p, (unsigned)nct, st);
+        int rc = up ? (post ? launch_rbt_<5, true, true>(tm, p, (unsigned)nct, st, tm_up) : launch_rbt_<4, true, true>(tm, p, (unsigned)nct, st, tm_up))
+                    : (post ? launch_rbt_<5, true>(tm, p, (unsigned)nct, st) : launch_rbt_<4, true>(tm, p, (unsigned)nct, st));
         if (rc) return rc;
         // per-phase averages over the first CTAs of the launch (cycles of the SM clock)
         B2_CUDA_OK(cudaStreamSynchronize(st));
@@ -819,8 +920,15 @@ int launch_resblock_t(const ResBlockArgs &a, cudaStream_t st) {
         }
         return 0;
     }
-    if (post) return launch_rbt_<5, false>(tm, p, (unsigned)nct, st);
     const bool acc = p.acc_src != nullptr, dv = p.div != 1.0f, o32 = p.out32 != nullptr, ob = p.outb != nullptr;
+    if (up) {
+        // the vocoder's three stage-3 launches: store / accumulate / accumulate-average-conv_post; anything else takes the run-time epilogue
+        if (post) return launch_rbt_<5, false, true>(tm, p, (unsigned)nct, st, tm_up);
+        if (!acc && !dv && o32 && !ob) return launch_rbt_<0, false, true>(tm, p, (unsigned)nct, st, tm_up);
+        if (acc && !dv && o32 && !ob) return launch_rbt_<1, false, true>(tm, p, (unsigned)nct, st, tm_up);
+        return launch_rbt_<4, false, true>(tm, p, (unsigned)nct, st, tm_up);
+    }
+    if (post) return launch_rbt_<5, false>(tm, p, (unsigned)nct, st);
     if (!acc && !dv && o32 && !ob) return launch_rbt_<0, false>(tm, p, (unsigned)nct, st);
     if (acc && !dv && o32 && !ob) return launch_rbt_<1, false>(tm, p, (unsigned)nct, st);
     if (acc && dv && !o32 && ob) return launch_rbt_<2, false>(tm, p, (unsigned)nct, st);

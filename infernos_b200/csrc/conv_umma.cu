@@ -714,6 +714,15 @@ int umma_prepare_layer(Layer &l) {
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete tm; return set_error("cuTensorMapEncodeTiled failed with CUresult %d (Cin %d Cout %d taps %d)", (int)r, l.Cin, l.Cout, l.taps); }
     l.tmap = tm;
+    if (l.Cin == 64 && l.Cout == 128 && l.taps == 3) {
+        // upsampler 3 (64 -> 4 x 32): 8 KB boxes of one tap and 32 input channels for the stacked-output ResBlock kernel's weight ring
+        CUtensorMap *tq = new CUtensorMap();
+        cuuint32_t boxq[3] = {32u, 128u, 1u};
+        r = g_encode(tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)l.wbf, gdim, gstr, boxq, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { delete tq; return set_error("cuTensorMapEncodeTiled (upsampler box) failed with CUresult %d", (int)r); }
+        l.tmap_q = tq;
+    }
     if (nt == 256 && l.Cout == 256) {
         // the persistent kernel's 2-CTA multicast mode: the same tensor with a box of half the tile's rows
         CUtensorMap *th = new CUtensorMap();
@@ -729,6 +738,7 @@ int umma_prepare_layer(Layer &l) {
 void umma_free_layer(Layer &l) {
     if (l.tmap) { delete reinterpret_cast<CUtensorMap *>(l.tmap); l.tmap = nullptr; }
     if (l.tmap_half) { delete reinterpret_cast<CUtensorMap *>(l.tmap_half); l.tmap_half = nullptr; }
+    if (l.tmap_q) { delete reinterpret_cast<CUtensorMap *>(l.tmap_q); l.tmap_q = nullptr; }
 }
 
 template <int NT>

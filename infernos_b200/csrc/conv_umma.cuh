@@ -38,6 +38,10 @@ struct ResBlockArgs {
     // C = 32 only: fuse the vocoder's last step, audio[W][T] = tanh(conv_post(lrelu((acc_src + x3) / div, 0.01))); nothing else is written
     const float *post_w = nullptr, *post_b = nullptr;     // device: [7][32], [1]
     float *audio = nullptr;
+    // C = 32, stacked-output kernel only: x is not read but computed -- x = up_layer(up_in), the stage's upsampler (ConvTranspose1d k8 s4,
+    // 64 -> 32 channels, packed by tail.cu:pack_convT), up_in bf16 [W][T/4][64] already leaky-ReLU'd.  x must then be nullptr.
+    const __nv_bfloat16 *up_in = nullptr;
+    const Layer *up_layer = nullptr;
 };
 bool resblock_supported(int C, int taps);
 // gathers the six convolutions' bf16 weights into one TMA-addressable buffer (device allocations are appended to `allocs`)
@@ -48,8 +52,9 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st);
 bool resblock_t_supported(int C, int taps, const int dil[3]);
 int resblock_t_pack(ResBlockPack &out, std::vector<void *> &allocs, size_t &bytes);
 void resblock_t_free(ResBlockPack &p);
-int resblock_t_plan(int k, const int dil[3], int T, bool post, int &S, int &H, int &V, int &tiles, int off[3], int lim[3]);
+int resblock_t_plan(int k, const int dil[3], int T, bool post, int &S, int &H, int &V, int &tiles, int off[3], int lim[3], bool align4 = false);
 int launch_resblock_t(const ResBlockArgs &a, cudaStream_t st);
+bool resblock_t_enabled();          // B2_RB_T != 0
 extern int g_rbt_min_taps;          // > 0: smallest tap count launch_resblock hands to the stacked-output kernel (b2_debug_set_stacked_min_taps)
 // builds the TMA descriptor of a layer's bf16 weights; called once from b2_weights_finalize
 int umma_prepare_layer(Layer &l);

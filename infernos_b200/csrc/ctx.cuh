@@ -20,6 +20,8 @@ struct Layer {
     __nv_bfloat16 *wbf = nullptr;    // [taps][Cout][Cin] bf16, K-major (tensor-core path); nullptr if unused
     void *tmap = nullptr;            // host copy of the CUtensorMap for wbf (tensor-core path)
     void *tmap_half = nullptr;       // same weights, box of half the N tile: each CTA of a 2-CTA cluster fetches one half and multicasts it
+    void *tmap_q = nullptr;          // 64 -> 4 x 32 transposed conv only: box {32 ci, 128 rows, 1 tap}, SWIZZLE_64B (the stacked-output ResBlock kernel computes this upsampler itself)
+    std::vector<float> h_bias;       // host copy of the bias (transposed convs: per (phase, channel))
 };
 
 // the six convolutions of one ResBlock packed for the fused kernel (conv_resblock.cu)

@@ -136,6 +136,7 @@ static int pack_convT(b2_ctx *c, Layer &l, const HostTensor &w, const HostTensor
     std::vector<float> bb((size_t)N);
     for (int ph = 0; ph < 4; ph++)
         for (int co = 0; co < Cout; co++) bb[ph * Cout + co] = b.data[co];
+    l.h_bias = bb;
     if (upload(c, &l.w32, p)) return 1;
     if (upload(c, &l.bias, bb)) return 1;
     if (want_bf16) {
@@ -427,16 +428,25 @@ static int vocoder_bf16(b2_ctx *c, const float *xn, int W, int T, float *audio, 
         static const bool fusion_on = !(getenv("B2_RESBLOCK_FUSION") && atoi(getenv("B2_RESBLOCK_FUSION")) == 0);
         static const bool post_fusion = !(getenv("B2_POST_FUSION") && atoi(getenv("B2_POST_FUSION")) == 0);
         const bool fused = fusion_on && c->rb[i][0].tmap && c->rb[i][1].tmap && c->rb[i][2].tmap;
-        UmmaConvArgs u;
-        u.in = stage_in; u.layer = &c->up[i]; u.out32 = ws.h; u.outb = fused ? nullptr : ws.hb; u.outb_slope = 0.1f; u.W = W; u.T = Tc;
-        PROF(PC_CONV_TC, launch_conv_umma(u, st));
+        // Stage 3: the stacked-output ResBlock kernel computes the stage's upsampler itself (conv_resblock_t.cu, UP): no upsampler launch, and
+        // x (1.6 GB of fp32 at 4,096 windows, read by three launches) never exists in HBM.  Needs all three ResBlocks on that kernel; off with
+        // B2_UP_FUSION=0, with B2_RB_T=0, and while the stage-boundary taps are being recorded (they want x).
+        static const bool up_fusion_on = !(getenv("B2_UP_FUSION") && atoi(getenv("B2_UP_FUSION")) == 0);
+        const bool up_fused = fused && up_fusion_on && i == 3 && resblock_t_enabled() && c->up[i].tmap_q && !c->taps[1 + 2 * i] &&
+                              c->rb[i][0].tmap_t && c->rb[i][1].tmap_t && c->rb[i][2].tmap_t;
+        if (!up_fused) {
+            UmmaConvArgs u;
+            u.in = stage_in; u.layer = &c->up[i]; u.out32 = ws.h; u.outb = fused ? nullptr : ws.hb; u.outb_slope = 0.1f; u.W = W; u.T = Tc;
+            PROF(PC_CONV_TC, launch_conv_umma(u, st));
+        }
         Tc *= 4;
-        if (tap(c, 1 + 2 * i, ws.h, (size_t)W * Tc * STAGE_C[i], st)) return 1;
+        if (!up_fused && tap(c, 1 + 2 * i, ws.h, (size_t)W * Tc * STAGE_C[i], st)) return 1;
         if (fused) {
             // MRF mean (modeling_speecht5.py:3069-3072): s0 = rb0(x); s0 += rb1(x); (s0 + rb2(x)) / 3
             for (int j = 0; j < 3; j++) {
                 ResBlockArgs ra;
                 ra.x = ws.h; ra.pack = &c->rb[i][j]; ra.W = W; ra.T = Tc; ra.slope = 0.1f; ra.outb_slope = 0.1f;
+                if (up_fused) { ra.x = nullptr; ra.up_in = stage_in; ra.up_layer = &c->up[i]; }
                 ra.acc_src = (j > 0) ? ws.s0 : nullptr;
                 if (j < 2) ra.out32 = ws.s0;
                 else {
@@ -952,7 +962,7 @@ int b2_resblock_t_plan(int k, int d0, int d1, int d2, int T, int post, int *out)
     const int dil[3] = {d0, d1, d2};
     if (!resblock_t_supported(32, k, dil)) return set_error("b2_resblock_t_plan: k=%d dilations %d,%d,%d are not covered by the stacked-output kernel", k, d0, d1, d2);
     int S, H, V, tiles, off[3], lim[3];
-    if (resblock_t_plan(k, dil, T, post != 0, S, H, V, tiles, off, lim)) return 1;
+    if (resblock_t_plan(k, dil, T, (post & 1) != 0, S, H, V, tiles, off, lim, (post & 2) != 0)) return 1;
     out[0] = S; out[1] = H; out[2] = V; out[3] = tiles;
     for (int i = 0; i < 3; i++) { out[4 + i] = off[i]; out[7 + i] = lim[i]; }
     return 0;

@@ -12,11 +12,11 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import resblock_t_model as model   # noqa: E402
 
 
-def lib_plan(k, dil, T, post):
+def lib_plan(k, dil, T, post, up=False):
     from infernos_b200 import _lib
     lib = _lib.load()
     out = (ctypes.c_int * 10)()
-    rc = lib.b2_resblock_t_plan(k, dil[0], dil[1], dil[2], T, int(post), out)
+    rc = lib.b2_resblock_t_plan(k, dil[0], dil[1], dil[2], T, int(post) | (2 if up else 0), out)
     if rc:
         return None
     v = list(out)
@@ -38,6 +38,19 @@ def test_library_plan_equals_the_model_plan_and_the_model_equals_conv1d(case):
     assert pl == model.plan(k, dil, T, post)
     assert pl["S"] <= 512 and pl["H"] + pl["V"] <= pl["S"] - pl["H"] and pl["tiles"] * pl["V"] >= T
     err = model.check(k, dil, T, post, seed=sum(dil) + k + T, pl=pl)
+    assert err < 1e-12, err
+
+
+@pytest.mark.parametrize("case", [(3, (1, 3, 5), 3072, False), (7, (1, 3, 5), 1100, False), (11, (1, 3, 5), 1300, True), (11, (1, 3, 5), 392, True),
+                                  (7, (1, 3, 5), 4, False)])
+def test_fused_upsampler_variant_equals_conv_transpose_then_resblock(case):
+    """UP: x = ConvTranspose1d(k8, s4, p2)(stage input) is computed inside the kernel (three taps x two channel halves of MMAs into X, tiles
+    starting on a multiple of four rows) -- the model's restatement on the library's aligned plan against torch.conv_transpose1d + ResBlock"""
+    k, dil, T, post = case
+    pl = lib_plan(k, dil, T, post, up=True)
+    assert pl is not None and pl == model.plan(k, dil, T, post, align4=True)
+    assert pl["H"] % 4 == 0 and pl["V"] % 4 == 0 and pl["H"] + pl["V"] <= pl["S"] - pl["H"] and pl["tiles"] * pl["V"] >= T
+    err = model.check_up(k, dil, T, post, seed=k + T, pl=pl)
     assert err < 1e-12, err
 
 
