@@ -336,7 +336,16 @@ static constexpr int kThreads2 = 320;
 // tile's last load, 2 MMA thread past ACC_EMPTY, 3 ... past A_FULL(kb 0), 4 ... committed the tile, 5 epilogue past ACC_FULL, 6 epilogue done
 #define PDBG(ev) do { if (p.dbg && blockIdx.x < 160 && it < 16) p.dbg[((size_t)blockIdx.x * 16 + it) * 8 + (ev)] = (unsigned long long)clock64(); } while (0)
 
-template <int N_TILE, int MINB>
+// PAIR (N_TILE = 256 only, clusters of two CTAs = the two SMs of a TPC): `tcgen05.mma.cta_group::2`.  The CTAs of a pair work on two consecutive
+// 128-row tiles as ONE M = 256 MMA stream issued by the leader (cluster rank 0): each CTA keeps only ITS half of every weight tile (N rows
+// [128 * rank, +128): 16 KB per stage, so the ring is 7-8 deep in the shared memory that held 4 stages, and each SM fetches half the weight bytes
+// from L2), the tensor core of each SM reads A (4 KB) and half of B (4 KB) per K16 step instead of A + all of B (12 KB) from its own shared memory,
+// and each CTA's 128 accumulator rows land in its own TMEM, so the A producers and the epilogue are untouched.  Hand-offs that cross the pair:
+//   B_FULL   lives in the leader; both CTAs' TMA loads (`.cta_group::2`) count their bytes there
+//   A_FULL   of the leader takes one extra arrival per K block, sent by the peer's (otherwise idle) warp 5 once the peer's rows have landed
+//   B_EMPTY / A_EMPTY / ACC_FULL are signalled in both CTAs by the leader's multicast commits
+//   ACC_EMPTY of the leader counts the epilogue warps of both CTAs
+template <int N_TILE, int MINB, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
                                                                   const UmmaParams2 pp) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -344,7 +353,8 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
     const UmmaParams &p = pp.b;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = p.KB;
-    const uint32_t b_tile_bytes = (uint32_t)N_TILE * KB * 2;
+    constexpr int NBS = PAIR ? 8 : 4;        // barrier slots of the weight ring
+    const uint32_t b_tile_bytes = (uint32_t)(PAIR ? N_TILE / 2 : N_TILE) * KB * 2;
     const uint32_t a_bytes = ((uint32_t)p.R * p.Cin * 2 + 15) & ~15u;
     const int nB = pp.resident ? p.nkb * p.taps : p.stages;
     uint8_t *sB = smem;
@@ -354,24 +364,30 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
     // barrier map: [0,4) b_full  [4,8) b_empty  [8,24) a_full[2][8]  [24,40) a_empty[2][8]  [40,42) acc_full  [42,44) acc_empty
     const uint32_t bar0 = smem_u32(bars);
     auto B_FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
-    auto B_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(4 + s); };
-    auto A_FULL = [&](int buf, int kb) { return bar0 + 8u * (uint32_t)(8 + buf * 8 + kb); };
-    auto A_EMPTY = [&](int buf, int kb) { return bar0 + 8u * (uint32_t)(24 + buf * 8 + kb); };
-    auto ACC_FULL = [&](int a) { return bar0 + 8u * (uint32_t)(40 + a); };
-    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (uint32_t)(42 + a); };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 44);
+    auto B_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(NBS + s); };
+    auto A_FULL = [&](int buf, int kb) { return bar0 + 8u * (uint32_t)(2 * NBS + buf * 8 + kb); };
+    auto A_EMPTY = [&](int buf, int kb) { return bar0 + 8u * (uint32_t)(2 * NBS + 16 + buf * 8 + kb); };
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (uint32_t)(2 * NBS + 32 + a); };
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (uint32_t)(2 * NBS + 34 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NBS + 36);
+    const uint32_t crank = (PAIR || pp.mc) ? cluster_ctarank() : 0u;
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
-        for (int s = 0; s < 4; s++) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), pp.mc ? 2 : 1); }     // multicast: both CTAs' MMAs release a slot
+        for (int s = 0; s < NBS; s++) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), (!PAIR && pp.mc) ? 2 : 1); }     // multicast: both CTAs' MMAs release a slot
         for (int b = 0; b < 2; b++)
-            for (int k = 0; k < 8; k++) { mbar_init(A_FULL(b, k), 128); mbar_init(A_EMPTY(b, k), 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
+            for (int k = 0; k < 8; k++) { mbar_init(A_FULL(b, k), (PAIR && crank == 0) ? 129 : 128); mbar_init(A_EMPTY(b, k), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), PAIR ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * N_TILE)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * N_TILE)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * N_TILE)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(pp.mc ? &tmap_h : &tmap_w) : "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -379,7 +395,6 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
     if (pp.mc) cluster_sync_all();           // the peer's barriers exist before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t crank = pp.mc ? cluster_ctarank() : 0u;
     // everything above overlapped the previous kernel (PDL); the weight producer (warp 4) reads nothing a kernel writes and goes straight on
     if (warp != 4) pdl_wait();
 
@@ -466,7 +481,10 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                         // last read of this accumulator: hand it back to the MMA warp
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
+                        if (lane == 0) {
+                            if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(ACC_EMPTY(acc), 0u));    // the leader's MMA thread waits for both CTAs' epilogues
+                            else mbar_arrive(ACC_EMPTY(acc));
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 8; i++)
@@ -537,7 +555,21 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                     tile_coords(tile, w0, t0, n0);
                     for (int kb = 0; kb < p.nkb; kb++)
                         for (int j = 0; j < p.taps; j++) {
+                            if (p.flags & 32) continue;      // what-if: no weight ring at all (no loads, no barrier traffic)
                             mbar_wait(B_EMPTY(stage), phase ^ 1);
+                            if (p.flags & 16) {      // what-if: no weight traffic at all (the MMAs read whatever the ring holds)
+                                if (!PAIR || crank == 0) mbar_arrive(B_FULL(stage));
+                                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                                continue;
+                            }
+                            if constexpr (PAIR) {
+                                // my half of the tile into MY shared memory; the bytes of both halves are counted on the leader's barrier
+                                if (crank == 0) mbar_expect_tx(B_FULL(stage), 2 * b_tile_bytes);
+                                tma_load_3d_2sm(smem_u32(sB + (size_t)stage * b_tile_bytes), &tmap_h, mapa_u32(B_FULL(stage), 0u), kb * KB,
+                                                n0 + (int)crank * (N_TILE / 2), j);
+                                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                                continue;
+                            }
                             mbar_expect_tx(B_FULL(stage), b_tile_bytes);
                             if (pp.mc)       // my half of the tile, into both CTAs: L2 serves every weight byte once per cluster
                                 tma_load_3d_mc(smem_u32(sB + (size_t)stage * b_tile_bytes) + crank * (b_tile_bytes / 2), &tmap_h, B_FULL(stage),
@@ -553,8 +585,20 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
         // =========================== MMA issuer ===========================
         // the issue loop runs in one elected thread on the uniform datapath: see k_conv_umma
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-        if (elect_one()) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((128u >> 4) << 24);
+        if (PAIR && crank != 0) {
+            // the peer of a pair issues no MMAs: its warp 5 tells the leader when each K block of the PEER's rows has landed
+            if (elect_one()) {
+                for (int it = 0; it < pp.iters; ++it) {
+                    const int abuf = (pp.nA == 2) ? (it & 1) : 0, ause = (pp.nA == 2) ? (it >> 1) : it;
+                    for (int kb = 0; kb < p.nkb; kb++) {
+                        mbar_wait(A_FULL(abuf, kb), (uint32_t)(ause & 1));
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // cp.async writes -> the tensor core's (async proxy) reads
+                        mbar_arrive_cluster(mapa_u32(A_FULL(abuf, kb), 0u));
+                    }
+                }
+            }
+        } else if (elect_one()) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
             const uint32_t b_layout = (KB == 64) ? 2u : 4u;
             const uint64_t adesc0 = smem_desc(smem_u32(sA), (uint32_t)p.R * 16, 128u, 0u);
             const uint64_t bdesc0 = smem_desc(smem_u32(sB), 0u, 8u * (uint32_t)KB * 2, b_layout);
@@ -567,38 +611,46 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
                 if (!pp.mc && tile >= pp.total_tiles) break;
                 const int acc = it & 1, use = it >> 1;
                 const int abuf = (pp.nA == 2) ? (it & 1) : 0, ause = (pp.nA == 2) ? (it >> 1) : it;
-                mbar_wait(ACC_EMPTY(acc), (uint32_t)((use & 1) ^ 1));
+                if constexpr (PAIR) mbar_wait_cluster(ACC_EMPTY(acc), (uint32_t)((use & 1) ^ 1));
+                else mbar_wait(ACC_EMPTY(acc), (uint32_t)((use & 1) ^ 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 PDBG(2);
                 const uint64_t adesc_t = adesc0 + (uint64_t)((uint32_t)abuf * a_buf_16);
                 const uint32_t tmem_acc = tb + (uint32_t)(acc * N_TILE);
                 uint32_t accum = 0;
                 for (int kb = 0; kb < p.nkb; kb++) {
-                    mbar_wait(A_FULL(abuf, kb), (uint32_t)(ause & 1));
+                    if constexpr (PAIR) mbar_wait_cluster(A_FULL(abuf, kb), (uint32_t)(ause & 1));
+                    else mbar_wait(A_FULL(abuf, kb), (uint32_t)(ause & 1));
                     if (kb == 0) PDBG(3);
                     if (!(p.flags & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     for (int j = 0; j < p.taps; j++) {
                         uint64_t bdesc_s;
                         if (pp.resident) bdesc_s = bdesc0 + (uint64_t)((uint32_t)(kb * p.taps + j) * b_tile_16);
                         else {
-                            mbar_wait(B_FULL(stage), phase);
+                            if (!(p.flags & 32)) mbar_wait(B_FULL(stage), phase);
                             bdesc_s = bdesc0 + (uint64_t)((uint32_t)stage * b_tile_16);
                         }
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t a_row = (uint32_t)(kb * (KB / 8) * p.R + j * p.dil);
                         for (int ks = 0; ks < ksteps; ks++) {
-                            if (!(p.flags & 2)) umma_f16(tmem_acc, adesc_t + (uint64_t)(a_row + (uint32_t)(ks * 2 * p.R)), bdesc_s + (uint64_t)(ks * 2), idesc, accum);
+                            if constexpr (PAIR) umma_f16_2cta(tmem_acc, adesc_t + (uint64_t)(a_row + (uint32_t)(ks * 2 * p.R)), bdesc_s + (uint64_t)(ks * 2), idesc, accum);
+                            else if (!(p.flags & 2)) umma_f16(tmem_acc, adesc_t + (uint64_t)(a_row + (uint32_t)(ks * 2 * p.R)), bdesc_s + (uint64_t)(ks * 2), idesc, accum);
                             accum = 1;
                         }
                         if (!pp.resident) {
-                            if (pp.mc) umma_commit_mc(B_EMPTY(stage), (uint16_t)3);
+                            if (p.flags & 32) { if (++stage == p.stages) { stage = 0; phase ^= 1; } continue; }
+                            if constexpr (PAIR) umma_commit_2cta(B_EMPTY(stage), (uint16_t)3);
+                            else if (pp.mc) umma_commit_mc(B_EMPTY(stage), (uint16_t)3);
                             else umma_commit(B_EMPTY(stage));
                             if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         }
                     }
-                    umma_commit(A_EMPTY(abuf, kb));     // this K block of the A buffer may be refilled once these MMAs retire
+                    // this K block of the A buffer may be refilled once these MMAs retire
+                    if constexpr (PAIR) umma_commit_2cta(A_EMPTY(abuf, kb), (uint16_t)3);
+                    else umma_commit(A_EMPTY(abuf, kb));
                 }
-                umma_commit(ACC_FULL(acc));
+                if constexpr (PAIR) umma_commit_2cta(ACC_FULL(acc), (uint16_t)3);
+                else umma_commit(ACC_FULL(acc));
                 PDBG(4);
             }
         }
@@ -649,7 +701,8 @@ __global__ void __launch_bounds__(kThreads2, MINB) k_conv_umma_p(const __grid_co
     __syncthreads();
     if (pp.mc) cluster_sync_all();           // nobody leaves while the peer may still arrive on this CTA's barriers
     if (warp == 5) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * N_TILE)) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * N_TILE)) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * N_TILE)) : "memory");
     }
 }
 
@@ -680,7 +733,7 @@ static int n_tile_for(const Layer &l) {
 
 static int umma_flags() {
     // bit 0: skip the proxy fence; what-if switches for profiling only (results are wrong with them):
-    // bit 1: issue no MMAs, bit 2: epilogue touches no global memory, bit 3: A producer loads nothing
+    // bit 1: issue no MMAs, bit 2: epilogue touches no global memory, bit 3: A producer loads nothing, bit 4: no weight loads, bit 5: no weight ring (neither loads nor its barriers / commits) (persistent kernel)
     static const int f = (getenv("B2_NO_PROXY_FENCE") ? 1 : 0) | (getenv("B2_UMMA_WHATIF") ? atoi(getenv("B2_UMMA_WHATIF")) << 1 : 0);
     return f;
 }
@@ -857,25 +910,26 @@ static int launch_conv_umma_v1(const UmmaConvArgs &a, cudaStream_t st) {
 
 static int g_occ2[64][6] = {};
 
-template <int NT, int MINB>
+template <int NT, int MINB, bool PAIR = false>
 static int launch_nt2(const CUtensorMap &tm, const CUtensorMap *tm_half, UmmaParams2 &p, size_t smem, cudaStream_t st, int slot) {
     int dev = 0;
     B2_CUDA_OK(cudaGetDevice(&dev));
     if (dev >= 64) return set_error("conv_umma: device index too large");
     if (!g_occ2[dev][slot]) {
-        B2_CUDA_OK(cudaFuncSetAttribute(k_conv_umma_p<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B2_CUDA_OK(cudaFuncSetAttribute(k_conv_umma_p<NT, MINB, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         g_occ2[dev][slot] = 1;
     }
     int occ = 0;
-    B2_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_conv_umma_p<NT, MINB>, kThreads2, smem));
+    B2_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_conv_umma_p<NT, MINB, PAIR>, kThreads2, smem));
     occ = std::max(1, std::min(occ, std::min(MINB, 512 / (2 * NT))));
     int grid = std::min(p.total_tiles, sm_count() * occ);
+    if (PAIR) grid = std::min((p.total_tiles + 1) & ~1, (sm_count() * occ) & ~1);      // whole pairs; a tile past the end is a dummy (all rows masked)
     // Experiment (B2_UMMA_MULTICAST=1): weight multicast in 2-CTA clusters for the C=256 ResBlock convs (one N tile, weights streamed:
     // 0.8-2.9 GB of L2 reads per launch otherwise) -- each CTA fetches half of every weight tile and TMA-multicasts it to both.
     // Measured on B200: correct, and NO faster (23.92 vs 23.93 ms per step); a 2-deep instead of 3-deep weight ring costs only 2.6 %
     // as well, so these launches are bound neither by L2 reads nor by weight-fetch latency.  Off by default.
     static const bool mc_on = getenv("B2_UMMA_MULTICAST") && atoi(getenv("B2_UMMA_MULTICAST")) != 0;
-    p.mc = (mc_on && tm_half && p.ntiles == 1 && !p.resident && grid >= 2 && occ == 1) ? 1 : 0;
+    p.mc = PAIR ? 2 : ((mc_on && tm_half && p.ntiles == 1 && !p.resident && grid >= 2 && occ == 1) ? 1 : 0);
     if (p.mc) grid &= ~1;
     p.iters = cdiv(p.total_tiles, grid);
     static const bool pdbg_on = getenv("B2_UMMA_PDBG") != nullptr;
@@ -886,9 +940,7 @@ static int launch_nt2(const CUtensorMap &tm, const CUtensorMap *tm_half, UmmaPar
         cudaMemsetAsync(pdbg_buf, 0, kPdbgWords * 8, st);
         p.b.dbg = pdbg_buf;
     }
-    if (!p.mc) {
-        B2_CUDA_OK(launch_k(k_conv_umma_p<NT, MINB>, dim3(grid), dim3(kThreads2), smem, st, pdl_enabled(), tm, tm, p));
-        B2_LAUNCH_OK("k_conv_umma_p");
+    auto report = [&]() {
         if (pdbg_on) {
             cudaStreamSynchronize(st);
             static std::vector<unsigned long long> h(kPdbgWords);
@@ -915,16 +967,24 @@ static int launch_nt2(const CUtensorMap &tm, const CUtensorMap *tm_half, UmmaPar
                              p.b.N, p.b.Cin, p.b.taps, p.b.dil, p.b.T, p.b.residual != nullptr, p.b.out32 != nullptr, p.b.outb != nullptr, p.nA, p.b.stages, p.resident, p.iters,
                              d[0] / cnt, d[1] / cnt, d[2] / cnt, d[3] / cnt, d[4] / cnt, d[5] / cnt, d[6] / cnt, d[7] / cnt, cnt);
         }
+    };
+    if (!p.mc) {
+        B2_CUDA_OK(launch_k(k_conv_umma_p<NT, MINB, PAIR>, dim3(grid), dim3(kThreads2), smem, st, pdl_enabled(), tm, tm, p));
+        B2_LAUNCH_OK("k_conv_umma_p");
+        report();
         return 0;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads2); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    B2_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma_p<NT, MINB>, tm, *tm_half, (const UmmaParams2)p));
-    B2_LAUNCH_OK("k_conv_umma_p (2-CTA multicast)");
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (PAIR && pdl_enabled()) ? 2 : 1;
+    B2_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_umma_p<NT, MINB, PAIR>, tm, *tm_half, (const UmmaParams2)p));
+    B2_LAUNCH_OK(PAIR ? "k_conv_umma_p (cta_group::2)" : "k_conv_umma_p (2-CTA multicast)");
+    report();
     return 0;
 }
 
@@ -970,15 +1030,32 @@ int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
     pp.rows_per_thr = cdiv(p.R, 128 / cpr);
     if (pp.rows_per_thr > 12) return set_error("conv_umma: halo too large (%d rows)", p.R);
     const size_t a_bytes = ((size_t)p.R * l.Cin * 2 + 15) & ~(size_t)15;
-    const size_t b_tile = (size_t)nt * p.KB * 2;
-    const size_t fixed = kStageBytes + 48 * 8 + 16;
+    // The C = 256 layers (stage 0's 18 ResBlock convs, 4 ms of the step) run as CTA pairs on `tcgen05.mma.cta_group::2` (see k_conv_umma_p, PAIR):
+    // the single-CTA launches ran at the SM's shared-memory bandwidth, not at the tensor pipe's pace -- per k = 11 tile 2.1 MB of operand reads
+    // + 1.4 MB of TMA writes + 0.35 MB of A / epilogue traffic = 30k cycles at 128 B/cycle against 32.4k measured and 22.5k of tensor-pipe time.
+    // B2_UMMA_PAIR=0 keeps the single-CTA kernel.
+    static const bool pair_on = !(getenv("B2_UMMA_PAIR") && atoi(getenv("B2_UMMA_PAIR")) == 0);
+    const bool pair = pair_on && nt == 256 && pp.ntiles == 1 && l.tmap_half && pp.total_tiles >= 2 && p.KB == 64;
+    const size_t b_tile = (size_t)(pair ? nt / 2 : nt) * p.KB * 2;
+    const size_t fixed = kStageBytes + (pair ? 56 : 48) * 8 + 16;
     const size_t budget = 225 * 1024;
     const size_t all_w = (size_t)p.nkb * l.taps * b_tile;
     // weights stay resident when the whole CTA then still fits three to an SM; otherwise they stream through a TMA ring
-    pp.resident = (pp.ntiles == 1 && all_w + 2 * a_bytes + fixed <= 72 * 1024) ? 1 : 0;
+    pp.resident = (!pair && pp.ntiles == 1 && all_w + 2 * a_bytes + fixed <= 72 * 1024) ? 1 : 0;
     size_t b_bytes;
     if (pp.resident) { b_bytes = all_w; p.stages = 0; pp.nA = 2; }
-    else {
+    else if (pair) {
+        // 16 KB per stage and CTA: two A buffers where four stages still fit beside them, else one A buffer; then as deep a ring as fits (at most 8)
+        static const int prefer_na = getenv("B2_UMMA_P_NA") ? atoi(getenv("B2_UMMA_P_NA")) : 0;
+        static const int st_cap = getenv("B2_UMMA_P_STAGES") ? atoi(getenv("B2_UMMA_P_STAGES")) : 8;
+        int stages = 8;
+        pp.nA = 2;
+        if (prefer_na == 1 || (prefer_na == 0 && 4 * b_tile + 2 * a_bytes + fixed > budget)) pp.nA = 1;
+        while (stages > 2 && stages * b_tile + pp.nA * a_bytes + fixed > budget) stages--;
+        stages = std::max(1, std::min(stages, std::min(st_cap, 8)));
+        p.stages = std::min(stages, std::max(1, p.nkb * l.taps));
+        b_bytes = p.stages * b_tile;
+    } else {
         // Streamed weights need a DEEP ring before a second A buffer: an N=256 tile consumes 64 B of weights per cycle, i.e. 4 x 32 KB
         // in flight at ~1 us of L2 latency.  (B2_UMMA_PDBG: with two A buffers and a 2-deep ring the MMA loop of the C=256 layers ran
         // at 1.8x its tensor-pipe time, with one A buffer -- K blocks recycled as their MMAs retire -- and 3-4 stages at 1.4x.)
@@ -1006,7 +1083,9 @@ int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
             if (occ128 >= 2 && smem <= 100 * 1024) return launch_nt2<128, 2>(tm, nullptr, pp, smem, st, 4);
             return launch_nt2<128, 1>(tm, nullptr, pp, smem, st, 2);
         }
-        default: return launch_nt2<256, 1>(tm, th, pp, smem, st, 3);
+        default:
+            if (pair) return launch_nt2<256, 1, true>(tm, th, pp, smem, st, 5);
+            return launch_nt2<256, 1>(tm, th, pp, smem, st, 3);
     }
 }
 

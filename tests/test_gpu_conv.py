@@ -48,6 +48,9 @@ SHAPES = [
     (3, 3072, 32, 32, 11, 5), (2, 768, 64, 64, 7, 3), (3, 192, 128, 128, 3, 1), (5, 48, 256, 256, 11, 5),
     (5, 48, 256, 256, 3, 1), (20, 12, 512, 1024, 3, 1), (3, 48, 256, 512, 3, 1), (2, 192, 128, 256, 3, 1),
     (2, 768, 64, 128, 3, 1), (1, 3072, 32, 32, 3, 1), (2, 20, 256, 256, 7, 1), (1, 300, 64, 64, 11, 3),
+    # C = 256 runs as CTA pairs (cta_group::2): an odd tile count (19: the last pair's second tile is a dummy), and more tiles than CTAs
+    # (310 tiles on 148 CTAs: three passes over the rings, accumulators and A buffers, the last one with 134 dummy tiles)
+    (37, 48, 256, 256, 7, 3), (620, 48, 256, 256, 3, 1), (301, 48, 256, 256, 11, 5),
 ]
 
 

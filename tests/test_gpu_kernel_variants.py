@@ -42,7 +42,8 @@ def _run(tmp_path, name, env):
     ("cluster_multicast_weights", {"B2_UMMA_MULTICAST": "1"}),
     ("time_as_m_stage3", {"B2_RB_T": "0"}),
     ("stacked_outputs_for_k3_too", {"B2_RB_T_MINK": "3", "B2_UP_FUSION": "0"}),
-    ("separate_upsampler3", {"B2_UP_FUSION": "0"}),                        # default: stage 3's upsampler is computed inside its ResBlock launches                                   # round 2: the default stage-3 kernel stacks four outputs into N (conv_resblock_t.cu)
+    ("separate_upsampler3", {"B2_UP_FUSION": "0"}),                        # default: stage 3's upsampler is computed inside its ResBlock launches
+    ("single_cta_stage0", {"B2_UMMA_PAIR": "0"}),                          # default: the C = 256 layers run as CTA pairs on tcgen05.mma.cta_group::2 (conv_umma.cu, PAIR)
     ("eight_epilogue_warps_c32", {"B2_RB32_NEW": "8", "B2_RB_T": "0"}),
     ("lookahead_slab_prefetch", {"B2_RB_PFDIST": "-1"}),
     ("paired_conv_epilogue", {"B2_RB_PAIR": "1"}),
