@@ -47,7 +47,7 @@ def load_peaks():
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/): measured under the
     profiler at a smaller session count, scaled per window; {} when the summary is absent."""
-    for name in ("r2z_resblock_traffic.json", "r2_resblock_traffic.json", "r1_resblock_traffic.json"):          # the newest capture that is committed
+    for name in ("r3_resblock_traffic.json", "r2z_resblock_traffic.json", "r2_resblock_traffic.json", "r1_resblock_traffic.json"):          # the newest capture that is committed
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 d = json.load(f)
@@ -458,21 +458,22 @@ def main_b200(args, rank, local_rank, world):
         rb_ms, rb_n = ms_cls["resblock_tc"], n_cls["resblock_tc"]
         tf = 3 * FLOP_PER_WINDOW_RESBLOCK_STAGE * W_step * psteps / (rb_ms / 1e3) / 1e12
         roofline = {"bound": "tensor", "kernel": "k_resblock<C> / k_resblock_t (fused tcgen05 ResBlock: six convolutions per launch, residual stream in TMEM; "
-                                                 "stages C=128/64/32, 9 launches per sub-batch; the stage-3 k=7 / k=11 launches stack four output "
-                                                 "time steps into the MMA's N dimension)",
+                                                 "stages C=128/64/32, 9 launches per sub-batch; the three stage-3 launches stack four output "
+                                                 "time steps into the MMA's N dimension and compute the stage's upsampler themselves -- its FLOPs, "
+                                                 "done three times, are not counted here)",
                     "achieved": round(tf, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(tf / peaks["tf_sustained"], 4),
                     "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
                     "traffic": traffic.get("k_resblock_bytes_per_launch"), "traffic_note": traffic.get("note"), "traffic_file": traffic.get("file"),
                     "flop_per_launch": round(3 * FLOP_PER_WINDOW_RESBLOCK_STAGE * W_step * psteps / rb_n),
                     "launches": rb_n, "avg_launch_ms": round(rb_ms / max(rb_n, 1), 4), "share_of_step": round(rb_ms / step_ms, 4),
                     "note": "M128xN32/N64 MMAs cap at 40 % / 67 % of the tensor peak (operand fetch from shared memory: 32 + N/4 cycles "
-                            "per K=16 step, tools/mma_rate.cu) -- the time-as-M kernel's bound at C=32/64; the stacked-output kernel (C=32, k>=5) "
+                            "per K=16 step, tools/mma_rate.cu) -- the time-as-M kernel's bound at C=32/64; the stacked-output kernel (C=32) "
                             "issues N=128 MMAs at the full rate but spends (k+3)/k of the useful cycles; halo rows and structural-zero columns "
                             "are not counted as work"}
     if tc_ms > 0:
         tf = FLOP_PER_WINDOW_TC * W_step * psteps / (tc_ms / 1e3) / 1e12
-        fam = {"bound": "tensor", "kernel": "all tcgen05 kernels (k_resblock + per-layer k_conv_umma / k_conv_umma_p: conv_pre, upsamplers, stage-0 ResBlock "
-                                            "convs, chunker convs)" if bf else "k_conv_simt",
+        fam = {"bound": "tensor", "kernel": "all tcgen05 kernels (k_resblock / k_resblock_t + per-layer k_conv_umma / k_conv_umma_p: conv_pre, upsamplers 0-2, "
+                                            "stage-0 ResBlock convs as CTA pairs on tcgen05.mma.cta_group::2, chunker convs)" if bf else "k_conv_simt",
                "achieved": round(tf, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(tf / peaks["tf_sustained"], 4),
                "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)", "traffic": None,
                "launches": tc_n, "avg_launch_ms": round(tc_ms / max(tc_n, 1), 4), "share_of_step": round(tc_ms / step_ms, 4)}

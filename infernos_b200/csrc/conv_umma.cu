@@ -1035,7 +1035,7 @@ int launch_conv_umma(const UmmaConvArgs &a, cudaStream_t st) {
     // + 1.4 MB of TMA writes + 0.35 MB of A / epilogue traffic = 30k cycles at 128 B/cycle against 32.4k measured and 22.5k of tensor-pipe time.
     // B2_UMMA_PAIR=0 keeps the single-CTA kernel.
     static const bool pair_on = !(getenv("B2_UMMA_PAIR") && atoi(getenv("B2_UMMA_PAIR")) == 0);
-    const bool pair = pair_on && nt == 256 && pp.ntiles == 1 && l.tmap_half && pp.total_tiles >= 2 && p.KB == 64;
+    const bool pair = pair_on && nt == 256 && pp.ntiles == 1 && l.tmap_half && pp.total_tiles >= 2 && p.KB == 64 && l.Cin >= 256;    // not upsampler 2 (128 -> 256: 0.38 vs 0.35 ms as a pair, launch list r3)
     const size_t b_tile = (size_t)(pair ? nt / 2 : nt) * p.KB * 2;
     const size_t fixed = kStageBytes + (pair ? 56 : 48) * 8 + 16;
     const size_t budget = 225 * 1024;
