@@ -62,7 +62,8 @@ struct RbParams {
     int dil0, dil1, dil2;
     unsigned long long m_tpw;
     unsigned long long *dbg;   // optional per-CTA phase timestamps (B2_RB_DBG analysis runs)
-    int dbg_flags;             // bit 0: no L2 prefetch of the slab at CTA start (B2_RB_NOPF=1: A/B switch)
+    int dbg_flags;             // bit 0: no L2 prefetch of the slab at CTA start (B2_RB_NOPF=1: A/B switch); bit 1: what-if, timing only (B2_RB_NORING=1): no weight
+                               // ring at all -- no TMA loads, no full / empty barrier traffic, the MMAs read whatever the ring area holds
     int pf_dist;               // > 0: also prefetch the slab of CTA blockIdx.x + pf_dist into L2 (the CTA that follows this one on the SM)
     float bias1[3 * kRbMaxC];  // conv1 biases                                         (constant bank: uniform loads)
     float cbias[3 * kRbMaxC];  // running sum of conv2 biases: cbias[i] = b2[0] + .. + b2[i]
@@ -648,6 +649,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
             for (int c = 0; c < 6; c++)
                 for (int g = 0; g < p.ngroups; g++)
                     for (int kb = 0; kb < NKB; kb++) {
+                        if (p.dbg_flags & 2) continue;
                         mbar_wait(W_EMPTY(slot), phase ^ 1);
                         mbar_expect_tx(W_FULL(slot), slot_bytes);
                         tma_load_3d(smem_u32(sW + (size_t)slot * slot_bytes), &tmap_w, W_FULL(slot), kb * KB, 0, c * p.taps + g * p.tps);
@@ -690,7 +692,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                         const int ntap = min(p.tps, p.taps - j0);
 #pragma unroll 1
                         for (int kb = 0; kb < NKB; kb++) {
-                            mbar_wait(W_FULL(slot), phase);
+                            if (!(p.dbg_flags & 2)) mbar_wait(W_FULL(slot), phase);
                             const uint64_t bdesc_g = bdesc0 + (uint64_t)((uint32_t)slot * slot_16);
                             const bool first = (g == 0) && (kb == 0), last = (g == p.ngroups - 1) && (kb == NKB - 1);
 #pragma unroll 1
@@ -720,7 +722,7 @@ __global__ void __launch_bounds__((NEW + 1 + NMW) * 32) __maxnreg__((C == 32) ? 
                                 }
                                 if (last) umma_commit(done0 + 8u * (uint32_t)s);
                             }
-                            umma_commit(W_EMPTY(slot));
+                            if (!(p.dbg_flags & 2)) umma_commit(W_EMPTY(slot));
                             if (++slot == p.nslots) { slot = 0; phase ^= 1; }
                         }
                     }
@@ -928,7 +930,8 @@ int launch_resblock(const ResBlockArgs &a, cudaStream_t st) {
     if (dbg_on && !dbg_buf) B2_CUDA_OK(cudaMalloc(&dbg_buf, dbg_n * 8));
     p.dbg = dbg_on ? dbg_buf : nullptr;
     static const int nopf = getenv("B2_RB_NOPF") ? atoi(getenv("B2_RB_NOPF")) : 0;
-    p.dbg_flags = nopf ? 1 : 0;
+    static const int noring = getenv("B2_RB_NORING") ? atoi(getenv("B2_RB_NORING")) : 0;
+    p.dbg_flags = (nopf ? 1 : 0) | (noring ? 2 : 0);
     // look-ahead prefetch distance in CTAs (B2_RB_PFDIST=-1: one resident set, i.e. two CTAs per SM at C = 32, one otherwise).  Measured on the
     // B200 (profiles/r2f_ab_lookahead_prefetch.json): no gain (nine ResBlock launches 15.67 ms with it, 15.41 ms without) -- the CTA's own
     // prefetch at its start already hides the HBM latency behind the co-resident CTA.  Off by default.
