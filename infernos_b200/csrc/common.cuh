@@ -40,7 +40,17 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 // Without the attribute both instructions are no-ops, so every kernel can carry them.  B2_PDL=0 launches everything the plain way.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// A kernel launched with the attribute is RESIDENT while its predecessor still runs: nothing a predecessor writes may be read before
+// griddepcontrol.wait returns.  The compiler does not know that -- a load through a `const __restrict__` parameter is an ld.global.nc of memory it takes to
+// be immutable for the kernel's lifetime, and nvcc did hoist one above the wait (k_attend's rowslot[m], read a pass too early: a 2.8 dB loss in
+// tests/test_gpu_decoder.py the day the kernel body changed).  So pdl_wait(p, q, ...) passes every pointer it is given through an empty asm AFTER the
+// wait: loads through them depend on that asm's output and cannot be scheduled above it.  Hand it every pointer to data another kernel produces;
+// tests/test_host_api.py scans the SASS of the library for global loads ahead of the wait.
+template <typename P> __device__ __forceinline__ void pdl_fresh(P &p) { asm volatile("" : "+l"(p) : : "memory"); }
+template <typename... P> __device__ __forceinline__ void pdl_wait(P &...p) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    (pdl_fresh(p), ...);
+}
 #endif
 bool pdl_enabled();
 

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) k_build_windows(const int32_t *__restrict
                                                       int B, int nframes, int max_sessions, unsigned *__restrict__ claim, unsigned epoch,
                                                       int *__restrict__ err_flag) {
     pdl_trigger();
-    pdl_wait();
+    pdl_wait(slots, mel, pre_pool);
     const int nwin = nframes / 8;
     __shared__ int s_ok;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(192) k_chunker_pre(const float *__restrict__ m
 // 0 (ci < 384) -- the two raw `.view` reinterpretations of HelloSippyRT.py:221-224 side by side as one channels-last bf16 tensor [W][12][384].
 __global__ void __launch_bounds__(384) k_chunker_in(const float *__restrict__ mel, const float *__restrict__ audio, __nv_bfloat16 *__restrict__ inb, int W) {
     pdl_trigger();
-    pdl_wait();
+    pdl_wait(mel, audio);
     const int ci = threadIdx.x;
     for (int w = blockIdx.x; w < W; w += gridDim.x) {
         float v[12];
@@ -417,7 +417,7 @@ int launch_chunker_pre(const float *mel, const float *audio, const float *wm, co
 
 __global__ void __launch_bounds__(256) k_chunker_final(const float *__restrict__ audio, const float *__restrict__ post, float *__restrict__ out, long long n) {
     pdl_trigger();
-    pdl_wait();
+    pdl_wait(audio, post);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         const long long w = e >> 11;

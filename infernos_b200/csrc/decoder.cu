@@ -179,7 +179,7 @@ __global__ void k_dec_gather(const int32_t *__restrict__ slots, const float *__r
                              float *__restrict__ x0, __nv_bfloat16 *__restrict__ x0b, int32_t *__restrict__ rowpos, int32_t *__restrict__ rowslot,
                              int max_sessions, int max_steps, int *__restrict__ err) {
     pdl_trigger();
-    pdl_wait();
+    pdl_wait(slots, last, step);
     const int m = blockIdx.x, c = threadIdx.x;            // 128 threads
     if (m >= M) return;
     int sl = slots[m];
@@ -197,7 +197,7 @@ __global__ void k_dec_gather(const int32_t *__restrict__ slots, const float *__r
 // fp32 mode: x = act(x) * colscale[col], in place (the bf16 GEMM does this in its epilogue)
 __global__ void k_act_scale(float *__restrict__ x, const float *__restrict__ colscale, size_t n, int N, int act) {
     pdl_trigger();
-    pdl_wait();
+    pdl_wait(x, colscale);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float v = x[i];
@@ -213,7 +213,7 @@ template <bool BF>
 __global__ void k_pos_cat(const float *__restrict__ fin, const float *__restrict__ pe, const float *__restrict__ alpha, const int32_t *__restrict__ rowpos,
                           const int32_t *__restrict__ slots, const float *__restrict__ spk, int M, float *__restrict__ cat, __nv_bfloat16 *__restrict__ catb) {
     pdl_trigger();
-    pdl_wait();
+    pdl_wait(fin, rowpos, slots, spk);
     const int m = blockIdx.x;
     if (m >= M) return;
     const int pos = rowpos[m], sl = slots[m];
@@ -262,6 +262,32 @@ __device__ __forceinline__ void ld_kv8(const __nv_bfloat16 *p, float (&v)[8]) {
     }
 }
 
+// the same piece held as loaded (bf16: four registers instead of eight) until it is used
+struct Raw8f { float4 a, b; };
+__device__ __forceinline__ void ld_raw8(const float *p, Raw8f &r) { r.a = *reinterpret_cast<const float4 *>(p); r.b = *reinterpret_cast<const float4 *>(p + 4); }
+__device__ __forceinline__ void ld_raw8(const __nv_bfloat16 *p, uint4 &r) { r = *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ void cvt_raw8(const Raw8f &r, float (&v)[8]) { v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w; }
+__device__ __forceinline__ void cvt_raw8(const uint4 &u, float (&v)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+#ifndef B2_ATT_U
+#define B2_ATT_U 4
+#endif
+#ifndef B2_ATT_UQ
+#define B2_ATT_UQ B2_ATT_U
+#endif
+#ifndef B2_ATT_UP
+#define B2_ATT_UP B2_ATT_U
+#endif
+constexpr int kAttUQ = B2_ATT_UQ, kAttUP = B2_ATT_UP;            // cached positions per 8-lane group and trip (loads in flight per lane): scores, context
+template <typename KV> struct RawOf { typedef Raw8f type; };
+template <> struct RawOf<__nv_bfloat16> { typedef uint4 type; };
+
 // One query position against a cached sequence, one CTA (128 threads) per (row, head)  (SpeechT5Attention.forward, :872-986; the 1/sqrt(64)
 // scaling is folded into the q projection at pack time).  SELF: the row's new key / value (columns 768.. / 1536.. of qkv) are appended to
 // the slot's cache at its step first, and the sequence is steps 0 .. step; otherwise keys / values are the sentence's cross-attention cache
@@ -274,7 +300,7 @@ __global__ void __launch_bounds__(128) k_attend(const float *__restrict__ q, int
                                                const int32_t *__restrict__ enc_len, KV *__restrict__ cache, size_t slot_stride, size_t pos_stride,
                                                size_t layer_off, float *__restrict__ ctx32, __nv_bfloat16 *__restrict__ ctxb) {
     pdl_trigger();
-    pdl_wait();
+    pdl_wait(q, slots, rowpos, enc_len, cache);
     extern __shared__ float sm[];                      // [T] scores | 64 q | 4 x 64 partial sums | 8 red
     const int m = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31, grp = lane >> 3, c8 = (lane & 7) * 8;
@@ -290,26 +316,47 @@ __global__ void __launch_bounds__(128) k_attend(const float *__restrict__ q, int
             st_kv(dst + H + tid, q[(size_t)m * ldq + 2 * H + h * HD + tid]);
         }
     }
+#ifdef B2_ATT_FENCE
+    __threadfence();
+#endif
     __syncthreads();
     float qv[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) qv[e] = qs[c8 + e];
     float mx = -INFINITY;
-    for (int j0 = warp * 4; j0 < T; j0 += 16) {
-        const int j = j0 + grp;
-        float acc = 0.0f;
-        if (j < T) {
+    // four positions per 8-lane group and trip, all four loads issued before the first is used: with one 16-byte load in flight per lane the
+    // kernel read the cache at 62 % of the HBM peak (ncu, round 2); the arithmetic and its order are unchanged
+    for (int jb = warp * 4; jb < T; jb += 16 * kAttUQ) {
+        typename RawOf<KV>::type raw[kAttUQ];
+#pragma unroll
+        for (int u = 0; u < kAttUQ; u++) {
+            const int j = jb + 16 * u + grp;
+            ld_raw8(base + (size_t)(j < T ? j : 0) * pos_stride + c8, raw[u]);         // a row past the end re-reads row 0 (its score is dropped)
+        }
+        float pd[kAttUQ];
+#pragma unroll
+        for (int u = 0; u < kAttUQ; u++) {
+            const int j = jb + 16 * u + grp;
             float kv[8];
-            ld_kv8(base + (size_t)j * pos_stride + c8, kv);
+            cvt_raw8(raw[u], kv);
+            float acc = 0.0f;
 #pragma unroll
             for (int e = 0; e < 8; e++) acc = fmaf(qv[e], kv[e], acc);
+            pd[u] = (j < T) ? acc : 0.0f;
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        if (j < T) {
-            if ((lane & 7) == 0) sc[j] = acc;
-            mx = fmaxf(mx, acc);
+#pragma unroll
+        for (int u = 0; u < kAttUQ; u++) {
+            pd[u] += __shfl_xor_sync(0xffffffffu, pd[u], 1);
+            pd[u] += __shfl_xor_sync(0xffffffffu, pd[u], 2);
+            pd[u] += __shfl_xor_sync(0xffffffffu, pd[u], 4);
+        }
+#pragma unroll
+        for (int u = 0; u < kAttUQ; u++) {
+            const int j = jb + 16 * u + grp;
+            if (j < T) {
+                if ((lane & 7) == 0) sc[j] = pd[u];
+                mx = fmaxf(mx, pd[u]);
+            }
         }
     }
     mx = block_max(mx, red);                            // (its barriers also publish sc[])
@@ -323,12 +370,21 @@ __global__ void __launch_bounds__(128) k_attend(const float *__restrict__ q, int
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) acc[e] = 0.0f;
-    for (int j = warp * 4 + grp; j < T; j += 16) {
-        float vv[8];
-        ld_kv8(base + (size_t)j * pos_stride + H + c8, vv);
-        const float pj = sc[j];
+    for (int jb = warp * 4 + grp; jb < T; jb += 16 * kAttUP) {
+        typename RawOf<KV>::type raw[kAttUP];
 #pragma unroll
-        for (int e = 0; e < 8; e++) acc[e] = fmaf(pj, vv[e], acc[e]);
+        for (int u = 0; u < kAttUP; u++)
+            if (jb + 16 * u < T) ld_raw8(base + (size_t)(jb + 16 * u) * pos_stride + H + c8, raw[u]);
+#pragma unroll
+        for (int u = 0; u < kAttUP; u++) {
+            if (jb + 16 * u < T) {
+                float vv[8];
+                cvt_raw8(raw[u], vv);
+                const float pj = sc[jb + 16 * u];
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc[e] = fmaf(pj, vv[e], acc[e]);
+            }
+        }
     }
 #pragma unroll
     for (int e = 0; e < 8; e++) {
@@ -351,7 +407,7 @@ __global__ void __launch_bounds__(128) k_attend(const float *__restrict__ q, int
 __global__ void __launch_bounds__(256) k_add_ln(float *__restrict__ h, const float *__restrict__ o, const float *__restrict__ w, const float *__restrict__ b,
                                                __nv_bfloat16 *__restrict__ hb, int M) {
     pdl_trigger();
-    pdl_wait();
+    pdl_wait(h, o);
     __shared__ float red[8];
     const int m = blockIdx.x, tid = threadIdx.x;
     if (m >= M) return;
@@ -376,7 +432,7 @@ __global__ void __launch_bounds__(256) k_add_ln(float *__restrict__ h, const flo
 // after the speaker projection: h = relu(x) as fp32 residual stream + bf16 operand
 __global__ void k_relu_dual(const float *__restrict__ x, float *__restrict__ h, __nv_bfloat16 *__restrict__ hb, size_t n) {
     pdl_trigger();
-    pdl_wait();
+    pdl_wait(x);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float v = fmaxf(x[i], 0.0f);
@@ -389,7 +445,7 @@ __global__ void k_relu_dual(const float *__restrict__ x, float *__restrict__ h, 
 __global__ void k_dec_finish(const float *__restrict__ out, const int32_t *__restrict__ slots, int M, int s, int nsteps,
                              float *__restrict__ mel, float *__restrict__ prob, float *__restrict__ last, int32_t *__restrict__ step, int max_sessions) {
     pdl_trigger();
-    pdl_wait();
+    pdl_wait(out, slots, last, step);
     const int m = blockIdx.x, c = threadIdx.x;           // 192 threads
     if (m >= M) return;
     const int sl = slots[m];
@@ -469,6 +525,8 @@ struct DecLinear {
     __nv_bfloat16 *wbf = nullptr;          // bf16 [N][K]
     CUtensorMap tmB;                       // box 64 x NT over wbf
     int nt = 128;
+    CUtensorMap tmB256;                    // box 64 x 256 over wbf (N % 256 == 0, N >= 2048): 128 x 256 tiles when 128 x 128 ones would not fit one wave
+    bool has256 = false;
 };
 
 struct b2_dec {
@@ -562,6 +620,10 @@ int upload_linear(b2_dec *d, DecLinear &l, int Kp, int Np, const std::vector<flo
         if (dalloc(d, &l.wbf, hb.size(), false)) return 1;
         B2_CUDA_OK(cudaMemcpy(l.wbf, hb.data(), hb.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
         if (make_map(&l.tmB, l.wbf, Np, Kp, l.nt)) return 1;
+        if (l.nt == 128 && Np % 256 == 0) {
+            if (make_map(&l.tmB256, l.wbf, Np, Kp, 256)) return 1;
+            l.has256 = true;
+        }
     } else {
         std::vector<float> t((size_t)Kp * Np);
         for (int n = 0; n < Np; n++)
@@ -603,31 +665,34 @@ int make_tma_2d_bf16(CUtensorMap *tm, const void *ptr, long long rows, int K, lo
     return 0;
 }
 
-static bool g_gemm_attr[64][4] = {};
+static bool g_gemm_attr[64][5] = {};
 
 int launch_gemm_tc(const GemmTcArgs &a, cudaStream_t st) {
     if (a.M <= 0) return 0;
-    if (!a.tmA || !a.tmB || !a.bias || (a.nt != 64 && a.nt != 128) || a.N % a.nt || a.K % 64 || a.K < 64) return set_error("gemm_tc: bad arguments (N %d nt %d K %d)", a.N, a.nt, a.K);
+    if (!a.tmA || !a.tmB || !a.bias || (a.nt != 64 && a.nt != 128 && a.nt != 256) || a.N % a.nt || a.K % 64 || a.K < 64) return set_error("gemm_tc: bad arguments (N %d nt %d K %d)", a.N, a.nt, a.K);
     GemmParams p;
     p.bias = a.bias; p.colscale = a.colscale; p.out32 = a.out32; p.outb = a.outb; p.M = a.M; p.N = a.N; p.K = a.K; p.ldo = a.N; p.act = a.act;
     dim3 grid((unsigned)cdiv(a.M, 128), (unsigned)(a.N / a.nt));
     // ring depth: deep (8 x 24 KB / 6 x 32 KB) when the K loop is long enough to use it, 4 otherwise (B2_GEMM_DEEP=0: always 4)
     static const bool deep_on = !(getenv("B2_GEMM_DEEP") && atoi(getenv("B2_GEMM_DEEP")) == 0);
-    const bool deep = deep_on && a.K >= 512;
+    const bool deep = deep_on && a.K >= 512 && a.nt != 256;             // 128 x 256 tiles: 4 x 48 KB is all the shared memory there is
     const int stages = deep ? (a.nt == 128 ? 6 : 8) : 4;
-    const int slot = (a.nt == 128 ? 1 : 0) + (deep ? 2 : 0);
+    const int slot = a.nt == 256 ? 4 : (a.nt == 128 ? 1 : 0) + (deep ? 2 : 0);
     const size_t smem = (size_t)stages * (128 * 64 * 2 + (size_t)a.nt * 64 * 2) + (2 * stages + 1) * 8 + 16;
     int dev = 0;
     B2_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 64 && !g_gemm_attr[dev][slot]) {
-        if (a.nt == 128) B2_CUDA_OK(deep ? cudaFuncSetAttribute(k_gemm_tc<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        if (a.nt == 256) B2_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else if (a.nt == 128) B2_CUDA_OK(deep ? cudaFuncSetAttribute(k_gemm_tc<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                          : cudaFuncSetAttribute(k_gemm_tc<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else B2_CUDA_OK(deep ? cudaFuncSetAttribute(k_gemm_tc<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                              : cudaFuncSetAttribute(k_gemm_tc<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g_gemm_attr[dev][slot] = true;
     }
     const GemmParams cp = p;
-    if (a.nt == 128) {
+    if (a.nt == 256) {
+        B2_CUDA_OK(launch_k(k_gemm_tc<256, 4>, grid, dim3(192), smem, st, a.pdl, *a.tmA, *a.tmB, cp));
+    } else if (a.nt == 128) {
         if (deep) B2_CUDA_OK(launch_k(k_gemm_tc<128, 6>, grid, dim3(192), smem, st, a.pdl, *a.tmA, *a.tmB, cp));
         else B2_CUDA_OK(launch_k(k_gemm_tc<128, 4>, grid, dim3(192), smem, st, a.pdl, *a.tmA, *a.tmB, cp));
     } else {
@@ -649,6 +714,10 @@ int linear(b2_dec *d, const DecLinear &l, const float *A32, const CUtensorMap *t
     if (d->mode == B2_MODE_BF16) {
         GemmTcArgs g;
         g.tmA = tmA; g.tmB = &l.tmB; g.bias = l.bias; g.colscale = colscale; g.out32 = out32; g.outb = outb; g.M = M; g.N = l.N; g.K = l.K; g.nt = l.nt; g.act = act; g.pdl = d->use_pdl;
+        // One tile per CTA: when the 128 x 128 tiles of a wide layer do not fit one wave (ffn1 at 1,024 rows: 8 x 24 = 192 CTAs on 148 SMs, the second
+        // wave 30 % full: 46 us against 21 us for the 144-CTA qkv GEMM), 128 x 256 tiles do (96 CTAs).  B2_GEMM_NT256=0 keeps 128.
+        static const bool nt256_on = !(getenv("B2_GEMM_NT256") && atoi(getenv("B2_GEMM_NT256")) == 0);
+        if (nt256_on && l.has256 && (long long)cdiv(M, 128) * (l.N / 128) > sm_count()) { g.tmB = &l.tmB256; g.nt = 256; }
         return launch_gemm_tc(g, st);
     }
     ConvArgs a;

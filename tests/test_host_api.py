@@ -132,3 +132,42 @@ def test_g711_audio_chunk_carries_its_payload_past_the_encoder():
             G711ACodec().encode(ch)
         with pytest.raises(RuntimeError):
             G711Codec().encode(AudioChunk(audio, 8000))
+
+
+def test_no_global_load_is_scheduled_ahead_of_the_programmatic_launch_wait():
+    """Kernels launched with programmatic dependent launch are resident while their predecessor still runs; what it writes may only be read after
+    `griddepcontrol.wait` (SASS: ACQBULK).  nvcc treats loads through `const __restrict__` parameters as loads of immutable memory and once hoisted
+    one above the wait (csrc/common.cuh: pdl_wait).  Scan the built library: in every kernel that waits, no LDG / LD / LDGSTS may precede the wait
+    in program order; TMA loads may, in the tcgen05 kernels only (weights: written once at load time, their rings start ahead of the wait by design)."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    so = os.path.join(ROOT, "infernos_b200", "libinfernos_b200.so")
+    if not os.path.exists(cuobjdump) or not os.path.exists(so):
+        pytest.skip("cuobjdump or the built library is not here")
+    sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True, timeout=600).stdout
+    name, waited, pre, waits = None, False, {}, set()
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name, waited = m.group(1), False
+            continue
+        if name is None:
+            continue
+        if "ACQBULK" in line:
+            waited = True
+            waits.add(name)
+        elif not waited:
+            op = re.search(r"\s(LDG|LD|LDGSTS|UTMALDG)[.\s]", line)
+            if op:
+                pre.setdefault(name, []).append(op.group(1))
+    assert len(waits) >= 10, f"only {len(waits)} kernels contain a wait: the scan no longer sees the library's kernels"
+    bad = {}
+    for k in waits:
+        ops = set(pre.get(k, []))
+        if ops - {"UTMALDG"}:
+            bad[k] = sorted(ops)
+        elif "UTMALDG" in ops and not re.search(r"k_conv_umma|k_resblock|k_gemm_tc", k):
+            bad[k] = sorted(ops)
+    assert not bad, f"global loads ahead of griddepcontrol.wait: {bad}"
