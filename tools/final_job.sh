@@ -26,5 +26,5 @@ s=$(stat -c %s gpurun_out/${P}_tail_full.ncu-rep 2>/dev/null || echo 0); if [ "$
 tail -n 2 gpurun_out/ncu1.log gpurun_out/ncu2.log; wc -l gpurun_out/${P}_launches_raw.csv gpurun_out/${P}_tail_full_raw.csv
 # memcheck: the C = 256 pair kernel (per-layer tests) and one whole tail call (fused upsampler, pair kernel inside the step)
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest -q --no-header -x -m gpu \
-  "tests/test_gpu_conv.py::test_tensor_core_conv_matches_torch_on_bf16_operands" "tests/test_gpu_tail.py::test_tail_bf16_snr_and_state" > gpurun_out/${P}_sanitizer_memcheck.log 2>&1
+  "tests/test_gpu_conv.py::test_tensor_core_conv_matches_torch_on_bf16_operands" "tests/test_gpu_tail.py::test_tail_bf16_snr_and_state" "tests/test_gpu_decoder.py::test_decoder_two_calls_continuous_batching_and_sub_passes" > gpurun_out/${P}_sanitizer_memcheck.log 2>&1
 echo "rc=$?" >> gpurun_out/${P}_sanitizer_memcheck.log; tail -n 6 gpurun_out/${P}_sanitizer_memcheck.log
