@@ -331,31 +331,25 @@ __global__ void __launch_bounds__(128) k_attend(const float *__restrict__ q, int
 #pragma unroll
         for (int u = 0; u < kAttUQ; u++) {
             const int j = jb + 16 * u + grp;
-            ld_raw8(base + (size_t)(j < T ? j : 0) * pos_stride + c8, raw[u]);         // a row past the end re-reads row 0 (its score is dropped)
+            if (j < T) ld_raw8(base + (size_t)j * pos_stride + c8, raw[u]);
         }
-        float pd[kAttUQ];
 #pragma unroll
         for (int u = 0; u < kAttUQ; u++) {
+            if (jb + 16 * u >= T) break;                  // warp-uniform: a short sequence costs one position's arithmetic, not four
             const int j = jb + 16 * u + grp;
-            float kv[8];
-            cvt_raw8(raw[u], kv);
             float acc = 0.0f;
-#pragma unroll
-            for (int e = 0; e < 8; e++) acc = fmaf(qv[e], kv[e], acc);
-            pd[u] = (j < T) ? acc : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < kAttUQ; u++) {
-            pd[u] += __shfl_xor_sync(0xffffffffu, pd[u], 1);
-            pd[u] += __shfl_xor_sync(0xffffffffu, pd[u], 2);
-            pd[u] += __shfl_xor_sync(0xffffffffu, pd[u], 4);
-        }
-#pragma unroll
-        for (int u = 0; u < kAttUQ; u++) {
-            const int j = jb + 16 * u + grp;
             if (j < T) {
-                if ((lane & 7) == 0) sc[j] = pd[u];
-                mx = fmaxf(mx, pd[u]);
+                float kv[8];
+                cvt_raw8(raw[u], kv);
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc = fmaf(qv[e], kv[e], acc);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            if (j < T) {
+                if ((lane & 7) == 0) sc[j] = acc;
+                mx = fmaxf(mx, acc);
             }
         }
     }
