@@ -276,7 +276,7 @@ __device__ __forceinline__ void cvt_raw8(const uint4 &u, float (&v)[8]) {
     }
 }
 #ifndef B2_ATT_U
-#define B2_ATT_U 4
+#define B2_ATT_U 2          // measured: 2 positions in flight at 12 CTAs per SM (40 registers) beat 4 at 9 (56 registers): 22.2 vs 23.9 ms per call, same box
 #endif
 #ifndef B2_ATT_UQ
 #define B2_ATT_UQ B2_ATT_U
@@ -295,8 +295,11 @@ template <> struct RawOf<__nv_bfloat16> { typedef uint4 type; };
 // Memory-bound (every cached key and value is read once per step): 8 lanes share one position, each owning 8 of the head's 64 dimensions,
 // so a warp reads four whole 128-byte (bf16) rows per load instruction; scores are reduced over the 8 lanes by shuffles, the value sum is
 // kept per lane and folded over positions at the end.
+#ifndef B2_ATT_MINB
+#define B2_ATT_MINB 12
+#endif
 template <typename KV, bool SELF>
-__global__ void __launch_bounds__(128) k_attend(const float *__restrict__ q, int ldq, const int32_t *__restrict__ slots, const int32_t *__restrict__ rowpos,
+__global__ void __launch_bounds__(128, B2_ATT_MINB) k_attend(const float *__restrict__ q, int ldq, const int32_t *__restrict__ slots, const int32_t *__restrict__ rowpos,
                                                const int32_t *__restrict__ enc_len, KV *__restrict__ cache, size_t slot_stride, size_t pos_stride,
                                                size_t layer_off, float *__restrict__ ctx32, __nv_bfloat16 *__restrict__ ctxb) {
     pdl_trigger();
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(128) k_attend(const float *__restrict__ q, int
 #pragma unroll
     for (int e = 0; e < 8; e++) qv[e] = qs[c8 + e];
     float mx = -INFINITY;
-    // four positions per 8-lane group and trip, all four loads issued before the first is used: with one 16-byte load in flight per lane the
+    // kAttUQ positions per 8-lane group and trip, all their loads issued before the first is used: with one 16-byte load in flight per lane the
     // kernel read the cache at 62 % of the HBM peak (ncu, round 2); the arithmetic and its order are unchanged
     for (int jb = warp * 4; jb < T; jb += 16 * kAttUQ) {
         typename RawOf<KV>::type raw[kAttUQ];
