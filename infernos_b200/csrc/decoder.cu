@@ -319,9 +319,6 @@ __global__ void __launch_bounds__(128, B2_ATT_MINB) k_attend(const float *__rest
             st_kv(dst + H + tid, q[(size_t)m * ldq + 2 * H + h * HD + tid]);
         }
     }
-#ifdef B2_ATT_FENCE
-    __threadfence();
-#endif
     __syncthreads();
     float qv[8];
 #pragma unroll
